@@ -1,0 +1,157 @@
+/*
+ * pinnstep.h -- C ABI of libpinnstep.so, the B200 (sm_100a) PINN loss-step library.
+ *
+ * The reference (giuliamesc/PINNs_Fluid_Dynamics) has no FFI: its training step sits behind
+ * nisaba's Python API and is handed over as Python closures over TensorFlow ops.  This header is
+ * the boundary a maintainer would bind instead; every entry point names the reference code it
+ * replaces (paths relative to the reference repository root).
+ *
+ *   model(x) + every inner gradient(tape, ., x)     Examples/Cavity_Steady/cavity_steady.py:159-188,
+ *                                                   Examples/Cavity_Unsteady/cavity_unsteady.py:169-199
+ *   PDE_MASS / PDE_MOM / dir_loss / neu_loss / PDE  cavity_steady.py:159-200, poiseuille_flow.py:173-209,
+ *                                                   colliding_flow.py:160-184, poisson_misto.py:62-80
+ *   ns.LossMeanSquares (mean of squared roots)      cavity_steady.py:204,212-225
+ *   ns.OptimizationProblem (sum_t w_t L_t, gradient
+ *   w.r.t. model.variables)                         cavity_steady.py:242
+ *
+ * Conventions
+ *   - plain C types only; all pointers named *_dev are DEVICE pointers owned by the caller and
+ *     must stay valid for the lifetime of the plan (point coordinates and rhs arrays) or of the
+ *     call (params / out).
+ *   - every function returns 0 (PINN_OK) or a negative PINN_E_* code; the message of the last
+ *     failure on the calling thread is available from pinn_last_error().  Nothing throws or
+ *     aborts across this boundary.
+ *   - work is enqueued asynchronously on the caller's stream (a cudaStream_t passed as void*);
+ *     pinn_loss_and_grad / pinn_loss do not allocate and do not synchronise, so they can be
+ *     captured in a CUDA graph.
+ *   - a plan is bound to one device and is not thread-safe; one plan per rank.
+ *
+ * Residual model.  Let J[o][c] be the Taylor jet of network output o at a point:
+ *   c = 0               value
+ *   c = 1 + i           d/dx_i              (i = 0..d-1, input column i)
+ *   c = 1 + d           d2/dx_sx^2          (sx = d-2: first spatial column)
+ *   c = 2 + d           d2/dx_sy^2          (sy = d-1: second spatial column)
+ * A loss term evaluates, on every point n of its point set,
+ *   r_n = sum_{o,c} coef[o][c] * J[o][c]
+ *       + conv * ( J[0][0] * J[conv_k][1+sx] + J[1][0] * J[conv_k][1+sy] )
+ *       - rhs_scale * rhs[n]
+ * which covers every closure of the five in-scope scripts (DESIGN.md section 3 lists the
+ * coefficient sets).  The term's loss value is  sum_n r_n^2 / (normalization * n_global)  and the
+ * total loss is  sum_t weight_t * value_t  (cavity_steady.py:212-231, nisaba semantics).
+ */
+#ifndef PINNSTEP_H
+#define PINNSTEP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PINN_VERSION 100 /* 0.1.0 */
+
+#define PINN_MAX_OUT 4   /* network outputs (u, v, p) padded to 4 */
+#define PINN_MAX_CH 6    /* value, d/dt, d/dx, d/dy, d2/dx2, d2/dy2 */
+#define PINN_MAX_DIM 3
+#define PINN_MAX_TERMS_PER_SET 8
+
+enum pinn_status {
+  PINN_OK = 0,
+  PINN_E_INVALID = -1,     /* bad argument / unsupported shape */
+  PINN_E_ALLOC = -2,       /* device or host allocation failed */
+  PINN_E_CUDA = -3,        /* a CUDA runtime call failed */
+  PINN_E_ARCH = -4,        /* device is not sm_100 */
+  PINN_E_NCCL = -5,        /* NCCL missing or a collective failed */
+  PINN_E_STATE = -6        /* call sequence error */
+};
+
+/* tanh MLP of the reference: Sequential([Dense(H,tanh)] * L + [Dense(O)]), cavity_steady.py:205-210.
+ * Parameters are one flat fp32 vector in Keras variable order [K1,b1,...,K_{L+1},b_{L+1}], kernels
+ * row-major [in,out] (y = x @ K + b). */
+typedef struct pinn_mlp_desc {
+  int32_t in_dim;      /* d: 2 (x,y) or 3 (t,x,y) */
+  int32_t width;       /* H */
+  int32_t n_hidden;    /* L */
+  int32_t out_dim;     /* O: 1 (Poisson) or 3 (u,v,p) */
+} pinn_mlp_desc;
+
+/* One loss term = one ns.LossMeanSquares entry of the script's loss table. */
+typedef struct pinn_term_desc {
+  float coef[PINN_MAX_OUT][PINN_MAX_CH]; /* linear part, see header comment */
+  float conv;                            /* coefficient of the convective product */
+  int32_t conv_k;                        /* which velocity component is convected */
+  float rhs_scale;                       /* multiplies rhs[n]; ignored when rhs_dev == NULL */
+  const float* rhs_dev;                  /* [n_local] fp32 or NULL */
+  double weight;                         /* ns.LossMeanSquares(weight=...) */
+  double normalization;                  /* ns.LossMeanSquares(normalization=...) */
+  int64_t n_global;                      /* number of roots of this term over ALL ranks */
+  int32_t train;                         /* 1: contributes to the total loss and gradient;
+                                            0: test loss (forward only, pinn_loss) */
+} pinn_term_desc;
+
+/* One point set = one category of the scripts (PDE / one boundary edge / IC / Vel / Pres / Test). */
+typedef struct pinn_pointset_desc {
+  const float* points_dev;   /* [n_local, d] fp32 row-major */
+  int64_t n_local;           /* rows on this rank (may be 0) */
+  int32_t n_terms;           /* terms evaluated on this set, fused in one pass */
+  int32_t deriv_order;       /* 0: value only; 1: + first derivatives; 2: + d2/dx2, d2/dy2 */
+  pinn_term_desc terms[PINN_MAX_TERMS_PER_SET];
+} pinn_pointset_desc;
+
+typedef struct pinn_plan pinn_plan;
+
+/* Library / device ------------------------------------------------------------------------- */
+int pinn_version(void);
+const char* pinn_last_error(void);
+
+/* Plan ------------------------------------------------------------------------------------- */
+/* Copies all descriptors; allocates the per-CTA partial workspace on `device`.  Term order in the
+ * outputs is set order then term order within the set. */
+int pinn_plan_create(const pinn_mlp_desc* mlp, const pinn_pointset_desc* sets, int32_t n_sets,
+                     int32_t device, pinn_plan** out);
+int pinn_plan_destroy(pinn_plan* plan);
+int64_t pinn_plan_param_count(const pinn_plan* plan);
+int32_t pinn_plan_term_count(const pinn_plan* plan);
+size_t pinn_plan_workspace_bytes(const pinn_plan* plan);
+/* Name of the engine chosen for the plan's networks: "fused_fp32" | "layered_fp32" | "layered_tf32x3". */
+const char* pinn_plan_engine(const pinn_plan* plan);
+/* Kernel launches enqueued by the last pinn_loss_and_grad / pinn_loss call. */
+int32_t pinn_plan_last_launch_count(const pinn_plan* plan);
+/* Replace the rhs array of one term (e.g. re-drawn noise) without rebuilding the plan. */
+int pinn_plan_set_rhs(pinn_plan* plan, int32_t set_index, int32_t term_index, const float* rhs_dev);
+
+/* Hot path --------------------------------------------------------------------------------- */
+/* out_dev: [P + T] fp32.  out[0..P) = d/dtheta of  sum_{t in train} weight_t/(normalization_t*n_global_t) * sum_n r_n^2
+ * over the LOCAL points; out[P + t] = local sum_n r_n^2 of term t (train and test terms alike; test
+ * terms are only filled by pinn_loss).  With every rank's out summed (pinn_allreduce_sum or any SUM
+ * all-reduce) the result is the exact global gradient and the global sums of squares.
+ * Replaces: nisaba's per-epoch  loss = sum_t w_t*LMS_t();  grads = tape.gradient(loss, variables). */
+int pinn_loss_and_grad(pinn_plan* plan, const float* params_dev, float* out_dev, void* stream);
+/* Forward only (no gradient): fills out[P + t] for ALL terms, leaves out[0..P) untouched.
+ * Replaces: the evaluation of `losses_test` at every log point (cavity_steady.py:233-235). */
+int pinn_loss(pinn_plan* plan, const float* params_dev, float* out_dev, void* stream);
+/* Forward-only network evaluation, values only: y[n, o] = model(x)[n, o].
+ * Replaces: model(grid) in the scripts' post-processing (cavity_steady.py:254-268). */
+int pinn_forward(const pinn_mlp_desc* mlp, const float* params_dev, const float* points_dev,
+                 int64_t n, float* y_dev, int32_t device, void* stream);
+
+/* Multi-GPU -------------------------------------------------------------------------------- */
+/* The only cross-GPU dependency of a step is the SUM of the [P+T] vector.  These wrap the NCCL
+ * that is already loaded in the process (dlopen "libnccl.so.2"); a torch.distributed all_reduce on
+ * the same buffer is equivalent. */
+int pinn_nccl_unique_id(void* id128_out);                          /* 128-byte ncclUniqueId */
+int pinn_comm_create(const void* id128, int32_t world, int32_t rank, int32_t device, void** comm_out);
+int pinn_comm_destroy(void* comm);
+int pinn_allreduce_sum(void* comm, float* buf_dev, int64_t count, void* stream);
+
+/* Optimiser helpers on the flat vectors (rows (f) rank 1 of SURVEY.md section 8) ------------ */
+/* Keras Adam: m,v update with bias correction folded in the step size, epsilon outside the sqrt
+ * (tf.keras.optimizers.Adam(learning_rate=1e-2), cavity_steady.py:246). step is 1-based. */
+int pinn_adam_step(float* params_dev, const float* grad_dev, float* m_dev, float* v_dev, int64_t count,
+                   float lr, float beta1, float beta2, float eps, int64_t step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PINNSTEP_H */

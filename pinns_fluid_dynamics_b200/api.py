@@ -1,0 +1,351 @@
+"""nisaba-shaped facade: the names the reference's example scripts call, backed by libpinnstep.so.
+
+    ns.LossMeanSquares(name, eval_roots, weight=1.0, normalization=1.0)   cavity_steady.py:204,212-225
+    ns.Loss(name, eval_loss, normalization, weight, non_negative)          colliding_flow_pressmean.py:196
+    ns.OptimizationProblem(variables, losses, losses_test, callbacks=[])   cavity_steady.py:242
+    ns.minimize(pb, 'keras', optimizer, num_epochs)                        cavity_steady.py:246
+    ns.minimize(pb, 'scipy', 'BFGS' | 'L-BFGS-B', num_epochs)              cavity_steady.py:247, poisson.py:75
+    ns.utils.HistoryPlotCallback / load_json / plot_history, pb.save_history   cavity_steady.py:243-245, poisson.py:81-83
+    ns.config.get_dtype()                                                   poisson.py:47
+
+``eval_roots`` is a declarative ``ResidualForm`` (or a zero-argument callable returning one, so the
+scripts' ``lambda: PDE_MOM(0)`` idiom still reads the same) instead of a TensorFlow closure.
+History bookkeeping follows the saved History_Loss.json files: entries every 10
+iterations of each round plus iteration 0 of the round, ``loss_global = sum_t weight_t*log_t``,
+test losses excluded from the total, rounds named ``keras_<Optimizer>`` / ``scipy_<method>``.
+"""
+from __future__ import annotations
+
+import json
+import math
+from typing import Callable, List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import _capi
+from .engine import CompiledProblem, CudaPlan, assemble_losses, compile_problem
+from .residuals import ResidualForm
+
+LOG_STRIDE = 10
+
+
+class config:
+    @staticmethod
+    def get_dtype():
+        """The reference computes in float64 (Model.json); this build computes in FP32 by design."""
+        return torch.float32
+
+
+# ------------------------------------------------------------------------------------------------
+# model
+# ------------------------------------------------------------------------------------------------
+
+class TanhMLP:
+    """tf.keras.Sequential([Dense(H, tanh)] * L + [Dense(O)]) with GlorotUniform / zeros init
+    (cavity_steady.py:205-210, Model.json).  ``variables`` are views, in Keras order and layout, of
+    one flat FP32 vector -- the vector the kernels and optimisers work on."""
+
+    def __init__(self, dim: int, hidden: Sequence[int], out_dim: int, device=None, seed: Optional[int] = None):
+        if len(set(hidden)) != 1:
+            raise ValueError("all hidden layers must have the same width")
+        self.dim, self.hidden, self.out_dim = int(dim), [int(h) for h in hidden], int(out_dim)
+        sizes = [self.dim] + self.hidden + [self.out_dim]
+        self.shapes = []
+        for i in range(len(sizes) - 1):
+            self.shapes += [(sizes[i], sizes[i + 1]), (sizes[i + 1],)]
+        n = sum(int(np.prod(s)) for s in self.shapes)
+        if device is None:
+            device = "cuda" if torch.cuda.is_available() else "cpu"
+        self.flat = torch.zeros(n, dtype=torch.float32, device=device)
+        self.variables: List[torch.Tensor] = []
+        off = 0
+        for s in self.shapes:
+            k = int(np.prod(s))
+            self.variables.append(self.flat[off:off + k].view(*s))
+            off += k
+        rng = np.random.default_rng(seed)
+        w = []
+        for i in range(len(sizes) - 1):
+            lim = math.sqrt(6.0 / (sizes[i] + sizes[i + 1]))
+            w += [rng.uniform(-lim, lim, size=(sizes[i], sizes[i + 1])), np.zeros(sizes[i + 1])]
+        self.set_weights(w)
+
+    def set_weights(self, arrays) -> None:
+        if len(arrays) != len(self.variables):
+            raise ValueError("wrong number of weight arrays")
+        for v, a in zip(self.variables, arrays):
+            a = torch.as_tensor(np.asarray(a), dtype=torch.float32)
+            if tuple(a.shape) != tuple(v.shape):
+                raise ValueError(f"weight shape {tuple(a.shape)} does not match {tuple(v.shape)}")
+            v.copy_(a)
+
+    def get_weights(self) -> List[np.ndarray]:
+        return [v.detach().cpu().numpy().copy() for v in self.variables]
+
+    def __call__(self, x) -> torch.Tensor:
+        """model(x): values only, [n, O] (post-processing grids, cavity_steady.py:254-268)."""
+        import ctypes as C
+        if not self.flat.is_cuda:
+            raise _capi.PinnLibraryError("model(x) runs on the GPU only (no CPU fallback)")
+        lib = _capi.load()
+        x = torch.as_tensor(x, dtype=torch.float32, device=self.flat.device).contiguous()
+        y = torch.empty(x.shape[0], self.out_dim, dtype=torch.float32, device=self.flat.device)
+        mlp = _capi.MlpDesc(self.dim, self.hidden[0], len(self.hidden), self.out_dim)
+        stream = C.c_void_p(torch.cuda.current_stream(self.flat.device).cuda_stream)
+        _capi.check(lib.pinn_forward(C.byref(mlp), C.c_void_p(self.flat.data_ptr()), C.c_void_p(x.data_ptr()),
+                                     x.shape[0], C.c_void_p(y.data_ptr()), self.flat.device.index or 0, stream),
+                    "pinn_forward")
+        return y
+
+    def to_json(self) -> str:
+        """Architecture record in the shape of Keras' Model.json (cavity_steady.py:250-251)."""
+        layers = [{"class_name": "InputLayer", "config": {"batch_input_shape": [None, self.dim], "dtype": "float32"}}]
+        for i, h in enumerate(self.hidden + [self.out_dim]):
+            act = "tanh" if i < len(self.hidden) else "linear"
+            layers.append({"class_name": "Dense", "config": {
+                "name": f"dense_{i}", "units": h, "activation": act, "use_bias": True, "dtype": "float32",
+                "kernel_initializer": {"class_name": "GlorotUniform", "config": {"seed": None}},
+                "bias_initializer": {"class_name": "Zeros", "config": {}}}})
+        return json.dumps({"class_name": "Sequential", "config": {"name": "sequential", "layers": layers},
+                           "backend": "pinns_fluid_dynamics_b200"})
+
+    def save_weights(self, path: str) -> None:
+        """h5py is unavailable: weights go to ``.npz`` with Keras' dataset names as keys."""
+        names = {}
+        for i in range(len(self.variables) // 2):
+            names[f"dense_{i}/kernel:0"] = self.variables[2 * i].detach().cpu().numpy()
+            names[f"dense_{i}/bias:0"] = self.variables[2 * i + 1].detach().cpu().numpy()
+        np.savez(path, **names)
+
+
+# ------------------------------------------------------------------------------------------------
+# losses
+# ------------------------------------------------------------------------------------------------
+
+class LossMeanSquares:
+    """value = mean(roots**2) / normalization; history fields weight / non_negative / display_sqrt."""
+
+    def __init__(self, name: str, eval_roots: Union[ResidualForm, Callable[[], ResidualForm]],
+                 weight: float = 1.0, normalization: float = 1.0):
+        form = eval_roots() if callable(eval_roots) and not isinstance(eval_roots, ResidualForm) else eval_roots
+        if not isinstance(form, ResidualForm):
+            raise TypeError("eval_roots must be a ResidualForm (see pinns_fluid_dynamics_b200.residuals) "
+                            "or a callable returning one; arbitrary closures cannot be fused into the kernel")
+        self.name, self.form = name, form
+        self.weight, self.normalization = float(weight), float(normalization)
+        self.non_negative, self.display_sqrt = True, True
+
+
+class Loss:
+    """Generic scalar loss (``ns.Loss('PRESS_0', ...)`` of the out-of-scope pressmean variant).  Only
+    mean-square terms are on the fused path; a generic scalar closure is rejected loudly."""
+
+    def __init__(self, name, eval_loss, weight=1.0, normalization=1.0, non_negative=False):
+        raise NotImplementedError(
+            "ns.Loss with an arbitrary scalar closure is outside the fused loss-step path "
+            "(only used by colliding_flow_pressmean.py:196, SURVEY.md row 3b); use LossMeanSquares")
+
+
+# ------------------------------------------------------------------------------------------------
+# problem
+# ------------------------------------------------------------------------------------------------
+
+class OptimizationProblem:
+    def __init__(self, variables, losses, losses_test=None, callbacks=None, *, engine_factory=None,
+                 process_group=None):
+        self.variables = list(variables)
+        self.losses = list(losses)
+        if losses_test is None:
+            losses_test = []
+        elif isinstance(losses_test, LossMeanSquares):
+            losses_test = [losses_test]       # poisson.py:69,72 passes a single loss
+        self.losses_test = list(losses_test)
+        self.callbacks = [] if callbacks is None else callbacks
+        self.flat = self._flat_view(self.variables)
+        self.group = process_group
+        import torch.distributed as dist
+        self._dist = dist if (dist.is_available() and dist.is_initialized()) else None
+        self.rank = self._dist.get_rank(self.group) if self._dist else 0
+        self.world = self._dist.get_world_size(self.group) if self._dist else 1
+        self.compiled: CompiledProblem = compile_problem([tuple(v.shape) for v in self.variables],
+                                                         self.losses, self.losses_test, self.rank, self.world)
+        self.plan = (engine_factory or CudaPlan)(self.compiled)
+        self.iteration = 0
+        self.history = {
+            "log": {"iter": [], "round": [], "iter_round": [], "loss_global": []},
+            "losses": {l.name: {"weight": l.weight, "non_negative": l.non_negative,
+                                "display_sqrt": l.display_sqrt, "log": []} for l in self.losses},
+            "losses_test": {l.name: {"weight": l.weight, "non_negative": l.non_negative,
+                                     "display_sqrt": l.display_sqrt, "log": []} for l in self.losses_test},
+            "log_rounds": {"rounds": [], "iteration_start": []},
+        }
+
+    @staticmethod
+    def _flat_view(variables) -> torch.Tensor:
+        base = variables[0]._base if variables[0]._base is not None else None
+        n = sum(v.numel() for v in variables)
+        if base is not None and base.dim() == 1 and base.numel() == n and base.is_contiguous():
+            off, ok = 0, True
+            for v in variables:
+                ok &= v._base is base and v.storage_offset() == off and v.is_contiguous()
+                off += v.numel()
+            if ok:
+                return base
+        raise ValueError("variables must be the views of one flat FP32 vector in Keras order "
+                         "(use TanhMLP(...).variables)")
+
+    # ---- evaluation ---------------------------------------------------------------------------
+    def _reduce(self, out: torch.Tensor) -> torch.Tensor:
+        if self._dist is not None and self.world > 1:
+            self._dist.all_reduce(out, op=self._dist.ReduceOp.SUM, group=self.group)
+        return out
+
+    def loss_and_grad_device(self):
+        """One training-step evaluation, everything left on the device:
+        returns (grad [P] view, sumsq [T] in table order)."""
+        out = self._reduce(self.plan.loss_and_grad(self.flat))
+        return out[: self.compiled.n_params], self.plan.to_table_order(out)
+
+    def evaluate(self):
+        """(total loss, per-train-term values, flat gradient [P] on device)."""
+        grad, sumsq = self.loss_and_grad_device()
+        total, train_vals, _ = assemble_losses(self.compiled, sumsq.detach().double().cpu().numpy())
+        return total, train_vals, grad
+
+    def evaluate_all(self):
+        """Forward-only values of train and test terms (log points)."""
+        out = self._reduce(self.plan.loss_only(self.flat))
+        sumsq = self.plan.to_table_order(out).detach().double().cpu().numpy()
+        return assemble_losses(self.compiled, sumsq)
+
+    # ---- history ------------------------------------------------------------------------------
+    def begin_round(self, name: str) -> None:
+        h = self.history
+        if h["log"]["iter"]:
+            self.iteration = h["log"]["iter"][-1] + 1     # iteration_start == [0, 101] in the saved runs
+        h["log_rounds"]["rounds"].append(name)
+        h["log_rounds"]["iteration_start"].append(self.iteration)
+        self._iter_round = 0
+
+    def log_state(self) -> float:
+        total, train_vals, test_vals = self.evaluate_all()
+        h = self.history
+        h["log"]["iter"].append(self.iteration)
+        h["log"]["round"].append(len(h["log_rounds"]["rounds"]))
+        h["log"]["iter_round"].append(self._iter_round)
+        h["log"]["loss_global"].append(total)
+        for l, v in zip(self.losses, train_vals):
+            h["losses"][l.name]["log"].append(v)
+        for l, v in zip(self.losses_test, test_vals):
+            h["losses_test"][l.name]["log"].append(v)
+        for cb in self.callbacks:
+            cb(self, self._iter_round)
+        return total
+
+    def step_done(self) -> None:
+        self.iteration += 1
+        self._iter_round += 1
+        if self._iter_round % LOG_STRIDE == 0:
+            self.log_state()
+
+    def save_history(self, path: str) -> None:
+        if self.rank == 0:
+            with open(path, "w") as fh:
+                json.dump(self.history, fh, indent=2)
+
+
+# ------------------------------------------------------------------------------------------------
+# optimisers and minimize
+# ------------------------------------------------------------------------------------------------
+
+class Adam:
+    """tf.keras.optimizers.Adam(learning_rate=1e-2): beta_1 .9, beta_2 .999, epsilon 1e-7 (Keras 2.7
+    defaults), update  theta -= lr*sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v) + eps)."""
+
+    name = "Adam"
+
+    def __init__(self, learning_rate: float = 1e-3, beta_1: float = 0.9, beta_2: float = 0.999, epsilon: float = 1e-7):
+        self.lr, self.b1, self.b2, self.eps = learning_rate, beta_1, beta_2, epsilon
+        self.m = self.v = None
+        self.t = 0
+
+    def apply(self, flat: torch.Tensor, grad: torch.Tensor) -> None:
+        import ctypes as C
+        if self.m is None:
+            self.m, self.v = torch.zeros_like(flat), torch.zeros_like(flat)
+        self.t += 1
+        if flat.is_cuda:
+            lib = _capi.load()
+            stream = C.c_void_p(torch.cuda.current_stream(flat.device).cuda_stream)
+            _capi.check(lib.pinn_adam_step(C.c_void_p(flat.data_ptr()), C.c_void_p(grad.data_ptr()),
+                                           C.c_void_p(self.m.data_ptr()), C.c_void_p(self.v.data_ptr()),
+                                           flat.numel(), self.lr, self.b1, self.b2, self.eps, self.t, stream),
+                        "pinn_adam_step")
+        else:  # host tensors: only reached with an injected (test) engine
+            self.m.mul_(self.b1).add_(grad, alpha=1 - self.b1)
+            self.v.mul_(self.b2).addcmul_(grad, grad, value=1 - self.b2)
+            step = self.lr * math.sqrt(1 - self.b2 ** self.t) / (1 - self.b1 ** self.t)
+            flat.addcdiv_(self.m, self.v.sqrt().add_(self.eps), value=-step)
+
+
+class optimizers:
+    Adam = Adam
+
+
+def minimize(pb: OptimizationProblem, backend: str, optimizer, num_epochs: int) -> None:
+    if backend == "keras":
+        pb.begin_round(f"keras_{getattr(optimizer, 'name', type(optimizer).__name__)}")
+        pb.log_state()
+        for _ in range(num_epochs):
+            grad, _ = pb.loss_and_grad_device()
+            optimizer.apply(pb.flat, grad)
+            pb.step_done()
+    elif backend == "scipy":
+        import scipy.optimize
+        method = str(optimizer)
+        pb.begin_round(f"scipy_{method}")
+        pb.log_state()
+
+        def fun(theta: np.ndarray):
+            pb.flat.copy_(torch.as_tensor(theta, dtype=torch.float32))
+            total, _, grad = pb.evaluate()
+            return float(total), grad.detach().double().cpu().numpy()
+
+        def cb(_theta):
+            pb.step_done()
+
+        x0 = pb.flat.detach().double().cpu().numpy()
+        res = scipy.optimize.minimize(fun, x0, jac=True, method=method, callback=cb,
+                                      options={"maxiter": int(num_epochs)})
+        pb.flat.copy_(torch.as_tensor(res.x, dtype=torch.float32))
+    else:
+        raise ValueError(f"unknown backend {backend!r} (expected 'keras' or 'scipy')")
+
+
+# ------------------------------------------------------------------------------------------------
+# utils
+# ------------------------------------------------------------------------------------------------
+
+class utils:
+    @staticmethod
+    def load_json(path: str):
+        with open(path) as fh:
+            return json.load(fh)
+
+    @staticmethod
+    def plot_history(path: str) -> None:
+        """matplotlib is not available in this image; the JSON is what the reference's own
+        ``plot_loss`` consumes (cavity_steady.py:339-362)."""
+        return None
+
+    class HistoryPlotCallback:
+        """Every ``frequency`` iterations of a round: dump the history JSON (and, in the reference,
+        a PNG) -- cavity_steady.py:243-245."""
+
+        def __init__(self, frequency=100, gui=False, filename=None, filename_history=None):
+            self.frequency, self.filename, self.filename_history = frequency, filename, filename_history
+
+        def __call__(self, pb: OptimizationProblem, iter_round: int) -> None:
+            if self.filename_history and iter_round % self.frequency == 0:
+                pb.save_history(self.filename_history)

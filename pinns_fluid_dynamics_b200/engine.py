@@ -1,0 +1,250 @@
+"""Compilation of a loss table into point-set descriptors and the CUDA plan that evaluates them.
+
+``compile_problem`` is pure host logic (numpy): it groups the loss terms by point set, shards every
+point set over the ranks and computes the scale factors -- the part of nisaba's
+``OptimizationProblem`` that is not arithmetic.  ``CudaPlan`` binds the result to libpinnstep.so; it
+is the only evaluator the product ships (no CPU fallback).
+
+Sharding: every point set is cut into ``world`` contiguous chunks, the first
+``n mod world`` ranks get one extra row; a set smaller than ``world`` leaves the last ranks empty.
+Kernels return raw sum r^2 per term and the gradient of sum_t w_t/(nu_t N_t) sum r^2 with N_t the
+GLOBAL count, so a plain SUM all-reduce of the [P+T] vector is exact.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _capi
+from .residuals import MAX_CH, MAX_OUT, PointSet, ResidualForm
+
+MAX_TERMS_PER_SET = _capi.MAX_TERMS_PER_SET
+
+
+@dataclass
+class CompiledTerm:
+    name: str
+    form: ResidualForm
+    weight: float
+    normalization: float
+    train: bool
+    n_global: int
+    out_index: int = -1            # position in the [T] tail of the output vector (-1: identically zero)
+
+
+@dataclass
+class CompiledSet:
+    pointset: PointSet
+    start: int                     # first global row owned by this rank
+    stop: int
+    deriv_order: int
+    terms: List[CompiledTerm] = field(default_factory=list)
+
+    @property
+    def n_local(self) -> int:
+        return self.stop - self.start
+
+
+@dataclass
+class CompiledProblem:
+    mlp: Tuple[int, int, int, int]           # (d, H, L, O)
+    sets: List[CompiledSet]
+    terms: List[CompiledTerm]                # train terms first (table order), then test terms
+    n_params: int
+    rank: int
+    world: int
+
+    @property
+    def n_out_terms(self) -> int:
+        return sum(1 for t in self.terms if t.out_index >= 0)
+
+
+def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
+    base, rem = divmod(n, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def mlp_shape_from_variables(shapes: Sequence[Tuple[int, ...]]) -> Tuple[int, int, int, int]:
+    """(d, H, L, O) from Keras-ordered variable shapes [K1, b1, ..., K_{L+1}, b_{L+1}]."""
+    if len(shapes) < 4 or len(shapes) % 2:
+        raise ValueError("variables must be [K1, b1, ..., K_out, b_out] with at least one hidden layer")
+    kernels, biases = shapes[0::2], shapes[1::2]
+    d, H = kernels[0]
+    L = len(kernels) - 1
+    O = kernels[-1][1]
+    for i, (k, b) in enumerate(zip(kernels, biases)):
+        exp_in = d if i == 0 else H
+        exp_out = O if i == L else H
+        if tuple(k) != (exp_in, exp_out) or tuple(b) != (exp_out,):
+            raise ValueError(f"layer {i}: expected kernel {(exp_in, exp_out)} / bias {(exp_out,)}, got {k} / {b}")
+    return int(d), int(H), int(L), int(O)
+
+
+def param_count(d: int, H: int, L: int, O: int) -> int:
+    return d * H + H + (L - 1) * (H * H + H) + H * O + O
+
+
+def compile_problem(var_shapes, losses, losses_test=(), rank: int = 0, world: int = 1) -> CompiledProblem:
+    """``losses`` / ``losses_test``: objects with .name, .form (ResidualForm), .weight, .normalization."""
+    d, H, L, O = mlp_shape_from_variables(var_shapes)
+    if O > MAX_OUT:
+        raise ValueError(f"at most {MAX_OUT} network outputs are supported")
+    terms: List[CompiledTerm] = []
+    for train, table in ((True, losses), (False, losses_test)):
+        for l in table:
+            f = l.form
+            if f.pointset.dim != d:
+                raise ValueError(f"term {l.name}: point set has dim {f.pointset.dim}, network input is {d}")
+            for (o, c), v in f.coef.items():
+                if v != 0.0 and (o >= O or c >= 1 + d + 2):
+                    raise ValueError(f"term {l.name}: coefficient on output {o} / channel {c} out of range")
+            if f.conv != 0.0 and O < 2:
+                raise ValueError(f"term {l.name}: convective product needs outputs 0 and 1")
+            terms.append(CompiledTerm(l.name, f, float(l.weight), float(l.normalization), train, f.pointset.n))
+    # group by point set, first-appearance order; split groups larger than the ABI allows
+    by_set: Dict[int, List[CompiledTerm]] = {}
+    order: List[PointSet] = []
+    for t in terms:
+        if t.form.identically_zero:
+            continue
+        ps = t.form.pointset
+        if ps.uid not in by_set:
+            by_set[ps.uid] = []
+            order.append(ps)
+        by_set[ps.uid].append(t)
+    sets: List[CompiledSet] = []
+    nxt = 0
+    for ps in order:
+        group = by_set[ps.uid]
+        start, stop = shard_bounds(ps.n, rank, world)
+        for i in range(0, len(group), MAX_TERMS_PER_SET):
+            chunk = group[i:i + MAX_TERMS_PER_SET]
+            cs = CompiledSet(ps, start, stop, max(t.form.deriv_order() for t in chunk), chunk)
+            sets.append(cs)
+    for t in terms:  # output order = table order (train first), independent of grouping
+        if not t.form.identically_zero:
+            t.out_index = nxt
+            nxt += 1
+    return CompiledProblem((d, H, L, O), sets, terms, param_count(d, H, L, O), rank, world)
+
+
+def assemble_losses(cp: CompiledProblem, sumsq: np.ndarray) -> Tuple[float, List[float], List[float]]:
+    """(total, train values, test values) from the GLOBAL sums of squares.
+    value_t = sum r^2 / (N_t * normalization_t); total = sum_train weight_t * value_t
+    (nisaba semantics evidenced by History_Loss.json).  An empty point set gives
+    NaN, like the reference's mean over an empty tensor (quirk Q3)."""
+    train_vals, test_vals = [], []
+    total = 0.0
+    for t in cp.terms:
+        if t.out_index < 0:
+            v = 0.0
+        elif t.n_global == 0:
+            v = float("nan")
+        else:
+            v = float(sumsq[t.out_index]) / (t.n_global * t.normalization)
+        if t.train:
+            train_vals.append(v)
+            total += t.weight * v
+        else:
+            test_vals.append(v)
+    return total, train_vals, test_vals
+
+
+class CudaPlan:
+    """Device-side evaluator: owns the device copies of the local point/rhs shards and the
+    ``pinn_plan``.  Raises if CUDA or the library is unavailable."""
+
+    def __init__(self, cp: CompiledProblem, device=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise _capi.PinnLibraryError("CUDA device required: the PINN loss step has no CPU fallback")
+        self.lib = _capi.load()
+        self.cp = cp
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._keep = []
+        descs = (_capi.PointSetDesc * max(1, len(cp.sets)))()
+        self._pts_cache: Dict[int, "torch.Tensor"] = {}
+        for si, cs in enumerate(cp.sets):
+            ds = descs[si]
+            key = cs.pointset.uid
+            if key not in self._pts_cache:
+                local = np.ascontiguousarray(cs.pointset.points[cs.start:cs.stop])
+                self._pts_cache[key] = torch.from_numpy(local).to(self.device)
+            pts = self._pts_cache[key]
+            ds.points_dev = pts.data_ptr() if cs.n_local else None
+            ds.n_local = cs.n_local
+            ds.n_terms = len(cs.terms)
+            ds.deriv_order = cs.deriv_order
+            for ti, t in enumerate(cs.terms):
+                td = ds.terms[ti]
+                m = t.form.coef_matrix()
+                for o in range(MAX_OUT):
+                    for c in range(MAX_CH):
+                        td.coef[o][c] = float(m[o, c])
+                td.conv, td.conv_k, td.rhs_scale = float(t.form.conv), int(t.form.conv_k), float(t.form.rhs_scale)
+                rhs = t.form.rhs_array()
+                if rhs is not None and cs.n_local:
+                    r = torch.from_numpy(np.ascontiguousarray(rhs[cs.start:cs.stop])).to(self.device)
+                    self._keep.append(r)
+                    td.rhs_dev = r.data_ptr()
+                else:
+                    td.rhs_dev = None
+                td.weight, td.normalization = t.weight, t.normalization
+                td.n_global, td.train = t.n_global, 1 if t.train else 0
+        d, H, L, O = cp.mlp
+        mlp = _capi.MlpDesc(d, H, L, O)
+        handle = C.c_void_p()
+        _capi.check(self.lib.pinn_plan_create(C.byref(mlp), descs, len(cp.sets), self.device.index or 0,
+                                              C.byref(handle)), "pinn_plan_create")
+        self.handle = handle
+        # kernel term order is set order / term order; map to table order
+        self._perm = [t.out_index for cs in cp.sets for t in cs.terms]
+        self.n_kernel_terms = len(self._perm)
+        self.P = cp.n_params
+        self.out = torch.zeros(self.P + max(1, self.n_kernel_terms), dtype=torch.float32, device=self.device)
+        self._perm_t = torch.tensor(self._perm, dtype=torch.long, device=self.device)
+        self.engine = self.lib.pinn_plan_engine(handle).decode()
+
+    def _stream(self):
+        import torch
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def loss_and_grad(self, params_flat):
+        """Enqueue one step; returns the device vector [P + T] (gradient, then per-term sum r^2 in
+        KERNEL term order -- use ``to_table_order``)."""
+        assert params_flat.is_cuda and params_flat.dtype.is_floating_point and params_flat.is_contiguous()
+        _capi.check(self.lib.pinn_loss_and_grad(self.handle, C.c_void_p(params_flat.data_ptr()),
+                                                C.c_void_p(self.out.data_ptr()), self._stream()),
+                    "pinn_loss_and_grad")
+        return self.out
+
+    def loss_only(self, params_flat):
+        _capi.check(self.lib.pinn_loss(self.handle, C.c_void_p(params_flat.data_ptr()),
+                                       C.c_void_p(self.out.data_ptr()), self._stream()), "pinn_loss")
+        return self.out
+
+    def to_table_order(self, out):
+        """[T_table] tensor of sum r^2 indexed by CompiledTerm.out_index."""
+        import torch
+        res = torch.zeros(max(1, self.cp.n_out_terms), dtype=out.dtype, device=out.device)
+        if self.n_kernel_terms:
+            res[self._perm_t] = out[self.P:self.P + self.n_kernel_terms]
+        return res
+
+    def last_launch_count(self) -> int:
+        return int(self.lib.pinn_plan_last_launch_count(self.handle))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.pinn_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

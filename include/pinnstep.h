@@ -118,6 +118,12 @@ size_t pinn_plan_workspace_bytes(const pinn_plan* plan);
 const char* pinn_plan_engine(const pinn_plan* plan);
 /* Kernel launches enqueued by the last pinn_loss_and_grad / pinn_loss call. */
 int32_t pinn_plan_last_launch_count(const pinn_plan* plan);
+/* Per-kernel device timing for benchmarks: when enabled, each fused kernel launch of the plan is
+ * bracketed by CUDA events on the caller's stream (this makes the call non graph-capturable).
+ * pinn_plan_kernel_time_ms returns the duration of the last launch of the kernel that handled the
+ * point sets of derivative order `deriv_order` (2 = collocation kernel); it synchronises on that event. */
+int pinn_plan_enable_timing(pinn_plan* plan, int32_t on);
+int pinn_plan_kernel_time_ms(pinn_plan* plan, int32_t deriv_order, float* ms_out);
 /* Replace the rhs array of one term (e.g. re-drawn noise) without rebuilding the plan. */
 int pinn_plan_set_rhs(pinn_plan* plan, int32_t set_index, int32_t term_index, const float* rhs_dev);
 

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(LIB_DIR, "libpinnstep.so")
 EXPORTED_SYMBOLS = (
     "pinn_version", "pinn_last_error", "pinn_plan_create", "pinn_plan_destroy", "pinn_plan_param_count",
     "pinn_plan_term_count", "pinn_plan_workspace_bytes", "pinn_plan_engine", "pinn_plan_last_launch_count",
-    "pinn_plan_set_rhs", "pinn_loss_and_grad", "pinn_loss", "pinn_forward", "pinn_nccl_unique_id",
+    "pinn_plan_set_rhs", "pinn_plan_enable_timing", "pinn_plan_kernel_time_ms", "pinn_loss_and_grad", "pinn_loss", "pinn_forward", "pinn_nccl_unique_id",
     "pinn_comm_create", "pinn_comm_destroy", "pinn_allreduce_sum", "pinn_adam_step",
 )
 
@@ -79,6 +79,8 @@ def load(path: Optional[str] = None) -> C.CDLL:
     lib.pinn_plan_engine.argtypes = [vp]; lib.pinn_plan_engine.restype = C.c_char_p
     lib.pinn_plan_last_launch_count.argtypes = [vp]; lib.pinn_plan_last_launch_count.restype = i32
     lib.pinn_plan_set_rhs.argtypes = [vp, i32, i32, vp]
+    lib.pinn_plan_enable_timing.argtypes = [vp, i32]
+    lib.pinn_plan_kernel_time_ms.argtypes = [vp, i32, C.POINTER(C.c_float)]
     lib.pinn_loss_and_grad.argtypes = [vp, vp, vp, vp]
     lib.pinn_loss.argtypes = [vp, vp, vp, vp]
     lib.pinn_forward.argtypes = [C.POINTER(MlpDesc), vp, vp, i64, vp, i32, vp]

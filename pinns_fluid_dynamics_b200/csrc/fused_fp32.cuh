@@ -1,0 +1,681 @@
+// Fused FP32 loss-step kernel for narrow tanh MLPs (H <= 32): Taylor-mode jets forward, residuals,
+// weighted mean-square terms and the hand-written reverse sweep to parameter gradients, all in ONE
+// kernel with every activation kept on chip.
+//
+// Replaces (reference, per epoch): 3 x model(x) + 14 inner tape.gradient sweeps + nisaba's outer
+// tape.gradient over the collocation set (cavity_steady.py:159-188,212-214,242) and the per-term
+// forwards of dir_loss / neu_loss (cavity_steady.py:192-200, poiseuille_flow.py:199-209).
+//
+// Work decomposition
+//   * a WARP owns a chunk of 16 points from layer 1 to the parameter-gradient contribution; warps
+//     never synchronise with each other inside the main loop (only __syncwarp).
+//   * lane = (lr, lc): lr = lane>>2 owns points {2lr, 2lr+1} of the chunk, lc = lane&3 owns the
+//     neurons {lc + 4*jj}.  A hidden layer is a register-tiled FP32 GEMM
+//     [C*16 rows] x [H] x [H]: per k-step a lane loads its two points' C channel values (C LDS.64)
+//     and TC weights (LDS.128, pre-permuted so they are contiguous per lane) and issues 2*C*TC FFMA.
+//   * jets live in shared memory as J[neuron k][channel c][point p] (row stride RS = 16C+4 floats,
+//     RS/4 odd so the weight-gradient GEMM's LDS.128 are bank-conflict free).
+//   * the whole parameter vector is staged into shared memory once per CTA by one TMA bulk copy
+//     (cp.async.bulk + mbarrier), then permuted/transposed copies are built for the GEMMs.
+//   * reverse sweep: z-bar overwrites the a-jets in place; the pre-activation jets are recovered
+//     from the stored a-jets (z_x = a_x / s, ...), so only the a-jets of layers 2..L and tanh(z1)
+//     are stored: (L-1)*C*H + H floats per point.
+//   * weight gradients of the H x H layers accumulate in registers across ALL chunks of a warp
+//     (4 x TC per lane per layer); small gradients (K1, b1, K_out, b_out) go through a warp shuffle
+//     reduction into per-warp shared-memory accumulators.  At the end the CTA sums its warps and
+//     writes ONE row of the workspace; a finalize kernel sums the rows (no atomics anywhere).
+#pragma once
+#include "common.cuh"
+
+namespace pinn {
+
+template <int D_, int H_, int L_, int O_, int ORDER_>
+struct FusedCfg {
+  static constexpr int D = D_, H = H_, L = L_, O = O_, ORDER = ORDER_;
+  static constexpr int C = n_channels(D, ORDER);
+  static constexpr int TC = H / 4;                  // neurons per lane
+  static constexpr int TI = (H + 7) / 8;            // weight-gradient rows per lane
+  static constexpr int RS = C * kChunk + 4;         // floats per neuron row of a jet buffer
+  static constexpr int NBUF = L - 1;                // jet buffers: layers 2..L
+  static constexpr int SX = D - 2, SY = D - 1;      // spatial input columns
+  static_assert(H % 4 == 0, "width must be a multiple of 4");
+  static_assert(L >= 3, "fused kernel needs >= 3 hidden layers (scratch aliasing)");
+  // CTA-shared weights (floats)
+  static constexpr int W_K = (L - 1) * H * H;
+  static constexpr int W_KT = (L - 1) * H * H;
+  static constexpr int W_K1 = D * H;
+  static constexpr int W_B = L * H;
+  static constexpr int W_KO = H * 4;
+  static constexpr int W_BO = 4;
+  static constexpr int W_TOTAL = W_K + W_KT + W_K1 + W_B + W_KO + W_BO + 4 /* mbarrier */;
+  // per-warp (floats)
+  static constexpr int PW_JETS = NBUF * H * RS;
+  static constexpr int PW_SCR = NBUF * (H * H + H);   // end-of-kernel reduction scratch (aliases the jets)
+  static constexpr int PW_BUF = PW_JETS > PW_SCR ? PW_JETS : PW_SCR;
+  static constexpr int PW_A1 = H * kChunk;
+  static constexpr int G_K1 = 0, G_B1 = D * H, G_KO = D * H + H, G_BO = D * H + H + H * 4;
+  static constexpr int PW_G = G_BO + 4;
+  static constexpr int PW_SQ = kMaxLaunchTerms;
+  static constexpr int PW_TOTAL = PW_BUF + PW_A1 + PW_G + PW_SQ;
+  static constexpr int kSmemMax = 232448;           // 227 KB opt-in limit per CTA on sm_100
+  static constexpr int NW_FIT = (kSmemMax - W_TOTAL * 4) / (PW_TOTAL * 4);
+  static constexpr int NW = NW_FIT > 8 ? 8 : NW_FIT;
+  static_assert(NW >= 2, "configuration does not fit shared memory");
+  static constexpr int SMEM_BYTES = (W_TOTAL + NW * PW_TOTAL) * 4;
+  static constexpr int P = D * H + H + (L - 1) * (H * H + H) + H * O + O;
+  static_assert(P <= NW * PW_TOTAL, "parameter staging area too small");
+  static_assert(NBUF * (H * H + H) <= PW_BUF, "end-of-kernel reduction scratch too small");
+  __host__ __device__ static constexpr int offK(int l) {  // l = 2..L, flat Keras offset of K_l
+    return D * H + H + (l - 2) * (H * H + H);
+  }
+  static constexpr int OFF_KO = D * H + H + (L - 1) * (H * H + H);
+  static constexpr int OFF_BO = OFF_KO + H * O;
+};
+
+// ---- tanh jets ---------------------------------------------------------------------------------
+
+template <class Cfg>
+__device__ __forceinline__ void jet_from_a0(float a0, const float (&zd)[Cfg::D], float zxx, float zyy,
+                                            float (&a)[Cfg::C]) {
+  constexpr int D = Cfg::D;
+  a[0] = a0;
+  if constexpr (Cfg::ORDER >= 1) {
+    const float s = fmaf(-a0, a0, 1.0f);
+#pragma unroll
+    for (int i = 0; i < D; ++i) a[1 + i] = s * zd[i];
+    if constexpr (Cfg::ORDER >= 2) {
+      const float q = -2.0f * a0 * s;
+      a[1 + D] = fmaf(q * zd[Cfg::SX], zd[Cfg::SX], s * zxx);
+      a[2 + D] = fmaf(q * zd[Cfg::SY], zd[Cfg::SY], s * zyy);
+    }
+  }
+}
+
+// z-bar from a-bar given the STORED a-jets of the layer (pre-activation jets recovered by division).
+template <class Cfg>
+__device__ __forceinline__ void tanh_jet_bwd(const float (&aj)[Cfg::C], const float (&ab)[Cfg::C],
+                                             float (&zb)[Cfg::C]) {
+  constexpr int D = Cfg::D;
+  const float a0 = aj[0];
+  const float s = fmaf(-a0, a0, 1.0f);
+  zb[0] = s * ab[0];
+  if constexpr (Cfg::ORDER >= 1) {
+    const float q = -2.0f * a0 * s;
+    const float rs = s > 0.0f ? __frcp_rn(s) : 0.0f;
+    float zd[D];
+    float acc = 0.0f;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      zd[i] = aj[1 + i] * rs;
+      zb[1 + i] = s * ab[1 + i];
+      acc = fmaf(zd[i], ab[1 + i], acc);
+    }
+    if constexpr (Cfg::ORDER >= 2) {
+      const float zx2 = zd[Cfg::SX] * zd[Cfg::SX], zy2 = zd[Cfg::SY] * zd[Cfg::SY];
+      const float zxx = (aj[1 + D] - q * zx2) * rs;
+      const float zyy = (aj[2 + D] - q * zy2) * rs;
+      const float qp = -2.0f * s * fmaf(-3.0f * a0, a0, 1.0f);
+      zb[1 + D] = s * ab[1 + D];
+      zb[2 + D] = s * ab[2 + D];
+      zb[1 + Cfg::SX] = fmaf(2.0f * q * zd[Cfg::SX], ab[1 + D], zb[1 + Cfg::SX]);
+      zb[1 + Cfg::SY] = fmaf(2.0f * q * zd[Cfg::SY], ab[2 + D], zb[1 + Cfg::SY]);
+      acc = fmaf(zxx, ab[1 + D], acc);
+      acc = fmaf(zyy, ab[2 + D], acc);
+      zb[0] = fmaf(qp, fmaf(zx2, ab[1 + D], zy2 * ab[2 + D]), zb[0]);
+    }
+    zb[0] = fmaf(q, acc, zb[0]);
+  }
+}
+
+// same for layer 1, whose pre-activation jet is (z, K1[i][j], 0, 0): no division needed.
+template <class Cfg>
+__device__ __forceinline__ void tanh_jet_bwd_l1(float a0, const float (&zd)[Cfg::D], const float (&ab)[Cfg::C],
+                                                float (&zb)[Cfg::C]) {
+  constexpr int D = Cfg::D;
+  const float s = fmaf(-a0, a0, 1.0f);
+  zb[0] = s * ab[0];
+  if constexpr (Cfg::ORDER >= 1) {
+    const float q = -2.0f * a0 * s;
+    float acc = 0.0f;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      zb[1 + i] = s * ab[1 + i];
+      acc = fmaf(zd[i], ab[1 + i], acc);
+    }
+    if constexpr (Cfg::ORDER >= 2) {
+      const float zx2 = zd[Cfg::SX] * zd[Cfg::SX], zy2 = zd[Cfg::SY] * zd[Cfg::SY];
+      const float qp = -2.0f * s * fmaf(-3.0f * a0, a0, 1.0f);
+      zb[1 + D] = s * ab[1 + D];
+      zb[2 + D] = s * ab[2 + D];
+      zb[1 + Cfg::SX] = fmaf(2.0f * q * zd[Cfg::SX], ab[1 + D], zb[1 + Cfg::SX]);
+      zb[1 + Cfg::SY] = fmaf(2.0f * q * zd[Cfg::SY], ab[2 + D], zb[1 + Cfg::SY]);
+      zb[0] = fmaf(qp, fmaf(zx2, ab[1 + D], zy2 * ab[2 + D]), zb[0]);
+    }
+    zb[0] = fmaf(q, acc, zb[0]);
+  }
+}
+
+// ---- register-tiled GEMM over one warp's 16 points --------------------------------------------
+// acc[c][jj] (x: point 2lr, y: point 2lr+1) += sum_k in[k][c][p] * W[k][lc*TC + jj]
+template <class Cfg>
+__device__ __forceinline__ void warp_gemm(const float* __restrict__ in, const float* __restrict__ W,
+                                          float2 (&acc)[Cfg::C][Cfg::TC], int lr, int lc) {
+  constexpr int C = Cfg::C, TC = Cfg::TC, H = Cfg::H, RS = Cfg::RS;
+  const float* arow = in + 2 * lr;
+  const float* wrow = W + lc * TC;
+#pragma unroll 2
+  for (int k = 0; k < H; ++k) {
+    float2 a[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) a[c] = *reinterpret_cast<const float2*>(arow + k * RS + c * kChunk);
+    float w[TC];
+    if constexpr (TC % 4 == 0) {
+#pragma unroll
+      for (int v = 0; v < TC / 4; ++v) {
+        const float4 t = *reinterpret_cast<const float4*>(wrow + k * H + 4 * v);
+        w[4 * v] = t.x; w[4 * v + 1] = t.y; w[4 * v + 2] = t.z; w[4 * v + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int jj = 0; jj < TC; ++jj) w[jj] = wrow[k * H + jj];
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+      for (int jj = 0; jj < TC; ++jj) {
+        acc[c][jj].x = fmaf(a[c].x, w[jj], acc[c][jj].x);
+        acc[c][jj].y = fmaf(a[c].y, w[jj], acc[c][jj].y);
+      }
+  }
+}
+
+// gK[ii][jj] += sum_{c,p} A[li+8ii][c][p] * Z[lj+4jj][c][p];  gb[jj] += sum_p Z[lj+4jj][0][p]
+template <class Cfg>
+__device__ __forceinline__ void warp_wgrad(const float* __restrict__ A, const float* __restrict__ Z,
+                                           float (&gK)[Cfg::TI][Cfg::TC], float (&gb)[Cfg::TC], int li, int lj) {
+  constexpr int C = Cfg::C, TC = Cfg::TC, TI = Cfg::TI, H = Cfg::H, RS = Cfg::RS;
+#pragma unroll 1
+  for (int cq = 0; cq < C * 4; ++cq) {      // (channel, point quad): offset cq*4 floats within a row
+    float4 av[TI];
+#pragma unroll
+    for (int ii = 0; ii < TI; ++ii) {
+      const int i = li + 8 * ii;
+      av[ii] = (i < H) ? *reinterpret_cast<const float4*>(A + i * RS + cq * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int jj = 0; jj < TC; ++jj) {
+      const float4 zv = *reinterpret_cast<const float4*>(Z + (lj + 4 * jj) * RS + cq * 4);
+#pragma unroll
+      for (int ii = 0; ii < TI; ++ii) {
+        float t = gK[ii][jj];
+        t = fmaf(av[ii].x, zv.x, t);
+        t = fmaf(av[ii].y, zv.y, t);
+        t = fmaf(av[ii].z, zv.z, t);
+        t = fmaf(av[ii].w, zv.w, t);
+        gK[ii][jj] = t;
+      }
+      if (cq < 4) gb[jj] += (zv.x + zv.y) + (zv.z + zv.w);   // channel 0 only: bias gradient
+    }
+  }
+}
+
+__device__ __forceinline__ float reduce_over_lr(float v) {   // sum over the 8 row-lanes (same lc)
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  return v;
+}
+__device__ __forceinline__ float reduce_warp(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// materialise the layer-1 a-jets of this lane's (2 points x TC neurons) from tanh(z1) in a1buf
+template <class Cfg>
+__device__ __forceinline__ void write_a1_jets(float* __restrict__ dst, const float* __restrict__ a1buf,
+                                              const float* __restrict__ sK1, int lr, int lc) {
+  constexpr int C = Cfg::C, TC = Cfg::TC, D = Cfg::D, H = Cfg::H, RS = Cfg::RS;
+#pragma unroll
+  for (int jj = 0; jj < TC; ++jj) {
+    const int j = lc + 4 * jj;
+    const float2 a0 = *reinterpret_cast<const float2*>(a1buf + j * kChunk + 2 * lr);
+    float zd[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) zd[i] = sK1[i * H + j];
+    float ax[C], ay[C];
+    jet_from_a0<Cfg>(a0.x, zd, 0.f, 0.f, ax);
+    jet_from_a0<Cfg>(a0.y, zd, 0.f, 0.f, ay);
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      *reinterpret_cast<float2*>(dst + j * RS + c * kChunk + 2 * lr) = make_float2(ax[c], ay[c]);
+  }
+}
+
+template <int D, int H, int L, int O, int ORDER, bool TRAIN>
+__global__ void __launch_bounds__(FusedCfg<D, H, L, O, ORDER>::NW * 32, 1)
+fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ segs, int n_segs, int total_chunks,
+                  float* __restrict__ ws, int ws_stride, int n_terms_total, int params_aligned) {
+  using Cfg = FusedCfg<D, H, L, O, ORDER>;
+  constexpr int C = Cfg::C, TC = Cfg::TC, TI = Cfg::TI, RS = Cfg::RS, NBUF = Cfg::NBUF, NW = Cfg::NW;
+  constexpr int SX = Cfg::SX, SY = Cfg::SY, P = Cfg::P;
+  extern __shared__ __align__(16) float smem[];
+  float* sK = smem;
+  float* sKT = sK + Cfg::W_K;
+  float* sK1 = sKT + Cfg::W_KT;
+  float* sB = sK1 + Cfg::W_K1;
+  float* sKo = sB + Cfg::W_B;
+  float* sBo = sKo + Cfg::W_KO;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sBo + Cfg::W_BO);
+  float* warp_base = smem + Cfg::W_TOTAL;
+
+  const int tid = threadIdx.x, nthr = NW * 32;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lc = lane & 3;
+
+  // ---- stage the parameter vector: one TMA bulk copy + tail, then permuted copies ---------------
+  {
+    float* raw = warp_base;   // aliases the warps' jet buffers; consumed before the main loop
+    const uint32_t bulk_bytes = params_aligned ? ((uint32_t)(P * 4) & ~15u) : 0u;
+    if (tid == 0) {
+      mbar_init(bar, 1);
+      fence_barrier_init();
+    }
+    __syncthreads();
+    if (tid == 0 && bulk_bytes) {
+      mbar_expect_tx(bar, bulk_bytes);
+      tma_bulk_g2s(raw, params, bulk_bytes, bar);
+    }
+    for (int i = (int)(bulk_bytes / 4) + tid; i < P; i += nthr) raw[i] = __ldg(params + i);
+    if (bulk_bytes) mbar_wait(bar, 0);
+    __syncthreads();
+    for (int idx = tid; idx < Cfg::W_K; idx += nthr) {
+      const int l = idx / (H * H), k = (idx / H) % H, col = idx % H;
+      const int g = col / TC, t = col % TC;           // lane group / slot
+      const int j = g + 4 * t;
+      sK[idx] = raw[Cfg::offK(l + 2) + k * H + j];    // sK[l][k][g][t]  = K_l[k][g+4t]
+      sKT[idx] = raw[Cfg::offK(l + 2) + j * H + k];   // sKT[l][k][g][t] = K_l[g+4t][k]
+    }
+    for (int idx = tid; idx < D * H; idx += nthr) sK1[idx] = raw[idx];
+    for (int idx = tid; idx < L * H; idx += nthr) {
+      const int l = idx / H, j = idx % H;
+      sB[idx] = (l == 0) ? raw[D * H + j] : raw[Cfg::offK(l + 1) + H * H + j];
+    }
+    for (int idx = tid; idx < H * 4; idx += nthr) {
+      const int j = idx >> 2, o = idx & 3;
+      sKo[idx] = (o < O) ? raw[Cfg::OFF_KO + j * O + o] : 0.f;
+    }
+    if (tid < 4) sBo[tid] = (tid < O) ? raw[Cfg::OFF_BO + tid] : 0.f;
+    __syncthreads();
+  }
+
+  float* buf = warp_base + warp * Cfg::PW_TOTAL;
+  float* a1buf = buf + Cfg::PW_BUF;
+  float* sg = a1buf + Cfg::PW_A1;
+  float* ssq = sg + Cfg::PW_G;
+  for (int i = lane; i < Cfg::PW_G + Cfg::PW_SQ; i += 32) sg[i] = 0.f;
+  __syncwarp();
+
+  float gK[NBUF][TI][TC];
+  float gb[NBUF][TC];
+#pragma unroll
+  for (int l = 0; l < NBUF; ++l)
+#pragma unroll
+    for (int jj = 0; jj < TC; ++jj) {
+      gb[l][jj] = 0.f;
+#pragma unroll
+      for (int ii = 0; ii < TI; ++ii) gK[l][ii][jj] = 0.f;
+    }
+
+  for (int chunk = blockIdx.x * NW + warp; chunk < total_chunks; chunk += gridDim.x * NW) {
+    int si = 0;
+    while (si + 1 < n_segs && chunk >= __ldg(&segs[si + 1].chunk_begin)) ++si;
+    const SegDev* __restrict__ seg = segs + si;
+    const long long n = seg->n;
+    const long long p0 = (long long)(chunk - seg->chunk_begin) * kChunk + 2 * lr;
+    const bool valid0 = p0 < n, valid1 = p0 + 1 < n;
+    const long long i0 = valid0 ? p0 : n - 1, i1 = valid1 ? p0 + 1 : n - 1;
+    float x0[D], x1[D];
+    {
+      const float* pts = seg->pts;
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        x0[i] = __ldg(pts + i0 * D + i);
+        x1[i] = __ldg(pts + i1 * D + i);
+      }
+    }
+
+    // ---- layer 1: z = x K1 + b1, a = tanh z; jets into the scratch buffer B(L) ----------------
+    float* const bufL = buf + (NBUF - 1) * H * RS;
+#pragma unroll
+    for (int jj = 0; jj < TC; ++jj) {
+      const int j = lc + 4 * jj;
+      float z0 = sB[j], z1 = z0;
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        const float w = sK1[i * H + j];
+        z0 = fmaf(x0[i], w, z0);
+        z1 = fmaf(x1[i], w, z1);
+      }
+      *reinterpret_cast<float2*>(a1buf + j * kChunk + 2 * lr) = make_float2(tanh_accurate(z0), tanh_accurate(z1));
+    }
+    write_a1_jets<Cfg>(bufL, a1buf, sK1, lr, lc);
+    __syncwarp();
+
+    // ---- hidden layers 2..L (+ output layer folded into the epilogue of layer L) --------------
+    float2 J[C][O];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+      for (int o = 0; o < O; ++o) J[c][o] = make_float2(0.f, 0.f);
+#pragma unroll 1
+    for (int l = 2; l <= L; ++l) {
+      const float* in = (l == 2) ? bufL : buf + (l - 3) * H * RS;
+      float* out = buf + (l - 2) * H * RS;
+      float2 acc[C][TC];
+#pragma unroll
+      for (int jj = 0; jj < TC; ++jj) {
+        const float b = sB[(l - 1) * H + lc + 4 * jj];
+        acc[0][jj] = make_float2(b, b);
+#pragma unroll
+        for (int c = 1; c < C; ++c) acc[c][jj] = make_float2(0.f, 0.f);
+      }
+      warp_gemm<Cfg>(in, sK + (l - 2) * H * H, acc, lr, lc);
+      __syncwarp();   // all lanes finished reading `in` (it may alias `out`)
+#pragma unroll
+      for (int jj = 0; jj < TC; ++jj) {
+        const int j = lc + 4 * jj;
+        float zx[C], zy[C], ax[C], ay[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) { zx[c] = acc[c][jj].x; zy[c] = acc[c][jj].y; }
+        float zdx[D], zdy[D];
+        float zxx0 = 0.f, zyy0 = 0.f, zxx1 = 0.f, zyy1 = 0.f;
+        if constexpr (ORDER >= 1) {
+#pragma unroll
+          for (int i = 0; i < D; ++i) { zdx[i] = zx[1 + i]; zdy[i] = zy[1 + i]; }
+        } else {
+#pragma unroll
+          for (int i = 0; i < D; ++i) { zdx[i] = 0.f; zdy[i] = 0.f; }
+        }
+        if constexpr (ORDER >= 2) { zxx0 = zx[1 + D]; zyy0 = zx[2 + D]; zxx1 = zy[1 + D]; zyy1 = zy[2 + D]; }
+        jet_from_a0<Cfg>(tanh_accurate(zx[0]), zdx, zxx0, zyy0, ax);
+        jet_from_a0<Cfg>(tanh_accurate(zy[0]), zdy, zxx1, zyy1, ay);
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+          *reinterpret_cast<float2*>(out + j * RS + c * kChunk + 2 * lr) = make_float2(ax[c], ay[c]);
+        if (l == L) {
+          const float4 ko = *reinterpret_cast<const float4*>(sKo + j * 4);
+          const float kov[4] = {ko.x, ko.y, ko.z, ko.w};
+#pragma unroll
+          for (int c = 0; c < C; ++c)
+#pragma unroll
+            for (int o = 0; o < O; ++o) {
+              J[c][o].x = fmaf(ax[c], kov[o], J[c][o].x);
+              J[c][o].y = fmaf(ay[c], kov[o], J[c][o].y);
+            }
+        }
+      }
+      __syncwarp();
+    }
+    // butterfly over the 4 neuron-lanes: every lane ends with the full output jets of its 2 points
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+      for (int o = 0; o < O; ++o) {
+        float vx = J[c][o].x, vy = J[c][o].y;
+        vx += __shfl_xor_sync(0xffffffffu, vx, 1); vy += __shfl_xor_sync(0xffffffffu, vy, 1);
+        vx += __shfl_xor_sync(0xffffffffu, vx, 2); vy += __shfl_xor_sync(0xffffffffu, vy, 2);
+        if (c == 0) { vx += sBo[o]; vy += sBo[o]; }
+        J[c][o] = make_float2(vx, vy);
+      }
+    if (seg->y_out != nullptr && lc == 0) {
+      float* y = seg->y_out;
+#pragma unroll
+      for (int o = 0; o < O; ++o) {
+        if (valid0) y[p0 * O + o] = J[0][o].x;
+        if (valid1) y[(p0 + 1) * O + o] = J[0][o].y;
+      }
+    }
+
+    // ---- residuals, sum of squares, adjoint of the output jets ---------------------------------
+    float2 Jb[C][O];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+      for (int o = 0; o < O; ++o) Jb[c][o] = make_float2(0.f, 0.f);
+    const int n_terms = seg->n_terms;
+#pragma unroll 1
+    for (int t = 0; t < n_terms; ++t) {
+      const TermDev* __restrict__ T = seg->terms + t;
+      if (TRAIN && !T->train) continue;
+      float2 r = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int o = 0; o < O; ++o)
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float cf = __ldg(&T->coef[o][c]);
+          r.x = fmaf(cf, J[c][o].x, r.x);
+          r.y = fmaf(cf, J[c][o].y, r.y);
+        }
+      float cv = 0.f;
+      int ck = 0;
+      if constexpr (ORDER >= 1 && O >= 2) {
+        cv = __ldg(&T->conv);
+        ck = __ldg(&T->conv_k);
+        const float2 ukx = ck == 0 ? J[1 + SX][0] : J[1 + SX][1];
+        const float2 uky = ck == 0 ? J[1 + SY][0] : J[1 + SY][1];
+        r.x = fmaf(cv, fmaf(J[0][0].x, ukx.x, J[0][1].x * uky.x), r.x);
+        r.y = fmaf(cv, fmaf(J[0][0].y, ukx.y, J[0][1].y * uky.y), r.y);
+      }
+      const float* rhs = T->rhs;
+      if (rhs != nullptr) {
+        const float rsx = __ldg(&T->rhs_scale);
+        r.x = fmaf(-rsx, __ldg(rhs + i0), r.x);
+        r.y = fmaf(-rsx, __ldg(rhs + i1), r.y);
+      }
+      r.x = valid0 ? r.x : 0.f;
+      r.y = valid1 ? r.y : 0.f;
+      float sq = (lc == 0) ? fmaf(r.x, r.x, r.y * r.y) : 0.f;
+      sq = reduce_warp(sq);
+      if (lane == 0) ssq[T->out_index] += sq;
+      if constexpr (TRAIN) {
+        const float sc = __ldg(&T->scale);
+        const float2 rb = make_float2(sc * r.x, sc * r.y);
+#pragma unroll
+        for (int o = 0; o < O; ++o)
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const float cf = __ldg(&T->coef[o][c]);
+            Jb[c][o].x = fmaf(cf, rb.x, Jb[c][o].x);
+            Jb[c][o].y = fmaf(cf, rb.y, Jb[c][o].y);
+          }
+        if constexpr (ORDER >= 1 && O >= 2) {
+          const float2 ukx = ck == 0 ? J[1 + SX][0] : J[1 + SX][1];
+          const float2 uky = ck == 0 ? J[1 + SY][0] : J[1 + SY][1];
+          const float2 m = make_float2(cv * rb.x, cv * rb.y);
+          Jb[0][0].x = fmaf(m.x, ukx.x, Jb[0][0].x); Jb[0][0].y = fmaf(m.y, ukx.y, Jb[0][0].y);
+          Jb[0][1].x = fmaf(m.x, uky.x, Jb[0][1].x); Jb[0][1].y = fmaf(m.y, uky.y, Jb[0][1].y);
+          const float2 m0 = ck == 0 ? m : make_float2(0.f, 0.f);
+          const float2 m1 = ck == 0 ? make_float2(0.f, 0.f) : m;
+          Jb[1 + SX][0].x = fmaf(m0.x, J[0][0].x, Jb[1 + SX][0].x); Jb[1 + SX][0].y = fmaf(m0.y, J[0][0].y, Jb[1 + SX][0].y);
+          Jb[1 + SY][0].x = fmaf(m0.x, J[0][1].x, Jb[1 + SY][0].x); Jb[1 + SY][0].y = fmaf(m0.y, J[0][1].y, Jb[1 + SY][0].y);
+          Jb[1 + SX][1].x = fmaf(m1.x, J[0][0].x, Jb[1 + SX][1].x); Jb[1 + SX][1].y = fmaf(m1.y, J[0][0].y, Jb[1 + SX][1].y);
+          Jb[1 + SY][1].x = fmaf(m1.x, J[0][1].x, Jb[1 + SY][1].x); Jb[1 + SY][1].y = fmaf(m1.y, J[0][1].y, Jb[1 + SY][1].y);
+        }
+      }
+    }
+
+    if constexpr (TRAIN) {
+      // ---- output layer backward + tanh-jet backward of layer L (in place in B(L)) ------------
+      {
+        // b_out gradient: sum over the warp's points of Jb[0][o] (identical in the 4 neuron-lanes)
+#pragma unroll
+        for (int o = 0; o < O; ++o) {
+          float v = reduce_over_lr(Jb[0][o].x + Jb[0][o].y);
+          if (lane == 0) sg[Cfg::G_BO + o] += v;
+        }
+#pragma unroll
+        for (int jj = 0; jj < TC; ++jj) {
+          const int j = lc + 4 * jj;
+          float ajx[C], ajy[C], abx[C], aby[C], zbx[C], zby[C];
+          const float4 ko = *reinterpret_cast<const float4*>(sKo + j * 4);
+          const float kov[4] = {ko.x, ko.y, ko.z, ko.w};
+          float pk[O];
+#pragma unroll
+          for (int o = 0; o < O; ++o) pk[o] = 0.f;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const float2 a = *reinterpret_cast<const float2*>(bufL + j * RS + c * kChunk + 2 * lr);
+            ajx[c] = a.x; ajy[c] = a.y;
+            float bx = 0.f, by = 0.f;
+#pragma unroll
+            for (int o = 0; o < O; ++o) {
+              bx = fmaf(Jb[c][o].x, kov[o], bx);
+              by = fmaf(Jb[c][o].y, kov[o], by);
+              pk[o] = fmaf(a.x, Jb[c][o].x, fmaf(a.y, Jb[c][o].y, pk[o]));
+            }
+            abx[c] = bx; aby[c] = by;
+          }
+#pragma unroll
+          for (int o = 0; o < O; ++o) {
+            const float v = reduce_over_lr(pk[o]);
+            if (lr == 0) sg[Cfg::G_KO + j * 4 + o] += v;
+          }
+          tanh_jet_bwd<Cfg>(ajx, abx, zbx);
+          tanh_jet_bwd<Cfg>(ajy, aby, zby);
+#pragma unroll
+          for (int c = 0; c < C; ++c)
+            *reinterpret_cast<float2*>(bufL + j * RS + c * kChunk + 2 * lr) = make_float2(zbx[c], zby[c]);
+        }
+        __syncwarp();
+      }
+      // ---- hidden layers L..2 -----------------------------------------------------------------
+#pragma unroll
+      for (int l = L; l >= 2; --l) {
+        float* Zl = buf + (l - 2) * H * RS;                    // holds z-bar of layer l
+        float* Aprev;                                          // a-jets of layer l-1
+        if (l > 2) {
+          Aprev = buf + (l - 3) * H * RS;
+        } else {
+          Aprev = bufL;                                        // free by now (L >= 3)
+          write_a1_jets<Cfg>(Aprev, a1buf, sK1, lr, lc);
+          __syncwarp();
+        }
+        warp_wgrad<Cfg>(Aprev, Zl, gK[l - 2], gb[l - 2], lr, lc);
+        float2 acc[C][TC];
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+#pragma unroll
+          for (int jj = 0; jj < TC; ++jj) acc[c][jj] = make_float2(0.f, 0.f);
+        warp_gemm<Cfg>(Zl, sKT + (l - 2) * H * H, acc, lr, lc);
+        __syncwarp();
+        if (l > 2) {
+#pragma unroll
+          for (int jj = 0; jj < TC; ++jj) {
+            const int j = lc + 4 * jj;
+            float ajx[C], ajy[C], abx[C], aby[C], zbx[C], zby[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              const float2 a = *reinterpret_cast<const float2*>(Aprev + j * RS + c * kChunk + 2 * lr);
+              ajx[c] = a.x; ajy[c] = a.y;
+              abx[c] = acc[c][jj].x; aby[c] = acc[c][jj].y;
+            }
+            tanh_jet_bwd<Cfg>(ajx, abx, zbx);
+            tanh_jet_bwd<Cfg>(ajy, aby, zby);
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+              *reinterpret_cast<float2*>(Aprev + j * RS + c * kChunk + 2 * lr) = make_float2(zbx[c], zby[c]);
+          }
+          __syncwarp();
+        } else {
+          // layer 1: z-bar stays in registers; K1 / b1 gradients via shuffle reduction
+#pragma unroll
+          for (int jj = 0; jj < TC; ++jj) {
+            const int j = lc + 4 * jj;
+            const float2 a0 = *reinterpret_cast<const float2*>(a1buf + j * kChunk + 2 * lr);
+            float zd[D], abx[C], aby[C], zbx[C], zby[C];
+#pragma unroll
+            for (int i = 0; i < D; ++i) zd[i] = sK1[i * H + j];
+#pragma unroll
+            for (int c = 0; c < C; ++c) { abx[c] = acc[c][jj].x; aby[c] = acc[c][jj].y; }
+            tanh_jet_bwd_l1<Cfg>(a0.x, zd, abx, zbx);
+            tanh_jet_bwd_l1<Cfg>(a0.y, zd, aby, zby);
+            const float vb = reduce_over_lr(zbx[0] + zby[0]);
+            if (lr == 0) sg[Cfg::G_B1 + j] += vb;
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+              float v = fmaf(x0[i], zbx[0], x1[i] * zby[0]);
+              if constexpr (ORDER >= 1) v += zbx[1 + i] + zby[1 + i];
+              v = reduce_over_lr(v);
+              if (lr == 0) sg[Cfg::G_K1 + i * H + j] += v;
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+
+  // ---- CTA reduction: sum the warps' partials and write this CTA's workspace row ---------------
+  __syncthreads();
+  float* row = ws + (size_t)blockIdx.x * ws_stride;
+  if constexpr (TRAIN) {
+    // dump the register accumulators into the (now idle) jet buffer of the warp, natural layout
+    float* scr = buf;
+#pragma unroll
+    for (int l = 0; l < NBUF; ++l)
+#pragma unroll
+      for (int jj = 0; jj < TC; ++jj) {
+        const int j = lc + 4 * jj;
+#pragma unroll
+        for (int ii = 0; ii < TI; ++ii) {
+          const int i = lr + 8 * ii;
+          if (i < H) scr[l * H * H + i * H + j] = gK[l][ii][jj];
+        }
+        if (lr == 0) scr[NBUF * H * H + l * H + j] = gb[l][jj];
+      }
+    __syncthreads();
+    for (int idx = tid; idx < P; idx += nthr) {
+      int off;   // offset inside a warp's private area
+      if (idx < D * H) off = Cfg::PW_BUF + Cfg::PW_A1 + Cfg::G_K1 + idx;
+      else if (idx < D * H + H) off = Cfg::PW_BUF + Cfg::PW_A1 + Cfg::G_B1 + (idx - D * H);
+      else if (idx < Cfg::OFF_KO) {
+        const int r = idx - (D * H + H);
+        const int l = r / (H * H + H), q = r % (H * H + H);
+        off = (q < H * H) ? l * H * H + q : NBUF * H * H + l * H + (q - H * H);
+      } else if (idx < Cfg::OFF_BO) {
+        const int r = idx - Cfg::OFF_KO;
+        off = Cfg::PW_BUF + Cfg::PW_A1 + Cfg::G_KO + (r / O) * 4 + (r % O);
+      } else off = Cfg::PW_BUF + Cfg::PW_A1 + Cfg::G_BO + (idx - Cfg::OFF_BO);
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) s += warp_base[w * Cfg::PW_TOTAL + off];
+      row[idx] = s;
+    }
+  }
+  for (int t = tid; t < n_terms_total; t += nthr) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s += warp_base[w * Cfg::PW_TOTAL + Cfg::PW_BUF + Cfg::PW_A1 + Cfg::PW_G + t];
+    row[ws_stride - n_terms_total + t] = s;
+  }
+}
+
+// rows -> out: out[i] = sum_r ws[r][i] for i in [i_begin, stride)
+__global__ void finalize_rows_kernel(const float* __restrict__ ws, int rows, int stride, int i_begin,
+                                     float* __restrict__ out) {
+  const int i = i_begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= stride) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int r = 0;
+  for (; r + 3 < rows; r += 4) {
+    s0 += ws[(size_t)r * stride + i];
+    s1 += ws[(size_t)(r + 1) * stride + i];
+    s2 += ws[(size_t)(r + 2) * stride + i];
+    s3 += ws[(size_t)(r + 3) * stride + i];
+  }
+  for (; r < rows; ++r) s0 += ws[(size_t)r * stride + i];
+  out[i] = (s0 + s1) + (s2 + s3);
+}
+
+}  // namespace pinn

@@ -1,0 +1,460 @@
+// libpinnstep.so -- C ABI (include/pinnstep.h) over the sm_100a kernels.
+#include "../../include/pinnstep.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "fused_fp32.cuh"
+
+using namespace pinn;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t e_ = (expr);                                                                   \
+    if (e_ != cudaSuccess)                                                                     \
+      return fail(PINN_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------
+struct LaunchTable {
+  int order = 0;
+  int n_segs = 0;
+  int total_chunks = 0;
+  SegDev* segs_dev = nullptr;
+};
+
+struct pinn_plan {
+  pinn_mlp_desc mlp{};
+  int device = 0;
+  int num_sms = 0;
+  int64_t P = 0;
+  int T = 0;
+  std::vector<pinn_pointset_desc> sets;
+  std::vector<int> term_base;            // first output slot of each set
+  LaunchTable train[3], eval[3];         // by derivative order
+  float* ws = nullptr;                   // [rows_max][P + T]
+  int rows_max = 0;
+  size_t ws_bytes = 0;
+  int last_launches = 0;
+  const char* engine = "fused_fp32";
+  bool timing = false;
+  cudaEvent_t ev0[3] = {nullptr, nullptr, nullptr}, ev1[3] = {nullptr, nullptr, nullptr};
+  bool ev_valid[3] = {false, false, false};
+};
+
+typedef void (*fused_fn)(const float*, const SegDev*, int, int, float*, int, int, int);
+
+struct FusedKernel {
+  fused_fn fn;
+  int smem_bytes;
+  int nw;
+};
+
+template <int D, int H, int L, int O, int ORDER, bool TRAIN>
+static FusedKernel make_kernel() {
+  using Cfg = FusedCfg<D, H, L, O, ORDER>;
+  return FusedKernel{(fused_fn)fused_step_kernel<D, H, L, O, ORDER, TRAIN>, Cfg::SMEM_BYTES, Cfg::NW};
+}
+
+template <int D, int H, int L, int O>
+static bool pick_order(int order, bool train, FusedKernel* k) {
+  switch (order) {
+    case 0: *k = train ? make_kernel<D, H, L, O, 0, true>() : make_kernel<D, H, L, O, 0, false>(); return true;
+    case 1: *k = train ? make_kernel<D, H, L, O, 1, true>() : make_kernel<D, H, L, O, 1, false>(); return true;
+    case 2: *k = train ? make_kernel<D, H, L, O, 2, true>() : make_kernel<D, H, L, O, 2, false>(); return true;
+  }
+  return false;
+}
+
+static bool pick_kernel(const pinn_mlp_desc& m, int order, bool train, FusedKernel* k) {
+  if (m.n_hidden != 3) return false;
+  if (m.in_dim == 2 && m.width == 32 && m.out_dim == 3) return pick_order<2, 32, 3, 3>(order, train, k);
+  if (m.in_dim == 3 && m.width == 32 && m.out_dim == 3) return pick_order<3, 32, 3, 3>(order, train, k);
+  if (m.in_dim == 2 && m.width == 20 && m.out_dim == 1) return pick_order<2, 20, 3, 1>(order, train, k);
+  return false;
+}
+
+static int64_t param_count(const pinn_mlp_desc& m) {
+  const int64_t d = m.in_dim, H = m.width, L = m.n_hidden, O = m.out_dim;
+  return d * H + H + (L - 1) * (H * H + H) + H * O + O;
+}
+
+static int build_table(pinn_plan* p, int order, bool train_only, LaunchTable* out) {
+  std::vector<SegDev> segs;
+  int chunk = 0;
+  for (size_t s = 0; s < p->sets.size(); ++s) {
+    const pinn_pointset_desc& ps = p->sets[s];
+    if (ps.deriv_order != order || ps.n_local <= 0) continue;
+    SegDev sd;
+    memset(&sd, 0, sizeof(sd));
+    int nt = 0;
+    for (int t = 0; t < ps.n_terms; ++t) {
+      const pinn_term_desc& td = ps.terms[t];
+      if (train_only && !td.train) continue;
+      TermDev& d = sd.terms[nt++];
+      memcpy(d.coef, td.coef, sizeof(d.coef));
+      d.conv = td.conv;
+      d.conv_k = td.conv_k;
+      d.rhs_scale = td.rhs_scale;
+      d.rhs = td.rhs_dev;
+      d.train = td.train;
+      d.out_index = p->term_base[s] + t;
+      const double denom = td.normalization * (double)td.n_global;
+      d.scale = (td.train && denom != 0.0) ? (float)(2.0 * td.weight / denom) : 0.f;
+    }
+    if (nt == 0) continue;
+    sd.pts = ps.points_dev;
+    sd.y_out = nullptr;
+    sd.n = ps.n_local;
+    sd.n_terms = nt;
+    sd.chunk_begin = chunk;
+    sd.n_chunks = (int)((ps.n_local + kChunk - 1) / kChunk);
+    chunk += sd.n_chunks;
+    segs.push_back(sd);
+  }
+  out->order = order;
+  out->n_segs = (int)segs.size();
+  out->total_chunks = chunk;
+  out->segs_dev = nullptr;
+  if (!segs.empty()) {
+    CUDA_TRY(cudaMalloc(&out->segs_dev, segs.size() * sizeof(SegDev)));
+    CUDA_TRY(cudaMemcpy(out->segs_dev, segs.data(), segs.size() * sizeof(SegDev), cudaMemcpyHostToDevice));
+  }
+  return PINN_OK;
+}
+
+extern "C" int pinn_version(void) { return PINN_VERSION; }
+extern "C" const char* pinn_last_error(void) { return g_err; }
+
+extern "C" int pinn_plan_create(const pinn_mlp_desc* mlp, const pinn_pointset_desc* sets, int32_t n_sets,
+                                int32_t device, pinn_plan** out) {
+  if (!mlp || !out || n_sets < 0 || (n_sets > 0 && !sets)) return fail(PINN_E_INVALID, "null argument");
+  *out = nullptr;
+  if (mlp->in_dim < 2 || mlp->in_dim > PINN_MAX_DIM || mlp->out_dim < 1 || mlp->out_dim > PINN_MAX_OUT ||
+      mlp->width < 4 || mlp->n_hidden < 1)
+    return fail(PINN_E_INVALID, "unsupported MLP shape d=%d H=%d L=%d O=%d", mlp->in_dim, mlp->width, mlp->n_hidden,
+                mlp->out_dim);
+  FusedKernel probe;
+  if (!pick_kernel(*mlp, 0, true, &probe))
+    return fail(PINN_E_INVALID,
+                "no engine for MLP d=%d H=%d L=%d O=%d (fused_fp32 covers 2-20x3-1, 2-32x3-3, 3-32x3-3)", mlp->in_dim,
+                mlp->width, mlp->n_hidden, mlp->out_dim);
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(PINN_E_ARCH, "device %d is sm_%d%d; this library is sm_100a only", device, prop.major, prop.minor);
+  pinn_plan* p = new (std::nothrow) pinn_plan();
+  if (!p) return fail(PINN_E_ALLOC, "out of host memory");
+  p->mlp = *mlp;
+  p->device = device;
+  p->num_sms = prop.multiProcessorCount;
+  p->P = param_count(*mlp);
+  int T = 0;
+  for (int s = 0; s < n_sets; ++s) {
+    const pinn_pointset_desc& ps = sets[s];
+    if (ps.n_terms < 0 || ps.n_terms > PINN_MAX_TERMS_PER_SET || ps.deriv_order < 0 || ps.deriv_order > 2 ||
+        ps.n_local < 0 || (ps.n_local > 0 && !ps.points_dev)) {
+      delete p;
+      return fail(PINN_E_INVALID, "bad point set %d", s);
+    }
+    p->sets.push_back(ps);
+    p->term_base.push_back(T);
+    T += ps.n_terms;
+  }
+  if (T > kMaxLaunchTerms) {
+    delete p;
+    return fail(PINN_E_INVALID, "%d loss terms exceed the limit of %d", T, kMaxLaunchTerms);
+  }
+  p->T = T;
+  for (int o = 0; o < 3; ++o) {
+    int rc = build_table(p, o, true, &p->train[o]);
+    if (rc == PINN_OK) rc = build_table(p, o, false, &p->eval[o]);
+    if (rc != PINN_OK) {
+      pinn_plan_destroy(p);
+      return rc;
+    }
+  }
+  p->rows_max = 3 * p->num_sms;
+  p->ws_bytes = (size_t)p->rows_max * (size_t)(p->P + p->T) * sizeof(float);
+  if (cudaMalloc(&p->ws, p->ws_bytes) != cudaSuccess) {
+    pinn_plan_destroy(p);
+    return fail(PINN_E_ALLOC, "cannot allocate %zu workspace bytes", p->ws_bytes);
+  }
+  // opt in to the large dynamic shared memory once, for every kernel the plan can launch
+  for (int o = 0; o < 3; ++o)
+    for (int tr = 0; tr < 2; ++tr) {
+      FusedKernel k;
+      pick_kernel(p->mlp, o, tr != 0, &k);
+      cudaError_t e = cudaFuncSetAttribute((const void*)k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, k.smem_bytes);
+      if (e != cudaSuccess) {
+        pinn_plan_destroy(p);
+        return fail(PINN_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", k.smem_bytes, cudaGetErrorString(e));
+      }
+    }
+  *out = p;
+  return PINN_OK;
+}
+
+extern "C" int pinn_plan_destroy(pinn_plan* p) {
+  if (!p) return PINN_OK;
+  cudaSetDevice(p->device);
+  for (int o = 0; o < 3; ++o) {
+    if (p->train[o].segs_dev) cudaFree(p->train[o].segs_dev);
+    if (p->eval[o].segs_dev) cudaFree(p->eval[o].segs_dev);
+  }
+  if (p->ws) cudaFree(p->ws);
+  for (int o = 0; o < 3; ++o) {
+    if (p->ev0[o]) cudaEventDestroy(p->ev0[o]);
+    if (p->ev1[o]) cudaEventDestroy(p->ev1[o]);
+  }
+  delete p;
+  return PINN_OK;
+}
+
+extern "C" int64_t pinn_plan_param_count(const pinn_plan* p) { return p ? p->P : 0; }
+extern "C" int32_t pinn_plan_term_count(const pinn_plan* p) { return p ? p->T : 0; }
+extern "C" size_t pinn_plan_workspace_bytes(const pinn_plan* p) { return p ? p->ws_bytes : 0; }
+extern "C" const char* pinn_plan_engine(const pinn_plan* p) { return p ? p->engine : ""; }
+extern "C" int32_t pinn_plan_last_launch_count(const pinn_plan* p) { return p ? p->last_launches : 0; }
+
+extern "C" int pinn_plan_enable_timing(pinn_plan* p, int32_t on) {
+  if (!p) return fail(PINN_E_INVALID, "null plan");
+  if (on && !p->ev0[0]) {
+    CUDA_TRY(cudaSetDevice(p->device));
+    for (int o = 0; o < 3; ++o) {
+      CUDA_TRY(cudaEventCreate(&p->ev0[o]));
+      CUDA_TRY(cudaEventCreate(&p->ev1[o]));
+    }
+  }
+  p->timing = on != 0;
+  return PINN_OK;
+}
+
+extern "C" int pinn_plan_kernel_time_ms(pinn_plan* p, int32_t order, float* ms_out) {
+  if (!p || !ms_out || order < 0 || order > 2) return fail(PINN_E_INVALID, "bad argument");
+  if (!p->ev_valid[order]) return fail(PINN_E_STATE, "no timed launch recorded for derivative order %d", order);
+  CUDA_TRY(cudaEventSynchronize(p->ev1[order]));
+  CUDA_TRY(cudaEventElapsedTime(ms_out, p->ev0[order], p->ev1[order]));
+  return PINN_OK;
+}
+
+extern "C" int pinn_plan_set_rhs(pinn_plan* p, int32_t set_index, int32_t term_index, const float* rhs_dev) {
+  if (!p || set_index < 0 || set_index >= (int)p->sets.size()) return fail(PINN_E_INVALID, "bad set index");
+  pinn_pointset_desc& ps = p->sets[set_index];
+  if (term_index < 0 || term_index >= ps.n_terms) return fail(PINN_E_INVALID, "bad term index");
+  ps.terms[term_index].rhs_dev = rhs_dev;
+  // rebuild the two tables of this derivative order (rare operation; synchronous)
+  CUDA_TRY(cudaSetDevice(p->device));
+  const int o = ps.deriv_order;
+  if (p->train[o].segs_dev) { cudaFree(p->train[o].segs_dev); p->train[o].segs_dev = nullptr; }
+  if (p->eval[o].segs_dev) { cudaFree(p->eval[o].segs_dev); p->eval[o].segs_dev = nullptr; }
+  int rc = build_table(p, o, true, &p->train[o]);
+  if (rc == PINN_OK) rc = build_table(p, o, false, &p->eval[o]);
+  return rc;
+}
+
+static int run(pinn_plan* p, const float* params, float* out, cudaStream_t st, bool train) {
+  if (!p || !params || !out) return fail(PINN_E_INVALID, "null argument");
+  const int stride = (int)(p->P + p->T);
+  int rows = 0, launches = 0;
+  const int aligned = ((uintptr_t)params & 15u) == 0;
+  // big derivative order first: the collocation kernel dominates
+  for (int o = 2; o >= 0; --o) {
+    const LaunchTable& lt = train ? p->train[o] : p->eval[o];
+    if (lt.n_segs == 0) continue;
+    FusedKernel k;
+    if (!pick_kernel(p->mlp, o, train, &k)) return fail(PINN_E_INVALID, "no kernel");
+    int grid = (lt.total_chunks + k.nw - 1) / k.nw;
+    if (grid > p->num_sms) grid = p->num_sms;
+    if (rows + grid > p->rows_max) return fail(PINN_E_STATE, "workspace rows exhausted");
+    if (p->timing) CUDA_TRY(cudaEventRecord(p->ev0[o], st));
+    k.fn<<<grid, k.nw * 32, k.smem_bytes, st>>>(params, lt.segs_dev, lt.n_segs, lt.total_chunks,
+                                                p->ws + (size_t)rows * stride, stride, p->T, aligned);
+    CUDA_TRY(cudaGetLastError());
+    if (p->timing) {
+      CUDA_TRY(cudaEventRecord(p->ev1[o], st));
+      p->ev_valid[o] = true;
+    }
+    rows += grid;
+    ++launches;
+  }
+  const int i_begin = train ? 0 : (int)p->P;
+  const int count = stride - i_begin;
+  if (rows == 0) {
+    CUDA_TRY(cudaMemsetAsync(out + i_begin, 0, sizeof(float) * count, st));
+  } else if (count > 0) {
+    finalize_rows_kernel<<<(count + 127) / 128, 128, 0, st>>>(p->ws, rows, stride, i_begin, out);
+    CUDA_TRY(cudaGetLastError());
+    ++launches;
+  }
+  p->last_launches = launches;
+  return PINN_OK;
+}
+
+extern "C" int pinn_loss_and_grad(pinn_plan* p, const float* params_dev, float* out_dev, void* stream) {
+  return run(p, params_dev, out_dev, (cudaStream_t)stream, true);
+}
+
+extern "C" int pinn_loss(pinn_plan* p, const float* params_dev, float* out_dev, void* stream) {
+  return run(p, params_dev, out_dev, (cudaStream_t)stream, false);
+}
+
+extern "C" int pinn_forward(const pinn_mlp_desc* mlp, const float* params_dev, const float* points_dev, int64_t n,
+                            float* y_dev, int32_t device, void* stream) {
+  if (!mlp || !params_dev || (n > 0 && (!points_dev || !y_dev))) return fail(PINN_E_INVALID, "null argument");
+  if (n <= 0) return PINN_OK;
+  FusedKernel k;
+  if (!pick_kernel(*mlp, 0, false, &k))
+    return fail(PINN_E_INVALID, "no engine for MLP d=%d H=%d L=%d O=%d", mlp->in_dim, mlp->width, mlp->n_hidden,
+                mlp->out_dim);
+  CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int num_sms = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
+  CUDA_TRY(cudaFuncSetAttribute((const void*)k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, k.smem_bytes));
+  SegDev sd;
+  memset(&sd, 0, sizeof(sd));
+  sd.pts = points_dev;
+  sd.y_out = y_dev;
+  sd.n = n;
+  sd.n_chunks = (int)((n + kChunk - 1) / kChunk);
+  SegDev* sd_dev = nullptr;
+  CUDA_TRY(cudaMallocAsync(&sd_dev, sizeof(SegDev), st));
+  CUDA_TRY(cudaMemcpyAsync(sd_dev, &sd, sizeof(SegDev), cudaMemcpyHostToDevice, st));
+  int grid = (sd.n_chunks + k.nw - 1) / k.nw;
+  if (grid > num_sms) grid = num_sms;
+  const int aligned = ((uintptr_t)params_dev & 15u) == 0;
+  k.fn<<<grid, k.nw * 32, k.smem_bytes, st>>>(params_dev, sd_dev, 1, sd.n_chunks, nullptr, 0, 0, aligned);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaFreeAsync(sd_dev, st));
+  return PINN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// NCCL through the library already loaded in the process (torch bundles libnccl.so.2)
+// ------------------------------------------------------------------------------------------------
+struct nccl_uid { char internal[128]; };
+typedef int (*nccl_get_uid_fn)(nccl_uid*);
+typedef int (*nccl_init_rank_fn)(void**, int, nccl_uid, int);
+typedef int (*nccl_destroy_fn)(void*);
+typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef const char* (*nccl_errstr_fn)(int);
+
+static struct {
+  void* h = nullptr;
+  nccl_get_uid_fn get_uid = nullptr;
+  nccl_init_rank_fn init_rank = nullptr;
+  nccl_destroy_fn destroy = nullptr;
+  nccl_allreduce_fn allreduce = nullptr;
+  nccl_errstr_fn errstr = nullptr;
+} g_nccl;
+
+static int nccl_load() {
+  if (g_nccl.h) return PINN_OK;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return fail(PINN_E_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+  g_nccl.get_uid = (nccl_get_uid_fn)dlsym(h, "ncclGetUniqueId");
+  g_nccl.init_rank = (nccl_init_rank_fn)dlsym(h, "ncclCommInitRank");
+  g_nccl.destroy = (nccl_destroy_fn)dlsym(h, "ncclCommDestroy");
+  g_nccl.allreduce = (nccl_allreduce_fn)dlsym(h, "ncclAllReduce");
+  g_nccl.errstr = (nccl_errstr_fn)dlsym(h, "ncclGetErrorString");
+  if (!g_nccl.get_uid || !g_nccl.init_rank || !g_nccl.destroy || !g_nccl.allreduce)
+    return fail(PINN_E_NCCL, "libnccl is missing a required symbol");
+  g_nccl.h = h;
+  return PINN_OK;
+}
+
+static int nccl_fail(const char* what, int rc) {
+  return fail(PINN_E_NCCL, "%s: %s", what, g_nccl.errstr ? g_nccl.errstr(rc) : "nccl error");
+}
+
+extern "C" int pinn_nccl_unique_id(void* id128_out) {
+  if (!id128_out) return fail(PINN_E_INVALID, "null argument");
+  int rc = nccl_load();
+  if (rc) return rc;
+  nccl_uid id;
+  int n = g_nccl.get_uid(&id);
+  if (n) return nccl_fail("ncclGetUniqueId", n);
+  memcpy(id128_out, &id, sizeof(id));
+  return PINN_OK;
+}
+
+extern "C" int pinn_comm_create(const void* id128, int32_t world, int32_t rank, int32_t device, void** comm_out) {
+  if (!id128 || !comm_out) return fail(PINN_E_INVALID, "null argument");
+  int rc = nccl_load();
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(device));
+  nccl_uid id;
+  memcpy(&id, id128, sizeof(id));
+  void* comm = nullptr;
+  int n = g_nccl.init_rank(&comm, world, id, rank);
+  if (n) return nccl_fail("ncclCommInitRank", n);
+  *comm_out = comm;
+  return PINN_OK;
+}
+
+extern "C" int pinn_comm_destroy(void* comm) {
+  if (!comm) return PINN_OK;
+  int rc = nccl_load();
+  if (rc) return rc;
+  int n = g_nccl.destroy(comm);
+  return n ? nccl_fail("ncclCommDestroy", n) : PINN_OK;
+}
+
+extern "C" int pinn_allreduce_sum(void* comm, float* buf_dev, int64_t count, void* stream) {
+  if (!comm || !buf_dev || count < 0) return fail(PINN_E_INVALID, "bad argument");
+  int rc = nccl_load();
+  if (rc) return rc;
+  int n = g_nccl.allreduce(buf_dev, buf_dev, (size_t)count, /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm, (cudaStream_t)stream);
+  return n ? nccl_fail("ncclAllReduce", n) : PINN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Adam (Keras 2.7 update rule) on the flat vector
+// ------------------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ theta, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float step_size, float b1, float b2, float eps) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i];
+  const float mi = fmaf(b1, m[i], (1.f - b1) * gi);
+  const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+  m[i] = mi;
+  v[i] = vi;
+  theta[i] -= step_size * mi / (sqrtf(vi) + eps);
+}
+
+extern "C" int pinn_adam_step(float* params_dev, const float* grad_dev, float* m_dev, float* v_dev, int64_t count,
+                              float lr, float beta1, float beta2, float eps, int64_t step, void* stream) {
+  if (!params_dev || !grad_dev || !m_dev || !v_dev || count < 0 || step < 1) return fail(PINN_E_INVALID, "bad argument");
+  if (count == 0) return PINN_OK;
+  const double t = (double)step;
+  const float step_size = (float)(lr * sqrt(1.0 - pow((double)beta2, t)) / (1.0 - pow((double)beta1, t)));
+  adam_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params_dev, grad_dev, m_dev, v_dev,
+                                                                                  count, step_size, beta1, beta2, eps);
+  CUDA_TRY(cudaGetLastError());
+  return PINN_OK;
+}

@@ -1,0 +1,158 @@
+"""GPU parity: CUDA loss step (through the facade and the C ABI) vs the float64 oracles on identical
+weights and points.  Tolerances are the north-star's: 1e-5 relative on loss values, 1e-4 relative L2
+on the parameter gradient."""
+import numpy as np
+import pytest
+import torch
+
+import pinns_fluid_dynamics_b200 as ns
+from pinns_fluid_dynamics_b200 import loss_tables, problems
+from pinns_fluid_dynamics_b200.engine import assemble_losses
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-5
+GRAD_RTOL = 1e-4
+
+SMALL = {
+    "poisson": dict(),
+    "poisson_misto": dict(),
+    "poiseuille_flow": dict(PDE=1000, BC=100, Vel=10, Pres=0, Test=100),
+    "colliding_flow": dict(PDE=1000, BC=100, Vel=5, Pres=1, Test=100),
+    "cavity_steady": dict(PDE=1000, BC=100, Vel=100, Pres=1, Test=100, noise_bnd=0.01, noise_fit=0.01),
+    "cavity_unsteady": dict(PDE=1000, BC=100, IC=100, Vel=3, Pres=1, Test=100, noise_bnd=0.05, noise_fit=0.05,
+                            n_times=4),
+}
+
+
+def _setup(name, kw, seed=1, bias_std=0.1, faithful=True):
+    from oracle import reference_step
+    data = problems.BUILDERS[name](seed=seed, **kw)
+    var = reference_step.glorot_uniform_variables(data.dim, data.hidden, data.out_dim, seed=seed + 10, bias_std=bias_std)
+    model = ns.TanhMLP(data.dim, data.hidden, data.out_dim, device="cuda")
+    model.set_weights([v.numpy() for v in var])
+    losses, ltest = loss_tables.build_loss_table(data, faithful=faithful)
+    pb = ns.OptimizationProblem(model.variables, losses, ltest)
+    return data, var, model, pb
+
+
+def _rel(a, b):
+    return abs(a - b) / max(abs(b), 1e-300)
+
+
+@pytest.mark.parametrize("name", list(SMALL))
+@pytest.mark.parametrize("bias_std", [0.0, 0.1])
+def test_step_matches_reference_restatement(name, bias_std):
+    """vs oracle/reference_step.py: nested reverse-mode, one forward per term, the scripts' closures."""
+    from oracle import reference_step
+    data, var, model, pb = _setup(name, SMALL[name], bias_std=bias_std)
+    total, values, grad = pb.evaluate()
+    ref = reference_step.build(data, var)
+    ref_values, ref_total, ref_grad = ref.loss_and_grad()
+    assert [l.name for l in pb.losses] == [l.name for l in ref.losses]
+    assert _rel(total, ref_total) < LOSS_RTOL
+    for l, v, rv in zip(pb.losses, values, ref_values):
+        if rv == 0.0:
+            assert v == 0.0, l.name          # quirk Q1: identically-zero mass residual
+        else:
+            assert _rel(v, rv) < LOSS_RTOL, (l.name, v, rv)
+    g = grad.double().cpu().numpy()
+    rg = ref_grad.numpy()
+    assert np.linalg.norm(g - rg) / np.linalg.norm(rg) < GRAD_RTOL
+    # test losses (forward only)
+    _, _, test_vals = pb.evaluate_all()
+    for v, rv in zip(test_vals, ref.test_values()):
+        assert _rel(v, rv) < LOSS_RTOL
+
+
+@pytest.mark.parametrize("name", ["colliding_flow", "poiseuille_flow", "cavity_steady"])
+def test_corrected_residuals_match_taylor_oracle(name):
+    """faithful=False (in-tape divergence, -laplacian) vs the Taylor-mode oracle."""
+    from oracle import taylor
+    data, var, model, pb = _setup(name, SMALL[name], faithful=False)
+    total, values, grad = pb.evaluate()
+    theta = torch.cat([v.reshape(-1) for v in var]).numpy()
+    out = taylor.loss_and_grad(pb.compiled, theta)
+    ref_total, ref_vals, _ = assemble_losses(pb.compiled, out[pb.compiled.n_params:])
+    assert _rel(total, ref_total) < LOSS_RTOL
+    for v, rv in zip(values, ref_vals):
+        assert _rel(v, rv) < LOSS_RTOL
+    g = grad.double().cpu().numpy()
+    rg = out[:pb.compiled.n_params]
+    assert np.linalg.norm(g - rg) / np.linalg.norm(rg) < GRAD_RTOL
+
+
+@pytest.mark.parametrize("n_pde", [1, 15, 16, 17, 33, 4097])
+def test_ragged_point_counts(n_pde):
+    """chunk tails: point counts that are not a multiple of the 16-point warp chunk."""
+    from oracle import taylor
+    kw = dict(PDE=n_pde, BC=7, Vel=3, Pres=1, Test=5, noise_bnd=0.01, noise_fit=0.01)
+    data, var, model, pb = _setup("cavity_steady", kw)
+    total, values, grad = pb.evaluate()
+    theta = torch.cat([v.reshape(-1) for v in var]).numpy()
+    out = taylor.loss_and_grad(pb.compiled, theta)
+    ref_total, ref_vals, _ = assemble_losses(pb.compiled, out[pb.compiled.n_params:])
+    assert _rel(total, ref_total) < LOSS_RTOL
+    g = grad.double().cpu().numpy()
+    rg = out[:pb.compiled.n_params]
+    assert np.linalg.norm(g - rg) / np.linalg.norm(rg) < GRAD_RTOL
+
+
+def test_empty_fit_set_gives_nan_like_reference():
+    """Q3: Fit_p over an empty point set is a mean over nothing -> NaN, and it poisons the total."""
+    kw = dict(PDE=64, BC=8, Vel=3, Pres=0, Test=5)
+    data, var, model, pb = _setup("cavity_steady", kw)
+    total, values, grad = pb.evaluate()
+    names = [l.name for l in pb.losses]
+    assert np.isnan(values[names.index("Fit_p")])
+    assert np.isnan(total)
+    assert torch.isfinite(grad).all()
+
+
+def test_large_set_against_taylor_oracle():
+    """100k collocation points (Colliding_Flow BASELINE size) vs the Taylor oracle."""
+    from oracle import taylor
+    kw = dict(PDE=100_000, BC=100, Vel=5, Pres=1, Test=100)
+    data, var, model, pb = _setup("colliding_flow", kw, faithful=False)
+    total, values, grad = pb.evaluate()
+    theta = torch.cat([v.reshape(-1) for v in var]).numpy()
+    out = taylor.loss_and_grad(pb.compiled, theta)
+    ref_total, _, _ = assemble_losses(pb.compiled, out[pb.compiled.n_params:])
+    assert _rel(total, ref_total) < LOSS_RTOL
+    g = grad.double().cpu().numpy()
+    rg = out[:pb.compiled.n_params]
+    assert np.linalg.norm(g - rg) / np.linalg.norm(rg) < GRAD_RTOL
+
+
+def test_determinism_run_to_run():
+    data, var, model, pb = _setup("cavity_steady", SMALL["cavity_steady"])
+    a = pb.plan.loss_and_grad(pb.flat).clone()
+    b = pb.plan.loss_and_grad(pb.flat).clone()
+    assert torch.equal(a, b)
+
+
+def test_model_forward_matches_oracle():
+    from oracle.nisaba_like import KerasMLP
+    data, var, model, pb = _setup("cavity_steady", SMALL["cavity_steady"])
+    x = torch.rand(1003, 2, dtype=torch.float32)
+    y = model(x.cuda()).double().cpu()
+    ref = KerasMLP(var)(x.double()).detach()
+    assert torch.allclose(y, ref, rtol=0, atol=2e-6)
+
+
+def test_linearity_in_weights_at_full_size():
+    """size-independent property at the BASELINE size (1M collocation points): the gradient of the
+    weighted loss is linear in the term weights."""
+    kw = dict(PDE=1_000_000, BC=1000, Vel=100, Pres=1, Test=100, noise_bnd=0.01, noise_fit=0.01)
+    data = problems.cavity_steady(seed=1, **kw)
+    model = ns.TanhMLP(2, [32, 32, 32], 3, device="cuda", seed=3)
+    losses, ltest = loss_tables.build_loss_table(data)
+    pb1 = ns.OptimizationProblem(model.variables, losses, ltest)
+    _, vals1, g1 = pb1.evaluate()
+    g1 = g1.clone()
+    for l in losses:
+        l.weight *= 2.0
+    pb2 = ns.OptimizationProblem(model.variables, losses, ltest)
+    _, vals2, g2 = pb2.evaluate()
+    assert np.allclose(vals1, vals2, rtol=1e-6)
+    assert torch.allclose(2.0 * g1, g2, rtol=1e-4, atol=1e-6 * float(g2.abs().max()))

@@ -154,8 +154,15 @@ def _fit_targets(data: ProblemData, grid: np.ndarray, fields_norm: Sequence[np.n
     data.sol_test = [f[idx["Test"]] for f in fields_norm]
 
 
+def _split_counts(n_pts: Dict[str, int], n_grid: int) -> Dict[str, int]:
+    """Counts handed to the permutation split.  A collocation request that fits the grid is taken
+    from it like the reference does; a larger one (BASELINE sizes) is sampled uniformly instead and
+    takes no grid vertices, so the Vel / Pres / Test subsets keep their requested sizes."""
+    return {**n_pts, "PDE": n_pts["PDE"] if n_pts["PDE"] <= n_grid else 0}
+
+
 def _collocation(grid, idx, n_pde, rng, lo, hi) -> np.ndarray:
-    if n_pde <= len(idx["PDE"]) or n_pde <= grid.shape[0]:
+    if n_pde <= grid.shape[0]:
         return grid[idx["PDE"]]
     lo, hi = np.asarray(lo, dtype=np.float64), np.asarray(hi, dtype=np.float64)
     return lo + rng.random((n_pde, len(lo))) * (hi - lo)
@@ -226,7 +233,7 @@ def cavity_steady(options: Optional[SimulationOptions] = None, seed: int = 1, fe
     rng = np.random.default_rng(seed)
     d = ProblemData("cavity_steady", 2, [32, 32, 32], 3, o)
     grid = build_grid(0, 1, 0, 1, 100, 100)
-    idx = split_indices(grid.shape[0], {**o.n_pts, "PDE": min(o.n_pts["PDE"], grid.shape[0])}, rng)
+    idx = split_indices(grid.shape[0], _split_counts(o.n_pts, grid.shape[0]), rng)
     u_ex, v_ex, p_ex = fem_fields if fem_fields is not None else synthetic_cavity_field(grid, lid_velocity)
     d.consts = {"norm_vel": max(spread(u_ex), spread(v_ex)), "norm_pre": spread(p_ex)}
     fields_norm = [u_ex / d.norm_vel, v_ex / d.norm_vel, p_ex / d.norm_pre]
@@ -250,7 +257,7 @@ def cavity_unsteady(options: Optional[SimulationOptions] = None, seed: int = 1, 
     time_vec = np.arange(0.0, T, dt)[:n_times]
     grid2 = build_grid(0, 1, 0, 1, 100, 100)
     grid = build_grid(0, 1, 0, 1, 100, 100, times=time_vec)
-    idx = split_indices(grid.shape[0], {**o.n_pts, "PDE": min(o.n_pts["PDE"], grid.shape[0])}, rng)
+    idx = split_indices(grid.shape[0], _split_counts(o.n_pts, grid.shape[0]), rng)
     u_ex, v_ex, p_ex = synthetic_cavity_field(grid[:, 1:], lid_velocity, t=grid[:, 0], T=T)
     # per-time-step mean subtraction of the pressure (cavity_unsteady.py:109)
     n2 = grid2.shape[0]
@@ -277,7 +284,7 @@ def colliding_flow(options: Optional[SimulationOptions] = None, seed: int = 1, *
     u_f = lambda x: 20 * x[:, 0] * x[:, 1] ** 3
     v_f = lambda x: 5 * x[:, 0] ** 4 - 5 * x[:, 1] ** 4
     grid = build_grid(-1, 1, -1, 1, 100, 100)
-    idx = split_indices(grid.shape[0], {**o.n_pts, "PDE": min(o.n_pts["PDE"], grid.shape[0])}, rng)
+    idx = split_indices(grid.shape[0], _split_counts(o.n_pts, grid.shape[0]), rng)
     u_ex, v_ex, p_ex = u_f(grid), v_f(grid), p_f(grid)
     d.consts = {"norm_vel": max(spread(u_ex), spread(v_ex)), "norm_pre": spread(p_ex)}
     fields_norm = [u_ex / d.norm_vel, v_ex / d.norm_vel, p_ex / d.norm_pre]
@@ -302,7 +309,7 @@ def poiseuille_flow(options: Optional[SimulationOptions] = None, seed: int = 1, 
     u_f = lambda x: -P_x * x[:, 1] * (2 - x[:, 1] / delta) * delta / (2 * mu)
     v_f = lambda x: 0 * x[:, 0]
     grid = build_grid(lx, ux, ly, uy, 100, 25)
-    idx = split_indices(grid.shape[0], {**o.n_pts, "PDE": min(o.n_pts["PDE"], grid.shape[0])}, rng)
+    idx = split_indices(grid.shape[0], _split_counts(o.n_pts, grid.shape[0]), rng)
     u_ex, v_ex, p_ex = u_f(grid), v_f(grid), p_f(grid)
     d.consts = {"norm_vel": max(spread(u_ex), spread(v_ex)), "norm_pre": spread(p_ex), "rho": rho, "mu": mu}
     fields_norm = [u_ex / d.norm_vel, v_ex / d.norm_vel, p_ex / d.norm_pre]

@@ -40,6 +40,13 @@ def _rel(a, b):
     return abs(a - b) / max(abs(b), 1e-300)
 
 
+def _term_close(v, rv):
+    """Per-term check.  A term's value is a mean of squared roots r = (O(1) network output) - (O(1)
+    target); FP32 leaves an absolute error of ~1 ulp of the operands in r, i.e. 2*sqrt(value)*1e-7 in
+    the value -- that floor matters only for terms that are themselves ~1e-8 (single-point fits)."""
+    return abs(v - rv) <= LOSS_RTOL * abs(rv) + 2e-7 * np.sqrt(abs(rv))
+
+
 @pytest.mark.parametrize("name", list(SMALL))
 @pytest.mark.parametrize("bias_std", [0.0, 0.1])
 def test_step_matches_reference_restatement(name, bias_std):
@@ -55,14 +62,14 @@ def test_step_matches_reference_restatement(name, bias_std):
         if rv == 0.0:
             assert v == 0.0, l.name          # quirk Q1: identically-zero mass residual
         else:
-            assert _rel(v, rv) < LOSS_RTOL, (l.name, v, rv)
+            assert _term_close(v, rv), (l.name, v, rv)
     g = grad.double().cpu().numpy()
     rg = ref_grad.numpy()
     assert np.linalg.norm(g - rg) / np.linalg.norm(rg) < GRAD_RTOL
     # test losses (forward only)
     _, _, test_vals = pb.evaluate_all()
     for v, rv in zip(test_vals, ref.test_values()):
-        assert _rel(v, rv) < LOSS_RTOL
+        assert _term_close(v, rv)
 
 
 @pytest.mark.parametrize("name", ["colliding_flow", "poiseuille_flow", "cavity_steady"])
@@ -76,7 +83,7 @@ def test_corrected_residuals_match_taylor_oracle(name):
     ref_total, ref_vals, _ = assemble_losses(pb.compiled, out[pb.compiled.n_params:])
     assert _rel(total, ref_total) < LOSS_RTOL
     for v, rv in zip(values, ref_vals):
-        assert _rel(v, rv) < LOSS_RTOL
+        assert _term_close(v, rv)
     g = grad.double().cpu().numpy()
     rg = out[:pb.compiled.n_params]
     assert np.linalg.norm(g - rg) / np.linalg.norm(rg) < GRAD_RTOL

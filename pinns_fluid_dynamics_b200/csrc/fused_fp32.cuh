@@ -182,10 +182,8 @@ __device__ __forceinline__ void warp_gemm(const float* __restrict__ in, const fl
 #pragma unroll
     for (int c = 0; c < C; ++c)
 #pragma unroll
-      for (int jj = 0; jj < TC; ++jj) {
-        acc[c][jj].x = fmaf(a[c].x, w[jj], acc[c][jj].x);
-        acc[c][jj].y = fmaf(a[c].y, w[jj], acc[c][jj].y);
-      }
+      for (int jj = 0; jj < TC; ++jj)   // packed FFMA2: both points of the lane, weight broadcast (R.F32 operand)
+        acc[c][jj] = __ffma2_rn(a[c], make_float2(w[jj], w[jj]), acc[c][jj]);
   }
 }
 

@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- collocation points per second per PINN training step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config Cavity_Steady] [--impl ours|reference]
+
+One "step" = forward jets + Navier-Stokes residuals + weighted mean-square loss + parameter
+gradients (+ all-reduce of the [P+T] vector when N>1) + Adam update, on the BASELINE workload
+(default: Cavity_Steady, 1 000 000 synthetic collocation points PER GPU -> weak scaling, plus the
+script's 4x1000 boundary, 100 velocity and 1 pressure fitting points).
+
+Printed keys (one JSON line on rank 0):
+  value      whole-job pts/s with inputs resident in HBM (device-timed per step, L2 flushed between steps)
+  e2e        the same through the public facade with HOST inputs: every step copies all point / target
+             arrays from pinned host memory, runs the step, and reads the per-term sums back
+  roofline   the collocation kernel (fused_step_kernel<...,ORDER=2,TRAIN>) against the MEASURED FP32
+             FFMA peak of this pool's B200 (profiles/fp32_peak_r01.json; MEASURED_PEAKS.json holds no
+             FP32 figure)
+  cpu_baseline   oracle/reference_step.py (torch float64 nested autodiff, the reference's step
+             structure) timed on this box's host cores on a bounded sample
+`--impl reference` times that CPU restatement alone (the real nisaba/TensorFlow stack cannot be
+installed: see DESIGN.md) on the same config/metric/unit.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CPU_SAMPLE_PDE = 20_000
+
+
+def flops_per_point(d, H, L, O, C):
+    """matmul FLOPs only, 2 per MAC, step = 3 x forward."""
+    return 3 * (2 * d * H + (L - 1) * C * 2 * H * H + C * 2 * H * O)
+
+
+class ClockSampler(threading.Thread):
+    """SM clock / throttle reasons during the timed regions (NVML, 10 ms period)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self.active = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            if self.active.is_set():
+                try:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    try:
+                        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for bit, name in names.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+            time.sleep(0.01)
+
+    def stop(self):
+        self._stop.set()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def cpu_reference_step_rate(config: str, steps: int, warmup: int, sample_pde: int = CPU_SAMPLE_PDE):
+    """Time oracle/reference_step.py (the reference's step structure, torch float64, all host
+    threads) on a bounded sample of the workload.  Returns (pts/s, ms/step, cores, sample text)."""
+    import numpy as np
+    import torch
+    from oracle import reference_step
+    from pinns_fluid_dynamics_b200 import problems
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    data = problems.build_baseline_config(config, seed=1, PDE=sample_pde)
+    var = reference_step.glorot_uniform_variables(data.dim, data.hidden, data.out_dim, seed=3)
+    pb = reference_step.build(data, var)
+    theta = [v.detach().clone() for v in pb.variables]
+    m = [torch.zeros_like(v) for v in theta]
+    v2 = [torch.zeros_like(v) for v in theta]
+
+    def one_step(t):
+        _, _, grad = pb.loss_and_grad()
+        off = 0
+        with torch.no_grad():   # Adam(1e-2) like cavity_steady.py:246
+            for i, p in enumerate(pb.variables):
+                g = grad[off:off + p.numel()].view_as(p); off += p.numel()
+                m[i].mul_(0.9).add_(g, alpha=0.1)
+                v2[i].mul_(0.999).addcmul_(g, g, value=0.001)
+                step = 1e-2 * (1 - 0.999 ** t) ** 0.5 / (1 - 0.9 ** t)
+                p.addcdiv_(m[i], v2[i].sqrt().add_(1e-7), value=-step)
+
+    for i in range(warmup):
+        one_step(i + 1)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        one_step(warmup + i + 1)
+    dt = time.perf_counter() - t0
+    sample = (f"{config}: {sample_pde} of the collocation points + all boundary/fit sets, "
+              f"{steps} steps after {warmup} warm-up, torch {torch.__version__} float64")
+    return sample_pde * steps / dt, dt / steps * 1e3, torch.get_num_threads(), sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    value, ms, cores, sample = cpu_reference_step_rate(args.config, args.steps, max(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": "collocation_points_per_second_per_training_step", "value": value,
+        "unit": "pts/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.config}: bounded CPU sample of {CPU_SAMPLE_PDE} collocation points per step "
+                               "+ the script's boundary/fit sets, tanh MLP of the config"},
+        "cpu_baseline": {"value": value, "unit": "pts/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "pts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "CPU restatement of the reference's nisaba/TensorFlow step (oracle/reference_step.py); "
+                "TensorFlow 2.7 and nisaba are not installable in this image",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import pinns_fluid_dynamics_b200 as ns
+    from pinns_fluid_dynamics_b200 import loss_tables, problems
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    per_gpu = args.pde_per_gpu or problems.BASELINE_CONFIGS[args.config]["PDE"]
+    data = problems.build_baseline_config(args.config, seed=1, PDE=per_gpu * world)
+    model = ns.TanhMLP(data.dim, data.hidden, data.out_dim, device=dev, seed=3)
+    # benchmark the full Navier-Stokes residual: in-tape mass term everywhere
+    faithful = data.name.startswith("cavity")
+    losses, ltest = loss_tables.build_loss_table(data, faithful=faithful)
+    pb = ns.OptimizationProblem(model.variables, losses, ltest)
+    opt = ns.Adam(learning_rate=1e-2)
+    plan = pb.plan
+    d, H, L, O = pb.compiled.mlp
+    n_local_pde = sum(cs.n_local for cs in pb.compiled.sets if cs.deriv_order == 2 and cs.pointset.name == "PDE")
+    n_global_pde = per_gpu * world
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up ---------------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        pb.training_step(opt)
+    launches_per_step = plan.last_launch_count() + 1   # + Adam kernel
+    barrier()
+
+    # ---- value: inputs resident in HBM, device-timed per step, L2 flushed between steps -----------
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    sampler.active.set()
+    for e0, e1 in ev:
+        flush.fill_(1.0)
+        e0.record()
+        pb.training_step(opt)
+        e1.record()
+    barrier()
+    sampler.active.clear()
+    ms_dev = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    t = torch.tensor([ms_dev], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev = float(t.item())
+    value = n_global_pde * args.steps / (ms_dev * 1e-3)
+
+    # ---- roofline: the collocation kernel alone, CUDA events around the launch inside the C ABI ----
+    plan.enable_timing(True)
+    kms = []
+    for _ in range(min(args.steps, 50)):
+        flush.fill_(1.0)
+        pb.training_step(opt)
+        kms.append(plan.kernel_time_ms(2))
+    plan.enable_timing(False)
+    k_ms = float(np.mean(kms))
+    C = 3 + d
+    flop_launch = n_local_pde * flops_per_point(d, H, L, O, C)
+    achieved = flop_launch / (k_ms * 1e-3) * 1e-12
+    peak, peak_src = 71.7, "fallback"
+    try:
+        with open(os.path.join(ROOT, "profiles", "fp32_peak_r01.json")) as fh:
+            pk = json.load(fh)
+        peak, peak_src = max(pk["ffma_chain_tflops"], pk["ffma2_chain_tflops"]), "profiles/fp32_peak_r01.json (tools/fp32_peak.cu on this pool)"
+    except Exception:
+        pass
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")) as fh:
+            tr = json.load(fh)
+        traffic = tr["dram_bytes_per_point"] * n_local_pde
+    except Exception:
+        pass
+
+    # ---- e2e: host-resident inputs, H2D every step, D2H of the per-term sums every step ----------
+    h2d = plan.pin_host_inputs()
+    T = max(1, pb.compiled.n_out_terms)
+    host_out = torch.empty(T, dtype=torch.float32).pin_memory()
+    for _ in range(3):
+        plan.upload_inputs(); s = pb.training_step(opt); host_out.copy_(s[:T], non_blocking=True); torch.cuda.synchronize()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.active.set()
+    e0.record()
+    for _ in range(args.steps):
+        plan.upload_inputs()
+        s = pb.training_step(opt)
+        host_out.copy_(s[:T], non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the caller reads the loss every step
+    e1.record()
+    barrier()
+    sampler.active.clear()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t.item())
+    e2e_value = n_global_pde * args.steps / (ms_e2e * 1e-3)
+    sampler.stop()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, ms, cores, sample = cpu_reference_step_rate(args.config, steps=5, warmup=2)
+        cpu = {"value": v, "unit": "pts/s", "cores": cores, "kind": "port", "sample": sample, "ms_per_step": ms}
+
+    if rank == 0:
+        line = {
+            "metric": "collocation_points_per_second_per_training_step", "value": value, "unit": "pts/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.config}: {per_gpu} uniform collocation points per GPU ({n_global_pde} total), "
+                                   f"{data.options.n_pts['BC']}x4 boundary, {data.options.n_pts['Vel']} velocity + "
+                                   f"{data.options.n_pts['Pres']} pressure fitting points, tanh MLP "
+                                   f"{d}-{H}x{L}-{O} ({pb.compiled.n_params} parameters), {len(losses)} loss terms",
+                       "engine": plan.engine, "parallelism": f"dp{world} (points sharded, NCCL all-reduce of {pb.compiled.n_params + T} floats)",
+                       "l2": "256 MiB device buffer rewritten between timed steps", "optimizer": "Adam(1e-2) update inside the step"},
+            "e2e": {"value": e2e_value, "unit": "pts/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(T * 4),
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "roofline": {"bound": "fp32_fma", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "fused_step_kernel<D,H,L,O,ORDER=2,TRAIN>", "kernel_ms": k_ms,
+                         "flop_per_point": flops_per_point(d, H, L, O, C), "points_per_launch": n_local_pde,
+                         "peak_source": peak_src,
+                         "hbm_GBps": (n_local_pde * 4 * d) / (k_ms * 1e-3) * 1e-9},
+            "cpu_baseline": cpu,
+            "clocks": sampler.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="Cavity_Steady")
+    ap.add_argument("--pde-per-gpu", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

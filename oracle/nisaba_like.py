@@ -158,9 +158,9 @@ class OptimizationProblem:
             grads = [torch.zeros_like(v) if g is None else g for g, v in zip(grads, self.variables)]
         else:
             grads = [torch.zeros_like(v) for v in self.variables]
-        return ([float(v) for v in values], float(total),
+        return ([float(v.detach()) for v in values], float(total.detach()),
                 torch.cat([g.reshape(-1) for g in grads]).detach())
 
     def test_values(self):
         with torch.enable_grad():
-            return [float(L()) for L in self.losses_test]
+            return [float(L().detach()) for L in self.losses_test]

@@ -207,6 +207,13 @@ class OptimizationProblem:
         out = self._reduce(self.plan.loss_and_grad(self.flat))
         return out[: self.compiled.n_params], self.plan.to_table_order(out)
 
+    def training_step(self, optimizer):
+        """One full training step, asynchronous: loss step (+ all-reduce) + optimiser update.
+        Returns the device vector of per-term sums of squares (table order)."""
+        grad, sumsq = self.loss_and_grad_device()
+        optimizer.apply(self.flat, grad)
+        return sumsq
+
     def evaluate(self):
         """(total loss, per-train-term values, flat gradient [P] on device)."""
         grad, sumsq = self.loss_and_grad_device()

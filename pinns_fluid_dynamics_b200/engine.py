@@ -166,6 +166,8 @@ class CudaPlan:
         self.cp = cp
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self._keep = []
+        self._inputs = []          # (host numpy shard, device tensor) of every point / rhs array
+        self._pinned = None
         descs = (_capi.PointSetDesc * max(1, len(cp.sets)))()
         self._pts_cache: Dict[int, "torch.Tensor"] = {}
         for si, cs in enumerate(cp.sets):
@@ -174,6 +176,8 @@ class CudaPlan:
             if key not in self._pts_cache:
                 local = np.ascontiguousarray(cs.pointset.points[cs.start:cs.stop])
                 self._pts_cache[key] = torch.from_numpy(local).to(self.device)
+                if cs.n_local:
+                    self._inputs.append((local, self._pts_cache[key]))
             pts = self._pts_cache[key]
             ds.points_dev = pts.data_ptr() if cs.n_local else None
             ds.n_local = cs.n_local
@@ -188,8 +192,10 @@ class CudaPlan:
                 td.conv, td.conv_k, td.rhs_scale = float(t.form.conv), int(t.form.conv_k), float(t.form.rhs_scale)
                 rhs = t.form.rhs_array()
                 if rhs is not None and cs.n_local:
-                    r = torch.from_numpy(np.ascontiguousarray(rhs[cs.start:cs.stop])).to(self.device)
+                    r_host = np.ascontiguousarray(rhs[cs.start:cs.stop])
+                    r = torch.from_numpy(r_host).to(self.device)
                     self._keep.append(r)
+                    self._inputs.append((r_host, r))
                     td.rhs_dev = r.data_ptr()
                 else:
                     td.rhs_dev = None
@@ -237,6 +243,31 @@ class CudaPlan:
 
     def last_launch_count(self) -> int:
         return int(self.lib.pinn_plan_last_launch_count(self.handle))
+
+    # ---- host-resident inputs (end-to-end path: data arrives in host memory every step) -------
+    def pin_host_inputs(self) -> int:
+        """Stage every local point / rhs shard in pinned host memory; returns the byte count one
+        ``upload_inputs`` moves."""
+        import torch
+        if self._pinned is None:
+            self._pinned = [(torch.from_numpy(h).pin_memory(), d) for h, d in self._inputs]
+        return sum(h.numel() * h.element_size() for h, _ in self._pinned)
+
+    def upload_inputs(self) -> None:
+        """Host -> device copy of all inputs into the buffers the plan already points at (async on
+        the current stream)."""
+        if self._pinned is None:
+            self.pin_host_inputs()
+        for h, d in self._pinned:
+            d.copy_(h, non_blocking=True)
+
+    def enable_timing(self, on: bool = True) -> None:
+        _capi.check(self.lib.pinn_plan_enable_timing(self.handle, 1 if on else 0), "pinn_plan_enable_timing")
+
+    def kernel_time_ms(self, deriv_order: int = 2) -> float:
+        ms = C.c_float()
+        _capi.check(self.lib.pinn_plan_kernel_time_ms(self.handle, deriv_order, C.byref(ms)), "pinn_plan_kernel_time_ms")
+        return float(ms.value)
 
     def close(self):
         if getattr(self, "handle", None):

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "fused_fp32.cuh"
+#include "layered_fp32.cuh"
 
 using namespace pinn;
 
@@ -43,6 +44,7 @@ struct LaunchTable {
   int n_segs = 0;
   int total_chunks = 0;
   SegDev* segs_dev = nullptr;
+  std::vector<SegDev> segs_host;
 };
 
 struct pinn_plan {
@@ -59,6 +61,10 @@ struct pinn_plan {
   size_t ws_bytes = 0;
   int last_launches = 0;
   const char* engine = "fused_fp32";
+  bool layered = false;          // wide/deep networks: per-layer kernels over an HBM workspace
+  float* act = nullptr;          // layered: [L][C_max][batch][H] jets
+  float* wt = nullptr;           // layered: K_l^T copies, l = 2..L
+  long long batch = 0;           // layered: points per batch (multiple of 64)
   bool timing = false;
   cudaEvent_t ev0[3] = {nullptr, nullptr, nullptr}, ev1[3] = {nullptr, nullptr, nullptr};
   bool ev_valid[3] = {false, false, false};
@@ -135,6 +141,7 @@ static int build_table(pinn_plan* p, int order, bool train_only, LaunchTable* ou
     segs.push_back(sd);
   }
   out->order = order;
+  out->segs_host = segs;
   out->n_segs = (int)segs.size();
   out->total_chunks = chunk;
   out->segs_dev = nullptr;
@@ -143,6 +150,126 @@ static int build_table(pinn_plan* p, int order, bool train_only, LaunchTable* ou
     CUDA_TRY(cudaMemcpy(out->segs_dev, segs.data(), segs.size() * sizeof(SegDev), cudaMemcpyHostToDevice));
   }
   return PINN_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// layered engine: host orchestration
+// ------------------------------------------------------------------------------------------------
+static bool layered_supported(const pinn_mlp_desc& m) {
+  return (m.in_dim == 2 || m.in_dim == 3) && (m.width == 64 || m.width == 128) && m.n_hidden >= 2 && m.out_dim == 3;
+}
+
+static int layered_alloc(pinn_plan* p) {
+  const pinn_mlp_desc& m = p->mlp;
+  long long max_n = 0;
+  for (const auto& ps : p->sets) max_n = ps.n_local > max_n ? ps.n_local : max_n;
+  const long long per_point = (long long)m.n_hidden * kMaxCh * m.width * 4;   // bytes of jets per point
+  long long batch = (4LL << 30) / per_point;                                  // <= 4 GiB of activations
+  batch = (batch / 64) * 64;
+  const long long need = ((max_n + 63) / 64) * 64;
+  if (batch > need) batch = need;
+  if (batch < 64) batch = 64;
+  p->batch = batch;
+  p->ws_bytes = (size_t)batch * per_point + (size_t)(m.n_hidden - 1) * m.width * m.width * 4;
+  if (cudaMalloc(&p->act, (size_t)batch * per_point) != cudaSuccess)
+    return fail(PINN_E_ALLOC, "cannot allocate %lld activation bytes", batch * per_point);
+  if (cudaMalloc(&p->wt, (size_t)(m.n_hidden - 1) * m.width * m.width * 4) != cudaSuccess)
+    return fail(PINN_E_ALLOC, "cannot allocate transposed weights");
+  return PINN_OK;
+}
+
+template <int D, int H, int O, int ORDER>
+static int layered_run_set(pinn_plan* p, const float* params, float* out, cudaStream_t st, bool train,
+                           const SegDev& seg, const SegDev* seg_dev, int* launches) {
+  using namespace pinn::layered;
+  constexpr int C = n_channels(D, ORDER);
+  const int L = p->mlp.n_hidden;
+  const size_t layer_stride = (size_t)p->batch * kMaxCh * H;   // floats between Act[l] buffers
+  const int smem = gemm_smem_bytes<C>();
+  static bool attr_done = false;
+  if (!attr_done) {
+    CUDA_TRY(cudaFuncSetAttribute((const void*)fwd_layer_kernel<D, H, ORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(cudaFuncSetAttribute((const void*)bwd_layer_kernel<D, H, ORDER, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(cudaFuncSetAttribute((const void*)bwd_layer_kernel<D, H, ORDER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_done = true;
+  }
+  const int off_ko = D * H + H + (L - 1) * (H * H + H);
+  for (long long b0 = 0; b0 < seg.n; b0 += p->batch) {
+    const long long nb = (seg.n - b0 < p->batch) ? seg.n - b0 : p->batch;
+    const int tiles = (int)((nb + kTile - 1) / kTile);
+    layer1_kernel<D, H, ORDER><<<tiles, kThreads, 0, st>>>(params, seg.pts, seg.n, b0, p->act);
+    for (int l = 2; l <= L; ++l) {
+      const float* K = params + D * H + H + (size_t)(l - 2) * (H * H + H);
+      fwd_layer_kernel<D, H, ORDER><<<tiles, kThreads, smem, st>>>(K, K + H * H, p->act + (l - 2) * layer_stride,
+                                                                  p->act + (l - 1) * layer_stride);
+    }
+    int grid_out = (tiles * kTile + 7) / 8;
+    if (grid_out > 8 * p->num_sms) grid_out = 8 * p->num_sms;
+    float* actL = p->act + (size_t)(L - 1) * layer_stride;
+    if (train)
+      out_layer_kernel<D, H, O, ORDER, true><<<grid_out, 256, 0, st>>>(params, off_ko, seg_dev, b0, tiles, actL, out, out + p->P);
+    else
+      out_layer_kernel<D, H, O, ORDER, false><<<grid_out, 256, 0, st>>>(params, off_ko, seg_dev, b0, tiles, actL, out, out + p->P);
+    *launches += L + 1;
+    if (train) {
+      for (int l = L; l >= 2; --l) {
+        float* gK = out + D * H + H + (size_t)(l - 2) * (H * H + H);
+        int gw = tiles < 2 * p->num_sms ? tiles : 2 * p->num_sms;
+        wgrad_kernel<C, H><<<gw, kThreads, 2 * 32 * H * 4, st>>>(p->act + (l - 2) * layer_stride, p->act + (l - 1) * layer_stride,
+                                                                 tiles, gK, gK + H * H);
+        const float* WT = p->wt + (size_t)(l - 2) * H * H;
+        if (l > 2) {
+          bwd_layer_kernel<D, H, ORDER, false><<<tiles, kThreads, smem, st>>>(WT, p->act + (l - 1) * layer_stride,
+                                                                             p->act + (l - 2) * layer_stride, params, seg.pts,
+                                                                             seg.n, b0, tiles, out);
+        } else {
+          int gb = tiles < 2 * p->num_sms ? tiles : 2 * p->num_sms;
+          bwd_layer_kernel<D, H, ORDER, true><<<gb, kThreads, smem, st>>>(WT, p->act + (l - 1) * layer_stride,
+                                                                         p->act + (l - 2) * layer_stride, params, seg.pts,
+                                                                         seg.n, b0, tiles, out);
+        }
+        *launches += 2;
+      }
+    }
+    CUDA_TRY(cudaGetLastError());
+  }
+  return PINN_OK;
+}
+
+template <int D, int H, int O>
+static int layered_run_t(pinn_plan* p, const float* params, float* out, cudaStream_t st, bool train, int* launches) {
+  for (int o = 2; o >= 0; --o) {
+    const LaunchTable& lt = train ? p->train[o] : p->eval[o];
+    for (int s = 0; s < lt.n_segs; ++s) {
+      int rc;
+      if (o == 2) rc = layered_run_set<D, H, O, 2>(p, params, out, st, train, lt.segs_host[s], lt.segs_dev + s, launches);
+      else if (o == 1) rc = layered_run_set<D, H, O, 1>(p, params, out, st, train, lt.segs_host[s], lt.segs_dev + s, launches);
+      else rc = layered_run_set<D, H, O, 0>(p, params, out, st, train, lt.segs_host[s], lt.segs_dev + s, launches);
+      if (rc != PINN_OK) return rc;
+    }
+  }
+  return PINN_OK;
+}
+
+static int run_layered(pinn_plan* p, const float* params, float* out, cudaStream_t st, bool train) {
+  const pinn_mlp_desc& m = p->mlp;
+  const int i_begin = train ? 0 : (int)p->P;
+  CUDA_TRY(cudaMemsetAsync(out + i_begin, 0, sizeof(float) * (size_t)(p->P + p->T - i_begin), st));
+  int launches = 0;
+  if (train) {
+    dim3 g(32, m.n_hidden - 1);
+    pinn::layered::transpose_weights_kernel<<<g, 256, 0, st>>>(params, m.width, m.n_hidden - 1, m.in_dim * m.width + m.width,
+                                                                m.width * m.width + m.width, p->wt);
+    ++launches;
+  }
+  int rc = PINN_E_INVALID;
+  if (m.in_dim == 3 && m.width == 128) rc = layered_run_t<3, 128, 3>(p, params, out, st, train, &launches);
+  else if (m.in_dim == 2 && m.width == 128) rc = layered_run_t<2, 128, 3>(p, params, out, st, train, &launches);
+  else if (m.in_dim == 3 && m.width == 64) rc = layered_run_t<3, 64, 3>(p, params, out, st, train, &launches);
+  else if (m.in_dim == 2 && m.width == 64) rc = layered_run_t<2, 64, 3>(p, params, out, st, train, &launches);
+  p->last_launches = launches;
+  return rc;
 }
 
 extern "C" int pinn_version(void) { return PINN_VERSION; }
@@ -157,10 +284,12 @@ extern "C" int pinn_plan_create(const pinn_mlp_desc* mlp, const pinn_pointset_de
     return fail(PINN_E_INVALID, "unsupported MLP shape d=%d H=%d L=%d O=%d", mlp->in_dim, mlp->width, mlp->n_hidden,
                 mlp->out_dim);
   FusedKernel probe;
-  if (!pick_kernel(*mlp, 0, true, &probe))
+  const bool use_fused = pick_kernel(*mlp, 0, true, &probe);
+  const bool use_layered = !use_fused && layered_supported(*mlp);
+  if (!use_fused && !use_layered)
     return fail(PINN_E_INVALID,
-                "no engine for MLP d=%d H=%d L=%d O=%d (fused_fp32 covers 2-20x3-1, 2-32x3-3, 3-32x3-3)", mlp->in_dim,
-                mlp->width, mlp->n_hidden, mlp->out_dim);
+                "no engine for MLP d=%d H=%d L=%d O=%d (fused_fp32: 2-20x3-1, 2-32x3-3, 3-32x3-3; layered_fp32: "
+                "d in {2,3}, H in {64,128}, L >= 2, O = 3)", mlp->in_dim, mlp->width, mlp->n_hidden, mlp->out_dim);
   CUDA_TRY(cudaSetDevice(device));
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
@@ -196,6 +325,17 @@ extern "C" int pinn_plan_create(const pinn_mlp_desc* mlp, const pinn_pointset_de
       return rc;
     }
   }
+  if (use_layered) {
+    p->layered = true;
+    p->engine = "layered_fp32";
+    int rc = layered_alloc(p);
+    if (rc != PINN_OK) {
+      pinn_plan_destroy(p);
+      return rc;
+    }
+    *out = p;
+    return PINN_OK;
+  }
   p->rows_max = 3 * p->num_sms;
   p->ws_bytes = (size_t)p->rows_max * (size_t)(p->P + p->T) * sizeof(float);
   if (cudaMalloc(&p->ws, p->ws_bytes) != cudaSuccess) {
@@ -225,6 +365,8 @@ extern "C" int pinn_plan_destroy(pinn_plan* p) {
     if (p->eval[o].segs_dev) cudaFree(p->eval[o].segs_dev);
   }
   if (p->ws) cudaFree(p->ws);
+  if (p->act) cudaFree(p->act);
+  if (p->wt) cudaFree(p->wt);
   for (int o = 0; o < 3; ++o) {
     if (p->ev0[o]) cudaEventDestroy(p->ev0[o]);
     if (p->ev1[o]) cudaEventDestroy(p->ev1[o]);
@@ -277,6 +419,7 @@ extern "C" int pinn_plan_set_rhs(pinn_plan* p, int32_t set_index, int32_t term_i
 
 static int run(pinn_plan* p, const float* params, float* out, cudaStream_t st, bool train) {
   if (!p || !params || !out) return fail(PINN_E_INVALID, "null argument");
+  if (p->layered) return run_layered(p, params, out, st, train);
   const int stride = (int)(p->P + p->T);
   int rows = 0, launches = 0;
   const int aligned = ((uintptr_t)params & 15u) == 0;
@@ -326,11 +469,49 @@ extern "C" int pinn_forward(const pinn_mlp_desc* mlp, const float* params_dev, c
   if (!mlp || !params_dev || (n > 0 && (!points_dev || !y_dev))) return fail(PINN_E_INVALID, "null argument");
   if (n <= 0) return PINN_OK;
   FusedKernel k;
-  if (!pick_kernel(*mlp, 0, false, &k))
-    return fail(PINN_E_INVALID, "no engine for MLP d=%d H=%d L=%d O=%d", mlp->in_dim, mlp->width, mlp->n_hidden,
-                mlp->out_dim);
   CUDA_TRY(cudaSetDevice(device));
   cudaStream_t st = (cudaStream_t)stream;
+  if (!pick_kernel(*mlp, 0, false, &k)) {
+    if (!layered_supported(*mlp))
+      return fail(PINN_E_INVALID, "no engine for MLP d=%d H=%d L=%d O=%d", mlp->in_dim, mlp->width, mlp->n_hidden,
+                  mlp->out_dim);
+    // wide/deep network: run the layered forward kernels over a temporary workspace (synchronous free)
+    pinn_plan tmp;
+    tmp.mlp = *mlp;
+    tmp.device = device;
+    tmp.P = param_count(*mlp);
+    CUDA_TRY(cudaDeviceGetAttribute(&tmp.num_sms, cudaDevAttrMultiProcessorCount, device));
+    pinn_pointset_desc fake;
+    memset(&fake, 0, sizeof(fake));
+    fake.n_local = n;
+    tmp.sets.push_back(fake);
+    int rc = layered_alloc(&tmp);
+    SegDev* sd_dev = nullptr;
+    if (rc == PINN_OK && cudaMalloc(&sd_dev, sizeof(SegDev)) != cudaSuccess) rc = fail(PINN_E_ALLOC, "segment descriptor");
+    if (rc == PINN_OK) {
+      SegDev sd;
+      memset(&sd, 0, sizeof(sd));
+      sd.pts = points_dev;
+      sd.y_out = y_dev;
+      sd.n = n;
+      cudaMemcpyAsync(sd_dev, &sd, sizeof(SegDev), cudaMemcpyHostToDevice, st);
+      LaunchTable lt;
+      lt.n_segs = 1;
+      lt.segs_host.push_back(sd);
+      lt.segs_dev = sd_dev;
+      tmp.eval[0] = lt;
+      float* dummy = nullptr;   // no terms: nothing is written through `out`
+      if (cudaMalloc(&dummy, sizeof(float) * (size_t)(tmp.P + 1)) != cudaSuccess) rc = fail(PINN_E_ALLOC, "scratch");
+      if (rc == PINN_OK) rc = run_layered(&tmp, params_dev, dummy, st, false);
+      cudaStreamSynchronize(st);
+      if (dummy) cudaFree(dummy);
+    }
+    if (sd_dev) cudaFree(sd_dev);
+    if (tmp.act) cudaFree(tmp.act);
+    if (tmp.wt) cudaFree(tmp.wt);
+    tmp.act = tmp.wt = nullptr;
+    return rc;
+  }
   int num_sms = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
   CUDA_TRY(cudaFuncSetAttribute((const void*)k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, k.smem_bytes));

@@ -163,3 +163,56 @@ def test_linearity_in_weights_at_full_size():
     _, vals2, g2 = pb2.evaluate()
     assert np.allclose(vals1, vals2, rtol=1e-6)
     assert torch.allclose(2.0 * g1, g2, rtol=1e-4, atol=1e-6 * float(g2.abs().max()))
+
+
+# ---- layered engine (wide / deep networks; BASELINE config 5 shape) ---------------------------------
+
+LAYERED = {
+    "unsteady_8x128": ("cavity_unsteady", dict(PDE=777, BC=65, IC=40, Vel=3, Pres=1, Test=50, noise_bnd=0.05,
+                                               noise_fit=0.05, n_times=3, hidden=(128,) * 8)),
+    "unsteady_2x64": ("cavity_unsteady", dict(PDE=300, BC=33, IC=20, Vel=3, Pres=1, Test=50, n_times=3, hidden=(64,) * 2)),
+}
+
+
+@pytest.mark.parametrize("key", sorted(LAYERED))
+def test_layered_engine_matches_taylor_oracle(key):
+    from oracle import taylor
+    name, kw = LAYERED[key]
+    data, var, model, pb = _setup(name, kw)
+    assert pb.plan.engine == "layered_fp32"
+    total, values, grad = pb.evaluate()
+    theta = torch.cat([v.reshape(-1) for v in var]).numpy()
+    out = taylor.loss_and_grad(pb.compiled, theta, include_test=True)
+    ref_total, ref_vals, ref_test = assemble_losses(pb.compiled, out[pb.compiled.n_params:])
+    assert _rel(total, ref_total) < LOSS_RTOL
+    for v, rv in zip(values, ref_vals):
+        assert _term_close(v, rv)
+    g = grad.double().cpu().numpy()
+    rg = out[:pb.compiled.n_params]
+    assert np.linalg.norm(g - rg) / np.linalg.norm(rg) < GRAD_RTOL
+    _, _, test_vals = pb.evaluate_all()
+    for v, rv in zip(test_vals, ref_test):
+        assert _term_close(v, rv)
+
+
+def test_layered_engine_matches_reference_restatement_small():
+    """8x128 network against the nested reverse-mode restatement itself (small point counts)."""
+    from oracle import reference_step
+    kw = dict(PDE=96, BC=20, IC=16, Vel=3, Pres=1, Test=20, noise_bnd=0.05, noise_fit=0.05, n_times=3, hidden=(128,) * 8)
+    data, var, model, pb = _setup("cavity_unsteady", kw)
+    total, values, grad = pb.evaluate()
+    ref = reference_step.build(data, var)
+    ref_values, ref_total, ref_grad = ref.loss_and_grad()
+    assert _rel(total, ref_total) < LOSS_RTOL
+    g = grad.double().cpu().numpy()
+    assert np.linalg.norm(g - ref_grad.numpy()) / np.linalg.norm(ref_grad.numpy()) < GRAD_RTOL
+
+
+def test_layered_model_forward():
+    from oracle.nisaba_like import KerasMLP
+    name, kw = LAYERED["unsteady_8x128"]
+    data, var, model, pb = _setup(name, kw)
+    x = torch.rand(333, 3, dtype=torch.float32)
+    y = model(x.cuda()).double().cpu()
+    ref = KerasMLP(var)(x.double()).detach()
+    assert torch.allclose(y, ref, rtol=0, atol=5e-6)

@@ -1,0 +1,787 @@
+// Tensor-core layered engine for H = 128 tanh MLPs (BASELINE config 5: 3-128x8-3): the hidden-layer
+// contractions run on tcgen05 (kind::tf32, FP32 accumulate in TMEM) with the 3-pass hi/lo split
+//   x*w ~= x_lo*w_hi + x_hi*w_lo + x_hi*w_hi,   hi = rna_tf32(x), lo = rna_tf32(x - hi),
+// because one TF32 pass misses the 1e-5 / 1e-4 parity tolerance (tools/tc_probe.cu).
+//
+// Measured facts this design rests on (tools/tc_probe.cu, tools/tc_layout_probe.cu on B200):
+//   * an M=128,N=128,K=8 tf32 MMA costs ~110 cycles, an N=256 one 128 cycles (= the pipe's floor), so the
+//     POINT ROWS go on the MMA N axis (240 or 256 rows per instruction) and the 128 neurons on M;
+//   * tf32 operands must be K-major (MN-major descriptors read nothing); raw FP32 words are truncated by
+//     the hardware, which is why both halves of the split are rounded to TF32 explicitly.
+//
+// Orientation: D[neuron j (TMEM lane)][row n (TMEM column)] = sum_k W[j][k] * Act[n][k].  A tile is P points
+// x C channels, rows n = c*P + p, NR = C*P in {240, 256}.  An epilogue thread owns one neuron of one TMEM
+// lane quarter and sees every channel of a point in its own registers, so the tanh-jet (and its adjoint)
+// needs no cross-lane traffic.
+//
+// HBM layout of every jet buffer (a-jets and z-bar alike): the UMMA K-major core-matrix tiling itself,
+//   off(n, k) = tile*NR*128 + (n/8)*1024 + (k/4)*32 + (n%8)*4 + (k%4)          [floats]
+// so a (row-group, K-chunk) block is contiguous for the producers of the forward/backward GEMMs, and a
+// 4-row x 4-neuron block is 64 contiguous bytes for the transposing producer of the weight-gradient GEMM.
+//
+//   tc_prep_weights     hi/lo images of K_l (backward operand) and K_l^T (forward operand)
+//   tc_layer1           a-jets of layer 1 (SIMT)
+//   tc_layer<MODE=0>    a_l   = tanh-jet(a_{l-1} K_l + b_l)                       tcgen05, persistent
+//   tc_out_layer        output GEMV, residuals, sum r^2, z-bar_L, K_out/b_out gradients (SIMT)
+//   tc_wgrad            K_l-bar += a_{l-1}^T z-bar_l, b_l-bar                     tcgen05, persistent
+//   tc_layer<MODE=1,2>  z-bar_{l-1} = tanh-jet-adjoint(z-bar_l K_l^T) in place    tcgen05, persistent
+//   tc_layer1_grad      K_1-bar, b_1-bar from z-bar_1 (SIMT)
+#pragma once
+#include "common.cuh"
+#include "layered_fp32.cuh"   // Jet, jet_fwd, jet_bwd
+#include "umma.cuh"
+
+namespace pinn {
+namespace tc {
+
+constexpr int kH = 128;
+
+template <int D, int ORDER>
+struct Geo {
+  static constexpr int C = n_channels(D, ORDER);
+  static constexpr int P = C == 6 ? 40 : C == 5 ? 48 : C == 4 ? 64 : C == 3 ? 80 : 256;   // points per tile
+  static constexpr int NR = C * P;                                                       // rows per tile = MMA N
+  static constexpr int RG = NR / 8;                                                      // 8-row groups per tile
+  static_assert(NR % 16 == 0 && NR <= 256 && P % 8 == 0, "tile geometry");
+};
+
+__host__ __device__ __forceinline__ size_t act_off(int n, int k) {
+  return (size_t)(n >> 3) * (8 * kH) + (size_t)(k >> 2) * 32 + (size_t)(n & 7) * 4 + (size_t)(k & 3);
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, float (&v)[4]) {
+  uint32_t r0, r1, r2, r3;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr) : "memory");
+  v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// round-to-nearest split: hi and lo are both exact TF32 values, so the tensor core's own truncation of its
+// operands loses nothing and the residual x - hi - lo (<= 2^-22 |x|) has no sign bias.  (A truncating split
+// leaves lo with 13 significant bits that the hardware cuts to 10: a one-sided 2^-21 error per product that
+// adds up over 8 layers to 1.3e-5 on a loss term -- measured.)
+__device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
+  hi = umma::rna_tf32(x);
+  lo = umma::rna_tf32(x - hi);
+}
+__device__ __forceinline__ void tf32_split4(const float4& v, float4& hi, float4& lo) {
+  tf32_split(v.x, hi.x, lo.x); tf32_split(v.y, hi.y, lo.y); tf32_split(v.z, hi.z, lo.z); tf32_split(v.w, hi.w, lo.w);
+}
+
+// ---- weight images -------------------------------------------------------------------------------
+// per hidden->hidden layer: [fwd hi | fwd lo | bwd hi | bwd lo], each a 128x128 K-major core-matrix tiling.
+//   fwd (A operand of  a K_l):     row m = output neuron j, k = input neuron i, value K_l[i][j]
+//   bwd (A operand of z-bar K_l^T): row m = input neuron i,  k = output neuron j, value K_l[i][j]
+constexpr int kImgFloats = kH * kH;
+constexpr int kLayerImgFloats = 4 * kImgFloats;
+
+__global__ void tc_prep_weights(const float* __restrict__ params, int off0, int stride, float* __restrict__ img) {
+  const int l = blockIdx.y;
+  const float* K = params + off0 + (size_t)l * stride;
+  float* out = img + (size_t)l * kLayerImgFloats;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < kH * kH; idx += gridDim.x * blockDim.x) {
+    const int i = idx / kH, j = idx % kH;
+    float hi, lo;
+    tf32_split(K[idx], hi, lo);
+    const size_t f = act_off(j, i), b = act_off(i, j);
+    out[f] = hi;
+    out[kImgFloats + f] = lo;
+    out[2 * kImgFloats + b] = hi;
+    out[3 * kImgFloats + b] = lo;
+  }
+}
+
+// ---- layer 1 (SIMT) --------------------------------------------------------------------------------
+template <int D, int ORDER>
+__global__ void __launch_bounds__(256) tc_layer1(const float* __restrict__ params, const float* __restrict__ pts, long long n,
+                                                 long long p_begin, float* __restrict__ act1) {
+  using G = Geo<D, ORDER>;
+  constexpr int C = G::C, P = G::P;
+  const int j = threadIdx.x & (kH - 1), pj = threadIdx.x >> 7;
+  const long long tile = blockIdx.x;
+  float zd[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) zd[i] = __ldg(params + i * kH + j);
+  const float b = __ldg(params + D * kH + j);
+  float* out = act1 + (size_t)tile * G::NR * kH;
+  for (int p = pj; p < P; p += 2) {
+    long long gp = p_begin + tile * P + p;
+    if (gp >= n) gp = n - 1;
+    float z = b;
+#pragma unroll
+    for (int i = 0; i < D; ++i) z = fmaf(__ldg(pts + gp * D + i), zd[i], z);
+    float a[C];
+    layered::jet_fwd<D, ORDER>(tanh_accurate(z), zd, 0.f, 0.f, a);
+#pragma unroll
+    for (int c = 0; c < C; ++c) out[act_off(c * P + p, j)] = a[c];
+  }
+}
+
+// ---- TMEM load helpers (no wait inside: issue several, then tmem_ld_wait) ---------------------------
+template <int N>
+__device__ __forceinline__ void tmem_ld_n(uint32_t taddr, float* v);
+template <>
+__device__ __forceinline__ void tmem_ld_n<4>(uint32_t taddr, float* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(taddr) : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_ld_n<8>(uint32_t taddr, float* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(taddr) : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_ld_n<16>(uint32_t taddr, float* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]),
+                 "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]) : "r"(taddr) : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_ld_n<32>(uint32_t taddr, float* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]),
+        "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]), "=f"(v[17]), "=f"(v[18]),
+        "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]),
+        "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
+      : "r"(taddr) : "memory");
+}
+// W consecutive columns starting at taddr, as the largest power-of-two loads (W % 4 == 0)
+template <int W, int O = 0>
+__device__ __forceinline__ void tmem_ld_span(uint32_t taddr, float* v) {
+  if constexpr (W - O >= 32) { tmem_ld_n<32>(taddr + O, v + O); tmem_ld_span<W, O + 32>(taddr, v); }
+  else if constexpr (W - O >= 16) { tmem_ld_n<16>(taddr + O, v + O); tmem_ld_span<W, O + 16>(taddr, v); }
+  else if constexpr (W - O >= 8) { tmem_ld_n<8>(taddr + O, v + O); tmem_ld_span<W, O + 8>(taddr, v); }
+  else if constexpr (W - O >= 4) { tmem_ld_n<4>(taddr + O, v + O); tmem_ld_span<W, O + 4>(taddr, v); }
+}
+template <int REGS> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
+template <int REGS> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
+
+// ---- tcgen05 hidden-layer kernel -------------------------------------------------------------------
+// The tensor core adds every MMA into its FP32 accumulator with TRUNCATION (measured, tools/
+// tc_accum_probe.cu: -1.1e-6 relative bias after the 48 MMAs of a K = 128 contraction, 5x the error of an
+// FFMA chain and one-sided, so it does not average out over layers).  The accumulator therefore only
+// lives for one K-chunk of 32 (12 MMAs, small lo-terms first): two TMEM buffers ping-pong by chunk and the
+// epilogue warps add each finished chunk into FP32 registers with round-to-nearest.  Warp roles (4 warp
+// groups, registers redistributed with setmaxnreg):
+//   WG0  warps 0-3    producers  global jets -> rna hi/lo split -> K-major stage blocks
+//   WG1-2 warps 4-11  epilogue   thread = neuron of lane quarter warp%4, half of the tile's points per group
+//   WG3  warp 12      MMA issuer (one lane); warps 13-15 idle
+constexpr int kProdWarps = 4;
+constexpr int kEpiWarps = 8;
+constexpr int kLayerThreads = 512;
+constexpr int kMmaWarp = 12;
+constexpr int kStages = 3;
+constexpr int kKC = 16;                       // K per pipeline stage (2 MMA k-steps)
+constexpr int kStagesPerChunk = 2;            // accumulator lifetime: K = 32
+constexpr int kChunks = kH / (kKC * kStagesPerChunk);
+
+template <int NR>
+struct LayerSmem {
+  static constexpr int W_BYTES = 2 * kH * kH * 4;          // hi + lo images of the layer's A operand
+  static constexpr int HALF = NR * kKC * 4;                // one stage's hi (or lo) B block
+  static constexpr int STAGE = 2 * HALF;
+  static constexpr int BAR_OFF = W_BYTES + kStages * STAGE;
+  static constexpr int TOTAL = BAR_OFF + 128;
+};
+
+// MODE 0: forward (bias + tanh-jet -> act_io written)
+// MODE 1: backward hidden (act_io holds a_{l-1}, overwritten by z-bar_{l-1})
+// MODE 2: backward into layer 1 (pre-activation jets are the constant rows of K1)
+template <int D, int ORDER, int MODE>
+__global__ void __launch_bounds__(kLayerThreads, 1) tc_layer(const float* __restrict__ w_img /* [hi|lo] */, const float* __restrict__ bias,
+                                                             const float* __restrict__ act_in, float* __restrict__ act_io,
+                                                             const float* __restrict__ params, int n_tiles) {
+  using G = Geo<D, ORDER>;
+  using S = LayerSmem<G::NR>;
+  constexpr int C = G::C, P = G::P, NR = G::NR, PH = P / 2;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sW = smem;
+  uint8_t* sStage = smem + S::W_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);   // [kStages]
+  uint64_t* empty = full + kStages;                                  // [kStages]
+  uint64_t* tfull = empty + kStages;                                 // [2]
+  uint64_t* tempty = tfull + 2;                                      // [2]
+  uint64_t* wbar = tempty + 2;
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(wbar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], kProdWarps); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], kEpiWarps); }
+    mbar_init(wbar, 1);
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) umma::tmem_alloc<512>(tslot);
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  umma::fence_after_thread_sync();
+  const uint32_t tmem = *tslot;
+
+  if (warp < kProdWarps) {
+    // ===== producers =====
+    reg_dec<96>();
+    if (tid == 0) {
+      mbar_expect_tx(wbar, S::W_BYTES);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        tma_bulk_g2s(sW + i * (S::W_BYTES / 4), reinterpret_cast<const uint8_t*>(w_img) + i * (S::W_BYTES / 4), S::W_BYTES / 4, wbar);
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(act_in + (size_t)tile * NR * kH);
+#pragma unroll 1
+      for (int kc = 0; kc < kH / kKC; ++kc) {
+        mbar_wait(&empty[stage], phase ^ 1u);
+        uint8_t* dst = sStage + stage * S::STAGE;
+        float4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int x = tid + 128 * i;                       // 16-byte chunk: row-group x/32, (k-chunk, row) x%32
+          if (x < NR * 4) v[i] = __ldg(reinterpret_cast<const float4*>(src + (size_t)(x >> 5) * 4096 + kc * 512 + (x & 31) * 16));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int x = tid + 128 * i;
+          if (x < NR * 4) {
+            float4 hi, lo;
+            tf32_split4(v[i], hi, lo);
+            *reinterpret_cast<float4*>(dst + x * 16) = hi;
+            *reinterpret_cast<float4*>(dst + S::HALF + x * 16) = lo;
+          }
+        }
+        umma::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[stage]);
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp >= kMmaWarp) {
+    // ===== MMA issuer =====
+    reg_dec<32>();
+    if (warp == kMmaWarp && lane == 0) {
+      mbar_wait(wbar, 0);
+      const uint32_t idesc = umma::idesc_tf32(kH, NR);
+      const uint32_t w_hi = (uint32_t)__cvta_generic_to_shared(sW), w_lo = w_hi + kH * kH * 4;
+      const uint32_t st0 = (uint32_t)__cvta_generic_to_shared(sStage);
+      int stage = 0, g = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+#pragma unroll 1
+        for (int ch = 0; ch < kChunks; ++ch, ++g) {
+          const int buf = g & 1;
+          if (g >= 2) mbar_wait(&tempty[buf], (uint32_t)(((g >> 1) - 1) & 1));
+          umma::fence_after_thread_sync();
+          const uint32_t d = tmem + (uint32_t)buf * 256u;
+          uint32_t acc = 0;
+#pragma unroll 1
+          for (int s = 0; s < kStagesPerChunk; ++s) {
+            mbar_wait(&full[stage], phase);
+            umma::fence_after_thread_sync();
+            const uint32_t b_hi = st0 + stage * S::STAGE, b_lo = b_hi + S::HALF;
+            const uint32_t ka = (uint32_t)((ch * kStagesPerChunk + s) * (kKC / 8)) * 256u;
+            uint64_t a_hi_d[kKC / 8], a_lo_d[kKC / 8], b_hi_d[kKC / 8], b_lo_d[kKC / 8];
+#pragma unroll
+            for (int ks = 0; ks < kKC / 8; ++ks) {
+              a_hi_d[ks] = umma::smem_desc(w_hi + ka + ks * 256, 128, 4096);
+              a_lo_d[ks] = umma::smem_desc(w_lo + ka + ks * 256, 128, 4096);
+              b_hi_d[ks] = umma::smem_desc(b_hi + ks * 256, 128, (kKC / 4) * 128);
+              b_lo_d[ks] = umma::smem_desc(b_lo + ks * 256, 128, (kKC / 4) * 128);
+            }
+            // small terms first: they meet a small accumulator
+#pragma unroll
+            for (int ks = 0; ks < kKC / 8; ++ks) { umma::mma_tf32_ss(d, a_lo_d[ks], b_hi_d[ks], idesc, acc); acc = 1; }
+#pragma unroll
+            for (int ks = 0; ks < kKC / 8; ++ks) umma::mma_tf32_ss(d, a_hi_d[ks], b_lo_d[ks], idesc, 1);
+#pragma unroll
+            for (int ks = 0; ks < kKC / 8; ++ks) umma::mma_tf32_ss(d, a_hi_d[ks], b_hi_d[ks], idesc, 1);
+            umma::commit(&empty[stage]);
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+          umma::commit(&tfull[buf]);
+        }
+      }
+    }
+  } else {
+    // ===== epilogue: chunk partial sums TMEM -> FP32 registers; tanh-jet (or its adjoint) -> global =====
+    reg_inc<184>();
+    const int q = warp & 3, half = (warp - kProdWarps) >> 2;
+    const int j = q * 32 + lane;
+    float bj = 0.f;
+    float k1[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) k1[i] = 0.f;
+    if constexpr (MODE == 0) bj = __ldg(bias + j);
+    if constexpr (MODE == 2) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) k1[i] = __ldg(params + i * kH + j);
+    }
+    int g = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      float* io = act_io + (size_t)tile * NR * kH;
+      float acc[C][PH];
+#pragma unroll 1
+      for (int ch = 0; ch < kChunks; ++ch, ++g) {
+        const int buf = g & 1;
+        mbar_wait(&tfull[buf], (uint32_t)((g >> 1) & 1));
+        umma::fence_after_thread_sync();
+        const uint32_t tb = tmem + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * PH);
+        if (ch == 0) {
+#pragma unroll
+          for (int c = 0; c < C; ++c) tmem_ld_span<PH>(tb + (uint32_t)(c * P), acc[c]);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+#pragma unroll
+            for (int o = 0; o < PH; o += 32) {
+              constexpr int W0 = PH < 32 ? PH : 32;
+              float t[W0];
+              if (PH - o >= W0) {
+                tmem_ld_span<W0>(tb + (uint32_t)(c * P + o), t);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < W0; ++i) acc[c][o + i] += t[i];
+              } else {
+                constexpr int W1 = PH % 32 == 0 ? 4 : PH % 32;    // tail of a span longer than 32 (PH = 40: 8)
+                float u[W1];
+                tmem_ld_span<W1>(tb + (uint32_t)(c * P + o), u);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < W1; ++i) acc[c][o + i] += u[i];
+              }
+            }
+          }
+        }
+        umma::fence_before_thread_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[buf]);
+      }
+      // ---- elementwise: 4 points at a time ----
+#pragma unroll
+      for (int i0 = 0; i0 < PH; i0 += 4) {
+        const int p0 = half * PH + i0;
+        float aj[C][4];
+        if constexpr (MODE == 1) {
+#pragma unroll
+          for (int c = 0; c < C; ++c)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) aj[c][i] = io[act_off(c * P + p0 + i, j)];
+        } else if constexpr (MODE == 2) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) aj[0][i] = io[act_off(p0 + i, j)];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float res[C];
+          if constexpr (MODE == 0) {
+            float zd[D], zxx = 0.f, zyy = 0.f;
+#pragma unroll
+            for (int t = 0; t < D; ++t) zd[t] = ORDER >= 1 ? acc[(ORDER >= 1) ? 1 + t : 0][i0 + i] : 0.f;
+            if constexpr (ORDER >= 2) { zxx = acc[(ORDER >= 2) ? 1 + D : 0][i0 + i]; zyy = acc[(ORDER >= 2) ? 2 + D : 0][i0 + i]; }
+            layered::jet_fwd<D, ORDER>(tanh_accurate(acc[0][i0 + i] + bj), zd, zxx, zyy, res);
+          } else {
+            float a1[C], ab[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) { a1[c] = (MODE == 2 && c > 0) ? 0.f : aj[c][i]; ab[c] = acc[c][i0 + i]; }
+            layered::jet_bwd<D, ORDER, MODE == 2>(a1, k1, ab, res);
+          }
+#pragma unroll
+          for (int c = 0; c < C; ++c) io[act_off(c * P + p0 + i, j)] = res[c];
+        }
+      }
+    }
+  }
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == kMmaWarp) umma::tmem_dealloc<512>(tmem);
+}
+
+// ---- tcgen05 weight gradient -----------------------------------------------------------------------
+// gK[i][j] += sum_rows a_prev[row][i] * zbar[row][j]; gb[j] += sum over value-channel rows of zbar[row][j].
+// The contraction runs over ROWS, so both operands are transposed on the way into shared memory: a
+// producer thread loads a 4-row x 4-neuron block (64 contiguous bytes) and stores four 16-byte K-chunks.
+// Row-group stride of the operand tiles is padded (1040 B) so those stores are bank-conflict free.
+// The TMEM accumulator lives for 4 stages (128 rows, 48 MMAs); drain warps add it into FP32 registers
+// (same truncation argument as tc_layer) and flush the 128 x 128 block with atomics at the end.
+constexpr int kWgThreads = 288;           // 4 producer warps, 4 drain warps, 1 MMA warp
+constexpr int kWgMmaWarp = 8;
+constexpr int kWgRows = 32;               // rows (K) per stage
+constexpr int kWgStagesPerChunk = 4;
+constexpr int kWgSBO = (kWgRows / 4) * 128 + 16;
+constexpr int kWgOp = (kH / 8) * kWgSBO;  // bytes of one operand tile (128 x 32, padded): 16640
+constexpr int kWgStage = 4 * kWgOp;       // A hi, A lo, Z hi, Z lo
+constexpr int kWgBarOff = kStages * kWgStage;
+constexpr int kWgSmem = kWgBarOff + 128 + kH * 4;
+
+__global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad(const float* __restrict__ act_prev, const float* __restrict__ zbar,
+                                                          long long total_rg, int rg_per_tile, int val_rg, float* __restrict__ gK,
+                                                          float* __restrict__ gb) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kWgBarOff);
+  uint64_t* empty = full + kStages;
+  uint64_t* tfull = empty + kStages;     // [2]
+  uint64_t* tempty = tfull + 2;          // [2]
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* sB = reinterpret_cast<float*>(smem + kWgBarOff + 128);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long n_stages = (total_rg + 3) / 4;             // 32-row stages in the batch
+  // this CTA's stages: s = blockIdx.x, blockIdx.x + gridDim.x, ...
+  const long long my_stages = n_stages > (long long)blockIdx.x ? (n_stages - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const long long my_chunks = (my_stages + kWgStagesPerChunk - 1) / kWgStagesPerChunk;
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 4); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
+    fence_barrier_init();
+  }
+  if (tid < kH) sB[tid] = 0.f;
+  if (warp == kWgMmaWarp) umma::tmem_alloc<256>(tslot);
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  umma::fence_after_thread_sync();
+  const uint32_t tmem = *tslot;
+
+  if (warp < 4) {
+    // ===== producers (transposing) =====
+    float bsum[2][4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) bsum[u][cc] = 0.f;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long st = blockIdx.x; st < n_stages; st += gridDim.x) {
+      mbar_wait(&empty[stage], phase ^ 1u);
+      uint8_t* dst = smem + stage * kWgStage;
+#pragma unroll
+      for (int mat = 0; mat < 2; ++mat) {
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(mat == 0 ? act_prev : zbar);
+        float4 v[2][4];
+        int kcs[2], rgs[2], rhs[2];
+        bool valrow[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          // 64 blocks per row-group: lanes 0..15 -> neuron chunk, lane>>4 -> row half; second warp of a pair -> chunk + 16
+          const int b = tid + 128 * u;
+          const int rg = b >> 6, w = b & 63;
+          const int kc = (w & 15) + 16 * (w >> 5), rh = (w >> 4) & 1;
+          kcs[u] = kc; rgs[u] = rg; rhs[u] = rh;
+          const long long frg = st * 4 + rg;
+          valrow[u] = false;
+          if (frg < total_rg) {
+            const float4* p = reinterpret_cast<const float4*>(src + (size_t)frg * 4096 + kc * 128 + rh * 64);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) v[u][r] = p[r];
+            valrow[u] = (int)(frg % rg_per_tile) < val_rg;
+          } else {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) v[u][r] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (mat == 1 && valrow[u]) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) { bsum[u][0] += v[u][r].x; bsum[u][1] += v[u][r].y; bsum[u][2] += v[u][r].z; bsum[u][3] += v[u][r].w; }
+          }
+          uint8_t* hi = dst + (mat * 2) * kWgOp;
+          uint8_t* lo = hi + kWgOp;
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            const int m = 4 * kcs[u] + cc;
+            const uint32_t off = (uint32_t)(m >> 3) * kWgSBO + (uint32_t)(rgs[u] * 2 + rhs[u]) * 128u + (uint32_t)(m & 7) * 16u;
+            const float e0 = cc == 0 ? v[u][0].x : cc == 1 ? v[u][0].y : cc == 2 ? v[u][0].z : v[u][0].w;
+            const float e1 = cc == 0 ? v[u][1].x : cc == 1 ? v[u][1].y : cc == 2 ? v[u][1].z : v[u][1].w;
+            const float e2 = cc == 0 ? v[u][2].x : cc == 1 ? v[u][2].y : cc == 2 ? v[u][2].z : v[u][2].w;
+            const float e3 = cc == 0 ? v[u][3].x : cc == 1 ? v[u][3].y : cc == 2 ? v[u][3].z : v[u][3].w;
+            float4 h4, l4;
+            tf32_split4(make_float4(e0, e1, e2, e3), h4, l4);
+            *reinterpret_cast<float4*>(hi + off) = h4;
+            *reinterpret_cast<float4*>(lo + off) = l4;
+          }
+        }
+      }
+      umma::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[stage]);
+      if (++stage == kStages) { stage = 0; phase ^= 1u; }
+    }
+    // bias gradient: threads sharing a neuron chunk meet in shared memory
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int b = tid + 128 * u, w = b & 63;
+      const int kc = (w & 15) + 16 * (w >> 5);
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) atomicAdd(&sB[4 * kc + cc], bsum[u][cc]);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (my_stages > 0) atomicAdd(gb + tid, sB[tid]);
+  } else if (warp < 8) {
+    // ===== drain warps: chunk partial sums -> FP32 registers -> global atomics =====
+    const int q = warp & 3;
+    const int i = q * 32 + lane;
+    float acc[kH];
+#pragma unroll
+    for (int c = 0; c < kH; ++c) acc[c] = 0.f;
+    for (long long ch = 0; ch < my_chunks; ++ch) {
+      const int buf = (int)(ch & 1);
+      mbar_wait(&tfull[buf], (uint32_t)((ch >> 1) & 1));
+      umma::fence_after_thread_sync();
+      const uint32_t tb = tmem + (uint32_t)buf * 128u + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+      for (int c0 = 0; c0 < kH; c0 += 32) {
+        float t[32];
+        tmem_ld_n<32>(tb + c0, t);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[c0 + c] += t[c];
+      }
+      umma::fence_before_thread_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
+    }
+    if (my_chunks > 0) {
+#pragma unroll
+      for (int c = 0; c < kH; ++c) atomicAdd(gK + (size_t)i * kH + c, acc[c]);
+    }
+  } else if (warp == kWgMmaWarp && lane == 0) {
+    const uint32_t idesc = umma::idesc_tf32(kH, kH);
+    const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(smem);
+    int stage = 0;
+    uint32_t phase = 0;
+    long long done_stages = 0;
+    for (long long ch = 0; ch < my_chunks; ++ch) {
+      const int buf = (int)(ch & 1);
+      if (ch >= 2) mbar_wait(&tempty[buf], (uint32_t)(((ch >> 1) - 1) & 1));
+      umma::fence_after_thread_sync();
+      const uint32_t d = tmem + (uint32_t)buf * 128u;
+      uint32_t acc = 0;
+      for (int s = 0; s < kWgStagesPerChunk && done_stages < my_stages; ++s, ++done_stages) {
+        mbar_wait(&full[stage], phase);
+        umma::fence_after_thread_sync();
+        const uint32_t a_hi = s0 + stage * kWgStage, a_lo = a_hi + kWgOp, z_hi = a_lo + kWgOp, z_lo = z_hi + kWgOp;
+#pragma unroll
+        for (int ks = 0; ks < kWgRows / 8; ++ks) {
+          umma::mma_tf32_ss(d, umma::smem_desc(a_lo + ks * 256, 128, kWgSBO), umma::smem_desc(z_hi + ks * 256, 128, kWgSBO), idesc, acc);
+          acc = 1;
+        }
+#pragma unroll
+        for (int ks = 0; ks < kWgRows / 8; ++ks)
+          umma::mma_tf32_ss(d, umma::smem_desc(a_hi + ks * 256, 128, kWgSBO), umma::smem_desc(z_lo + ks * 256, 128, kWgSBO), idesc, 1);
+#pragma unroll
+        for (int ks = 0; ks < kWgRows / 8; ++ks)
+          umma::mma_tf32_ss(d, umma::smem_desc(a_hi + ks * 256, 128, kWgSBO), umma::smem_desc(z_hi + ks * 256, 128, kWgSBO), idesc, 1);
+        umma::commit(&empty[stage]);
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      }
+      umma::commit(&tfull[buf]);
+    }
+  }
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == kWgMmaWarp) umma::tmem_dealloc<256>(tmem);
+}
+
+// ---- output layer + residuals + adjoint, one warp per point (SIMT) ----------------------------------
+template <int D, int O, int ORDER, bool TRAIN>
+__global__ void __launch_bounds__(256) tc_out_layer(const float* __restrict__ params, int off_ko, const SegDev* __restrict__ seg_ptr,
+                                                    long long p_begin, int n_tiles, float* __restrict__ actL,
+                                                    float* __restrict__ grad, float* __restrict__ sumsq) {
+  using G = Geo<D, ORDER>;
+  constexpr int C = G::C, P = G::P, H = kH;
+  constexpr int KL = H / 32;
+  constexpr int SX = D - 2, SY = D - 1;
+  const SegDev* __restrict__ seg = seg_ptr;
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const long long n = seg->n;
+  const float* Ko = params + off_ko;
+  const float* bo = Ko + H * O;
+  // lane owns k = 4*lane + q (q = 0..3): one 16-byte chunk of every row
+  float ko[KL][O];
+#pragma unroll
+  for (int q = 0; q < KL; ++q)
+#pragma unroll
+    for (int o = 0; o < O; ++o) ko[q][o] = __ldg(Ko + (4 * lane + q) * O + o);
+  float gko[KL][O];
+#pragma unroll
+  for (int q = 0; q < KL; ++q)
+#pragma unroll
+    for (int o = 0; o < O; ++o) gko[q][o] = 0.f;
+  float gbo[O];
+#pragma unroll
+  for (int o = 0; o < O; ++o) gbo[o] = 0.f;
+  float sq[kMaxTerms];
+#pragma unroll
+  for (int t = 0; t < kMaxTerms; ++t) sq[t] = 0.f;
+  const long long total_pts = (long long)n_tiles * P;
+  for (long long lp = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); lp < total_pts;
+       lp += (long long)gridDim.x * warps_per_block) {
+    const long long gp = p_begin + lp;
+    const bool valid = gp < n;
+    const long long tile = lp / P;
+    const int p = (int)(lp % P);
+    float* base = actL + (size_t)tile * G::NR * H;
+    float a[C][KL];
+    float J[C][O];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float4 av = *reinterpret_cast<const float4*>(base + act_off(c * P + p, 4 * lane));
+      a[c][0] = av.x; a[c][1] = av.y; a[c][2] = av.z; a[c][3] = av.w;
+#pragma unroll
+      for (int o = 0; o < O; ++o) J[c][o] = 0.f;
+#pragma unroll
+      for (int q = 0; q < KL; ++q)
+#pragma unroll
+        for (int o = 0; o < O; ++o) J[c][o] = fmaf(a[c][q], ko[q][o], J[c][o]);
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+      for (int o = 0; o < O; ++o) {
+        float v = J[c][o];
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+        J[c][o] = v + (c == 0 ? __ldg(bo + o) : 0.f);
+      }
+    if (seg->y_out != nullptr && valid && lane == 0) {
+#pragma unroll
+      for (int o = 0; o < O; ++o) seg->y_out[gp * O + o] = J[0][o];
+    }
+    float Jb[C][O];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+      for (int o = 0; o < O; ++o) Jb[c][o] = 0.f;
+    const int n_terms = seg->n_terms;
+#pragma unroll
+    for (int t = 0; t < kMaxTerms; ++t) {
+      if (t >= n_terms) break;
+      const TermDev* __restrict__ T = seg->terms + t;
+      if (TRAIN && !T->train) continue;
+      float r = 0.f;
+#pragma unroll
+      for (int o = 0; o < O; ++o)
+#pragma unroll
+        for (int c = 0; c < C; ++c) r = fmaf(__ldg(&T->coef[o][c]), J[c][o], r);
+      float cv = 0.f;
+      int ck = 0;
+      if constexpr (ORDER >= 1 && O >= 2) {
+        cv = __ldg(&T->conv);
+        ck = __ldg(&T->conv_k);
+        const float ukx = ck == 0 ? J[1 + SX][0] : J[1 + SX][1];
+        const float uky = ck == 0 ? J[1 + SY][0] : J[1 + SY][1];
+        r = fmaf(cv, fmaf(J[0][0], ukx, J[0][1] * uky), r);
+      }
+      if (T->rhs != nullptr && valid) r = fmaf(-__ldg(&T->rhs_scale), __ldg(T->rhs + gp), r);
+      if (!valid) r = 0.f;
+      sq[t] = fmaf(r, r, sq[t]);
+      if constexpr (TRAIN) {
+        const float rb = __ldg(&T->scale) * r;
+#pragma unroll
+        for (int o = 0; o < O; ++o)
+#pragma unroll
+          for (int c = 0; c < C; ++c) Jb[c][o] = fmaf(__ldg(&T->coef[o][c]), rb, Jb[c][o]);
+        if constexpr (ORDER >= 1 && O >= 2) {
+          const float ukx = ck == 0 ? J[1 + SX][0] : J[1 + SX][1];
+          const float uky = ck == 0 ? J[1 + SY][0] : J[1 + SY][1];
+          const float m = cv * rb;
+          Jb[0][0] = fmaf(m, ukx, Jb[0][0]);
+          Jb[0][1] = fmaf(m, uky, Jb[0][1]);
+          const float m0 = ck == 0 ? m : 0.f, m1 = ck == 0 ? 0.f : m;
+          Jb[1 + SX][0] = fmaf(m0, J[0][0], Jb[1 + SX][0]);
+          Jb[1 + SY][0] = fmaf(m0, J[0][1], Jb[1 + SY][0]);
+          Jb[1 + SX][1] = fmaf(m1, J[0][0], Jb[1 + SX][1]);
+          Jb[1 + SY][1] = fmaf(m1, J[0][1], Jb[1 + SY][1]);
+        }
+      }
+    }
+    if constexpr (TRAIN) {
+#pragma unroll
+      for (int o = 0; o < O; ++o) gbo[o] += Jb[0][o];
+      float zout[C][KL];
+#pragma unroll
+      for (int q = 0; q < KL; ++q) {
+        float aj[C], ab[C], zb[C], k1[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) k1[i] = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          aj[c] = a[c][q];
+          float b = 0.f;
+#pragma unroll
+          for (int o = 0; o < O; ++o) {
+            b = fmaf(Jb[c][o], ko[q][o], b);
+            gko[q][o] = fmaf(aj[c], Jb[c][o], gko[q][o]);
+          }
+          ab[c] = b;
+        }
+        layered::jet_bwd<D, ORDER, false>(aj, k1, ab, zb);
+#pragma unroll
+        for (int c = 0; c < C; ++c) zout[c][q] = zb[c];
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+        *reinterpret_cast<float4*>(base + act_off(c * P + p, 4 * lane)) = make_float4(zout[c][0], zout[c][1], zout[c][2], zout[c][3]);
+    }
+  }
+  if constexpr (TRAIN) {
+#pragma unroll
+    for (int q = 0; q < KL; ++q)
+#pragma unroll
+      for (int o = 0; o < O; ++o) atomicAdd(grad + off_ko + (4 * lane + q) * O + o, gko[q][o]);
+    if (lane == 0) {
+#pragma unroll
+      for (int o = 0; o < O; ++o) atomicAdd(grad + off_ko + H * O + o, gbo[o]);
+    }
+  }
+  if (lane == 0) {
+    const int n_terms = seg->n_terms;
+#pragma unroll
+    for (int t = 0; t < kMaxTerms; ++t)
+      if (t < n_terms && (!TRAIN || seg->terms[t].train)) atomicAdd(sumsq + seg->terms[t].out_index, sq[t]);
+  }
+}
+
+// ---- K1 / b1 gradients from z-bar_1 (SIMT): thread = neuron, block-strided over tiles ----------------
+template <int D, int ORDER>
+__global__ void __launch_bounds__(256) tc_layer1_grad(const float* __restrict__ zbar1, const float* __restrict__ pts, long long n,
+                                                      long long p_begin, int n_tiles, float* __restrict__ grad) {
+  using G = Geo<D, ORDER>;
+  constexpr int P = G::P;
+  __shared__ float sG[(1 + D) * kH];
+  for (int i = threadIdx.x; i < (1 + D) * kH; i += blockDim.x) sG[i] = 0.f;
+  __syncthreads();
+  const int j = threadIdx.x & (kH - 1), pj = threadIdx.x >> 7;
+  float gk[D], gbv = 0.f;
+#pragma unroll
+  for (int i = 0; i < D; ++i) gk[i] = 0.f;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const float* zt = zbar1 + (size_t)tile * G::NR * kH;
+    for (int p = pj; p < P; p += 2) {
+      long long gp = p_begin + (long long)tile * P + p;
+      if (gp >= n) gp = n - 1;
+      const float z0 = zt[act_off(p, j)];
+      gbv += z0;
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        float v = __ldg(pts + gp * D + i) * z0;
+        if constexpr (ORDER >= 1) v += zt[act_off((1 + i) * P + p, j)];
+        gk[i] += v;
+      }
+    }
+  }
+  atomicAdd(&sG[D * kH + j], gbv);
+#pragma unroll
+  for (int i = 0; i < D; ++i) atomicAdd(&sG[i * kH + j], gk[i]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < (1 + D) * kH; i += blockDim.x) atomicAdd(grad + i, sG[i]);   // [K1 | b1] are contiguous
+}
+
+}  // namespace tc
+}  // namespace pinn

@@ -13,6 +13,7 @@
 
 #include "fused_fp32.cuh"
 #include "layered_fp32.cuh"
+#include "layered_tc.cuh"
 
 using namespace pinn;
 
@@ -65,6 +66,9 @@ struct pinn_plan {
   float* act = nullptr;          // layered: [L][C_max][batch][H] jets
   float* wt = nullptr;           // layered: K_l^T copies, l = 2..L
   long long batch = 0;           // layered: points per batch (multiple of 64)
+  bool tc = false;               // layered_tf32x3: tcgen05 hidden layers (H = 128)
+  float* wimg = nullptr;         // tc: hi/lo operand images of K_l and K_l^T
+  size_t layer_stride = 0;       // tc: floats between per-layer jet buffers
   bool timing = false;
   cudaEvent_t ev0[3] = {nullptr, nullptr, nullptr}, ev1[3] = {nullptr, nullptr, nullptr};
   bool ev_valid[3] = {false, false, false};
@@ -272,6 +276,138 @@ static int run_layered(pinn_plan* p, const float* params, float* out, cudaStream
   return rc;
 }
 
+// ------------------------------------------------------------------------------------------------
+// tensor-core layered engine (H = 128): host orchestration
+// ------------------------------------------------------------------------------------------------
+static bool tc_supported(const pinn_mlp_desc& m) {
+  return (m.in_dim == 2 || m.in_dim == 3) && m.width == 128 && m.n_hidden >= 2 && m.out_dim == 3;
+}
+
+static int tc_alloc(pinn_plan* p) {
+  const pinn_mlp_desc& m = p->mlp;
+  long long max_n = 0;
+  for (const auto& ps : p->sets) max_n = ps.n_local > max_n ? ps.n_local : max_n;
+  const long long per_point = (long long)m.n_hidden * kMaxCh * tc::kH * 4;   // bytes of jets per point
+  long long budget = 4LL << 30;
+  if (const char* e = getenv("PINN_TC_WORKSPACE_MB")) {
+    const long long mb = atoll(e);
+    if (mb > 0) budget = mb << 20;
+  }
+  constexpr long long kAlign = 3840;   // lcm of the tile sizes (40, 48, 64, 80, 256 points)
+  long long batch = (budget / per_point / kAlign) * kAlign;
+  const long long need = ((max_n + kAlign - 1) / kAlign) * kAlign;
+  if (batch > need) batch = need;
+  if (batch < kAlign) batch = kAlign;
+  p->batch = batch;
+  p->layer_stride = (size_t)(6 * batch + 256) * tc::kH;
+  const size_t act_bytes = (size_t)m.n_hidden * p->layer_stride * 4;
+  const size_t img_bytes = (size_t)(m.n_hidden - 1) * tc::kLayerImgFloats * 4;
+  p->ws_bytes = act_bytes + img_bytes;
+  if (cudaMalloc(&p->act, act_bytes) != cudaSuccess) return fail(PINN_E_ALLOC, "cannot allocate %zu activation bytes", act_bytes);
+  if (cudaMalloc(&p->wimg, img_bytes) != cudaSuccess) return fail(PINN_E_ALLOC, "cannot allocate weight images");
+  return PINN_OK;
+}
+
+template <int D, int ORDER>
+static int tc_set_attrs() {
+  using S = tc::LayerSmem<tc::Geo<D, ORDER>::NR>;
+  CUDA_TRY(cudaFuncSetAttribute((const void*)tc::tc_layer<D, ORDER, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+  CUDA_TRY(cudaFuncSetAttribute((const void*)tc::tc_layer<D, ORDER, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+  CUDA_TRY(cudaFuncSetAttribute((const void*)tc::tc_layer<D, ORDER, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+  CUDA_TRY(cudaFuncSetAttribute((const void*)tc::tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kWgSmem));
+  return PINN_OK;
+}
+
+template <int D, int O, int ORDER>
+static int tc_run_set(pinn_plan* p, const float* params, float* out, cudaStream_t st, bool train, const SegDev& seg,
+                      const SegDev* seg_dev, int* launches) {
+  using G = tc::Geo<D, ORDER>;
+  using S = tc::LayerSmem<G::NR>;
+  constexpr int H = tc::kH;
+  const int L = p->mlp.n_hidden;
+  static bool attr_done = false;
+  if (!attr_done) {
+    int rc = tc_set_attrs<D, ORDER>();
+    if (rc != PINN_OK) return rc;
+    attr_done = true;
+  }
+  const int off_ko = D * H + H + (L - 1) * (H * H + H);
+  for (long long b0 = 0; b0 < seg.n; b0 += p->batch) {
+    const long long nb = (seg.n - b0 < p->batch) ? seg.n - b0 : p->batch;
+    const int tiles = (int)((nb + G::P - 1) / G::P);
+    const int grid = tiles < p->num_sms ? tiles : p->num_sms;
+    auto act = [&](int l) { return p->act + (size_t)(l - 1) * p->layer_stride; };   // jets of layer l (1-based)
+    tc::tc_layer1<D, ORDER><<<tiles, 256, 0, st>>>(params, seg.pts, seg.n, b0, act(1));
+    for (int l = 2; l <= L; ++l) {
+      const float* bias = params + D * H + H + (size_t)(l - 2) * (H * H + H) + H * H;
+      const float* img = p->wimg + (size_t)(l - 2) * tc::kLayerImgFloats;
+      tc::tc_layer<D, ORDER, 0><<<grid, tc::kLayerThreads, S::TOTAL, st>>>(img, bias, act(l - 1), act(l), params, tiles);
+    }
+    long long grid_out = ((long long)tiles * G::P + 7) / 8;
+    if (grid_out > 8LL * p->num_sms) grid_out = 8LL * p->num_sms;
+    if (train)
+      tc::tc_out_layer<D, O, ORDER, true><<<(int)grid_out, 256, 0, st>>>(params, off_ko, seg_dev, b0, tiles, act(L), out, out + p->P);
+    else
+      tc::tc_out_layer<D, O, ORDER, false><<<(int)grid_out, 256, 0, st>>>(params, off_ko, seg_dev, b0, tiles, act(L), out, out + p->P);
+    *launches += L + 1;
+    if (train) {
+      const long long total_rg = (long long)tiles * G::RG;
+      const long long chunks = (total_rg + 3) / 4;
+      const int gw = (int)(chunks < p->num_sms ? chunks : p->num_sms);
+      for (int l = L; l >= 2; --l) {
+        float* gK = out + D * H + H + (size_t)(l - 2) * (H * H + H);
+        tc::tc_wgrad<<<gw, tc::kWgThreads, tc::kWgSmem, st>>>(act(l - 1), act(l), total_rg, G::RG, G::P / 8, gK, gK + H * H);
+        const float* img = p->wimg + (size_t)(l - 2) * tc::kLayerImgFloats + 2 * tc::kImgFloats;
+        if (l > 2)
+          tc::tc_layer<D, ORDER, 1><<<grid, tc::kLayerThreads, S::TOTAL, st>>>(img, nullptr, act(l), act(l - 1), params, tiles);
+        else
+          tc::tc_layer<D, ORDER, 2><<<grid, tc::kLayerThreads, S::TOTAL, st>>>(img, nullptr, act(l), act(l - 1), params, tiles);
+        *launches += 2;
+      }
+      const int g1 = tiles < 2 * p->num_sms ? tiles : 2 * p->num_sms;
+      tc::tc_layer1_grad<D, ORDER><<<g1, 256, 0, st>>>(act(1), seg.pts, seg.n, b0, tiles, out);
+      ++*launches;
+    }
+    CUDA_TRY(cudaGetLastError());
+  }
+  return PINN_OK;
+}
+
+template <int D, int O>
+static int tc_run_t(pinn_plan* p, const float* params, float* out, cudaStream_t st, bool train, int* launches) {
+  for (int o = 2; o >= 0; --o) {
+    const LaunchTable& lt = train ? p->train[o] : p->eval[o];
+    if (p->timing && lt.n_segs > 0) CUDA_TRY(cudaEventRecord(p->ev0[o], st));
+    for (int s = 0; s < lt.n_segs; ++s) {
+      int rc;
+      if (o == 2) rc = tc_run_set<D, O, 2>(p, params, out, st, train, lt.segs_host[s], lt.segs_dev + s, launches);
+      else if (o == 1) rc = tc_run_set<D, O, 1>(p, params, out, st, train, lt.segs_host[s], lt.segs_dev + s, launches);
+      else rc = tc_run_set<D, O, 0>(p, params, out, st, train, lt.segs_host[s], lt.segs_dev + s, launches);
+      if (rc != PINN_OK) return rc;
+    }
+    if (p->timing && lt.n_segs > 0) {
+      CUDA_TRY(cudaEventRecord(p->ev1[o], st));
+      p->ev_valid[o] = true;
+    }
+  }
+  return PINN_OK;
+}
+
+static int run_tc(pinn_plan* p, const float* params, float* out, cudaStream_t st, bool train) {
+  const pinn_mlp_desc& m = p->mlp;
+  const int i_begin = train ? 0 : (int)p->P;
+  CUDA_TRY(cudaMemsetAsync(out + i_begin, 0, sizeof(float) * (size_t)(p->P + p->T - i_begin), st));
+  int launches = 0;
+  dim3 g(16, m.n_hidden - 1);
+  tc::tc_prep_weights<<<g, 256, 0, st>>>(params, m.in_dim * m.width + m.width, m.width * m.width + m.width, p->wimg);
+  ++launches;
+  int rc = PINN_E_INVALID;
+  if (m.in_dim == 3) rc = tc_run_t<3, 3>(p, params, out, st, train, &launches);
+  else if (m.in_dim == 2) rc = tc_run_t<2, 3>(p, params, out, st, train, &launches);
+  p->last_launches = launches;
+  return rc;
+}
+
 extern "C" int pinn_version(void) { return PINN_VERSION; }
 extern "C" const char* pinn_last_error(void) { return g_err; }
 
@@ -285,11 +421,14 @@ extern "C" int pinn_plan_create(const pinn_mlp_desc* mlp, const pinn_pointset_de
                 mlp->out_dim);
   FusedKernel probe;
   const bool use_fused = pick_kernel(*mlp, 0, true, &probe);
-  const bool use_layered = !use_fused && layered_supported(*mlp);
-  if (!use_fused && !use_layered)
+  const char* force = getenv("PINN_ENGINE");
+  const bool want_fp32 = force && strcmp(force, "layered_fp32") == 0;
+  const bool use_tc = !use_fused && tc_supported(*mlp) && !want_fp32;
+  const bool use_layered = !use_fused && !use_tc && layered_supported(*mlp);
+  if (!use_fused && !use_layered && !use_tc)
     return fail(PINN_E_INVALID,
-                "no engine for MLP d=%d H=%d L=%d O=%d (fused_fp32: 2-20x3-1, 2-32x3-3, 3-32x3-3; layered_fp32: "
-                "d in {2,3}, H in {64,128}, L >= 2, O = 3)", mlp->in_dim, mlp->width, mlp->n_hidden, mlp->out_dim);
+                "no engine for MLP d=%d H=%d L=%d O=%d (fused_fp32: 2-20x3-1, 2-32x3-3, 3-32x3-3; layered_tf32x3: "
+                "d in {2,3}, H = 128, L >= 2, O = 3; layered_fp32: d in {2,3}, H in {64,128}, L >= 2, O = 3)", mlp->in_dim, mlp->width, mlp->n_hidden, mlp->out_dim);
   CUDA_TRY(cudaSetDevice(device));
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
@@ -324,6 +463,17 @@ extern "C" int pinn_plan_create(const pinn_mlp_desc* mlp, const pinn_pointset_de
       pinn_plan_destroy(p);
       return rc;
     }
+  }
+  if (use_tc) {
+    p->tc = true;
+    p->engine = "layered_tf32x3";
+    int rc = tc_alloc(p);
+    if (rc != PINN_OK) {
+      pinn_plan_destroy(p);
+      return rc;
+    }
+    *out = p;
+    return PINN_OK;
   }
   if (use_layered) {
     p->layered = true;
@@ -367,6 +517,7 @@ extern "C" int pinn_plan_destroy(pinn_plan* p) {
   if (p->ws) cudaFree(p->ws);
   if (p->act) cudaFree(p->act);
   if (p->wt) cudaFree(p->wt);
+  if (p->wimg) cudaFree(p->wimg);
   for (int o = 0; o < 3; ++o) {
     if (p->ev0[o]) cudaEventDestroy(p->ev0[o]);
     if (p->ev1[o]) cudaEventDestroy(p->ev1[o]);
@@ -419,6 +570,7 @@ extern "C" int pinn_plan_set_rhs(pinn_plan* p, int32_t set_index, int32_t term_i
 
 static int run(pinn_plan* p, const float* params, float* out, cudaStream_t st, bool train) {
   if (!p || !params || !out) return fail(PINN_E_INVALID, "null argument");
+  if (p->tc) return run_tc(p, params, out, st, train);
   if (p->layered) return run_layered(p, params, out, st, train);
   const int stride = (int)(p->P + p->T);
   int rows = 0, launches = 0;

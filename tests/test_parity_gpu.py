@@ -179,7 +179,7 @@ def test_layered_engine_matches_taylor_oracle(key):
     from oracle import taylor
     name, kw = LAYERED[key]
     data, var, model, pb = _setup(name, kw)
-    assert pb.plan.engine == "layered_fp32"
+    assert pb.plan.engine == ("layered_tf32x3" if data.hidden[0] == 128 else "layered_fp32")
     total, values, grad = pb.evaluate()
     theta = torch.cat([v.reshape(-1) for v in var]).numpy()
     out = taylor.loss_and_grad(pb.compiled, theta, include_test=True)
@@ -206,6 +206,78 @@ def test_layered_engine_matches_reference_restatement_small():
     assert _rel(total, ref_total) < LOSS_RTOL
     g = grad.double().cpu().numpy()
     assert np.linalg.norm(g - ref_grad.numpy()) / np.linalg.norm(ref_grad.numpy()) < GRAD_RTOL
+
+
+def _setup_wide(name, kw, hidden, faithful=True, seed=1):
+    """a 2-D script's problem definition on a wide network (tile geometries C = 1, 3, 5 of the tensor-core engine)"""
+    from oracle import reference_step
+    data = problems.BUILDERS[name](seed=seed, **kw)
+    data.hidden = list(hidden)
+    var = reference_step.glorot_uniform_variables(data.dim, data.hidden, data.out_dim, seed=seed + 10, bias_std=0.1)
+    model = ns.TanhMLP(data.dim, data.hidden, data.out_dim, device="cuda")
+    model.set_weights([v.numpy() for v in var])
+    losses, ltest = loss_tables.build_loss_table(data, faithful=faithful)
+    pb = ns.OptimizationProblem(model.variables, losses, ltest)
+    return data, var, model, pb
+
+
+def _check_against_taylor(pb, var):
+    from oracle import taylor
+    total, values, grad = pb.evaluate()
+    theta = torch.cat([v.reshape(-1) for v in var]).numpy()
+    out = taylor.loss_and_grad(pb.compiled, theta, include_test=True)
+    ref_total, ref_vals, ref_test = assemble_losses(pb.compiled, out[pb.compiled.n_params:])
+    assert _rel(total, ref_total) < LOSS_RTOL, (total, ref_total)
+    for v, rv in zip(values, ref_vals):
+        assert _term_close(v, rv), (v, rv)
+    g = grad.double().cpu().numpy()
+    rg = out[:pb.compiled.n_params]
+    assert np.linalg.norm(g - rg) / np.linalg.norm(rg) < GRAD_RTOL
+    _, _, test_vals = pb.evaluate_all()
+    for v, rv in zip(test_vals, ref_test):
+        assert _term_close(v, rv)
+    return total, grad
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("poiseuille_flow", dict(PDE=500, BC=90, Vel=10, Pres=0, Test=60)),          # Neumann edge: C = 3 tiles
+    ("cavity_steady", dict(PDE=1111, BC=70, Vel=30, Pres=1, Test=60, noise_bnd=0.01, noise_fit=0.01)),
+])
+def test_tensor_core_engine_two_dimensional_problems(name, kw):
+    data, var, model, pb = _setup_wide(name, kw, (128,) * 3, faithful=False)
+    assert pb.plan.engine == "layered_tf32x3"
+    _check_against_taylor(pb, var)
+
+
+def test_tensor_core_engine_many_batches(monkeypatch):
+    """workspace squeezed to one 3840-point batch: 3 batches of collocation points, ragged last tile"""
+    monkeypatch.setenv("PINN_TC_WORKSPACE_MB", "1")
+    name, kw = LAYERED["unsteady_8x128"]
+    kw = dict(kw, PDE=9001)
+    data, var, model, pb = _setup(name, kw)
+    assert pb.plan.engine == "layered_tf32x3"
+    _check_against_taylor(pb, var)
+
+
+def test_tensor_core_engine_agrees_with_fp32_layered_engine(monkeypatch):
+    name, kw = LAYERED["unsteady_8x128"]
+    data, var, model, pb = _setup(name, kw)
+    t1, v1, g1 = pb.evaluate()
+    monkeypatch.setenv("PINN_ENGINE", "layered_fp32")
+    data, var, model, pb2 = _setup(name, kw)
+    assert pb2.plan.engine == "layered_fp32"
+    t2, v2, g2 = pb2.evaluate()
+    assert _rel(t1, t2) < LOSS_RTOL
+    assert float((g1 - g2).norm() / g2.norm()) < GRAD_RTOL
+
+
+def test_tensor_core_engine_is_deterministic_in_loss_terms():
+    name, kw = LAYERED["unsteady_8x128"]
+    data, var, model, pb = _setup(name, kw)
+    t1, v1, g1 = pb.evaluate()
+    t2, v2, g2 = pb.evaluate()
+    assert _rel(t1, t2) < 1e-6
+    assert float((g1 - g2).norm() / g2.norm()) < 1e-5      # atomics: summation order varies
 
 
 def test_layered_model_forward():

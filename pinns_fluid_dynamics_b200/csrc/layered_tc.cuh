@@ -10,14 +10,20 @@
 //     the hardware, which is why both halves of the split are rounded to TF32 explicitly.
 //
 // Orientation: D[neuron j (TMEM lane)][row n (TMEM column)] = sum_k W[j][k] * Act[n][k].  A tile is P points
-// x C channels, rows n = c*P + p, NR = C*P in {240, 256}.  An epilogue thread owns one neuron of one TMEM
-// lane quarter and sees every channel of a point in its own registers, so the tanh-jet (and its adjoint)
-// needs no cross-lane traffic.
+// x C channels, rows n = c*P + p, NR = C*P <= 240.  An epilogue thread owns one neuron of one TMEM lane
+// quarter and sees every channel of a point in its own registers, so the tanh-jet (and its adjoint) needs no
+// cross-lane traffic.
 //
-// HBM layout of every jet buffer (a-jets and z-bar alike): the UMMA K-major core-matrix tiling itself,
-//   off(n, k) = tile*NR*128 + (n/8)*1024 + (k/4)*32 + (n%8)*4 + (k%4)          [floats]
-// so a (row-group, K-chunk) block is contiguous for the producers of the forward/backward GEMMs, and a
-// 4-row x 4-neuron block is 64 contiguous bytes for the transposing producer of the weight-gradient GEMM.
+// HBM layout of every jet buffer (a-jets and z-bar alike), per tile: 16-byte chunks hold 4 CONSECUTIVE ROWS of
+// one neuron, 8 neurons per 128-byte line,
+//   off(n, k) = tile*NR*128 + (k/8)*(NR*8) + (n/4)*32 + (k%8)*4 + (n%4)          [floats]
+// * epilogue threads (neuron k, 4-point groups) load / store whole chunks: a warp instruction touches 4 full
+//   128-byte lines (the first version's 4-byte scattered accesses kept the LSU data pipe at 60-70 %);
+// * it is the UMMA K-major core-matrix tiling of the TRANSPOSED operand, i.e. exactly what the weight-gradient
+//   GEMM (contraction over rows) reads: its producer is a straight copy;
+// * the forward / backward producers load 4-neuron x 4-row blocks (64 contiguous bytes) and transpose them in
+//   registers; the row-group stride of their shared-memory stage blocks is padded to 528 B so those 16-byte
+//   stores are bank-conflict free.
 //
 //   tc_prep_weights     hi/lo images of K_l (backward operand) and K_l^T (forward operand)
 //   tc_layer1           a-jets of layer 1 (SIMT)
@@ -39,14 +45,19 @@ constexpr int kH = 128;
 template <int D, int ORDER>
 struct Geo {
   static constexpr int C = n_channels(D, ORDER);
-  static constexpr int P = C == 6 ? 40 : C == 5 ? 48 : C == 4 ? 64 : C == 3 ? 80 : 256;   // points per tile
+  static constexpr int P = C == 6 ? 40 : C == 5 ? 48 : C == 4 ? 56 : C == 3 ? 80 : 240;   // points per tile
   static constexpr int NR = C * P;                                                       // rows per tile = MMA N
-  static constexpr int RG = NR / 8;                                                      // 8-row groups per tile
-  static_assert(NR % 16 == 0 && NR <= 256 && P % 8 == 0, "tile geometry");
+  static_assert(NR % 16 == 0 && NR <= 240 && P % 8 == 0, "tile geometry");
 };
 
-__host__ __device__ __forceinline__ size_t act_off(int n, int k) {
-  return (size_t)(n >> 3) * (8 * kH) + (size_t)(k >> 2) * 32 + (size_t)(n & 7) * 4 + (size_t)(k & 3);
+// jet buffers: element (row n, neuron k) of a tile, in floats
+template <int NR>
+__host__ __device__ __forceinline__ size_t jet_off(int n, int k) {
+  return (size_t)(k >> 3) * (NR * 8) + (size_t)(n >> 2) * 32 + (size_t)(k & 7) * 4 + (size_t)(n & 3);
+}
+// weight images: K-major core-matrix tiling of a 128 x 128 operand (row m, contraction index k), in floats
+__host__ __device__ __forceinline__ size_t img_off(int m, int k) {
+  return (size_t)(m >> 3) * (8 * kH) + (size_t)(k >> 2) * 32 + (size_t)(m & 7) * 4 + (size_t)(k & 3);
 }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -66,8 +77,15 @@ __device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
   hi = umma::rna_tf32(x);
   lo = umma::rna_tf32(x - hi);
 }
+// activation split on the hot path: hi rounded to nearest by integer arithmetic (2 ops), lo = x - hi exact and
+// left for the tensor core to truncate.  lo's sign is independent of x's (hi is rounded, not truncated), so that
+// truncation is zero-mean: no bias, error <= 2^-22 |x|.  (cvt.rna.tf32 expands to 4 instructions on sm_100a.)
+__device__ __forceinline__ void tf32_split_fast(float x, float& hi, float& lo) {
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+  lo = x - hi;
+}
 __device__ __forceinline__ void tf32_split4(const float4& v, float4& hi, float4& lo) {
-  tf32_split(v.x, hi.x, lo.x); tf32_split(v.y, hi.y, lo.y); tf32_split(v.z, hi.z, lo.z); tf32_split(v.w, hi.w, lo.w);
+  tf32_split_fast(v.x, hi.x, lo.x); tf32_split_fast(v.y, hi.y, lo.y); tf32_split_fast(v.z, hi.z, lo.z); tf32_split_fast(v.w, hi.w, lo.w);
 }
 
 // ---- weight images -------------------------------------------------------------------------------
@@ -85,7 +103,7 @@ __global__ void tc_prep_weights(const float* __restrict__ params, int off0, int 
     const int i = idx / kH, j = idx % kH;
     float hi, lo;
     tf32_split(K[idx], hi, lo);
-    const size_t f = act_off(j, i), b = act_off(i, j);
+    const size_t f = img_off(j, i), b = img_off(i, j);
     out[f] = hi;
     out[kImgFloats + f] = lo;
     out[2 * kImgFloats + b] = hi;
@@ -115,7 +133,7 @@ __global__ void __launch_bounds__(256) tc_layer1(const float* __restrict__ param
     float a[C];
     layered::jet_fwd<D, ORDER>(tanh_accurate(z), zd, 0.f, 0.f, a);
 #pragma unroll
-    for (int c = 0; c < C; ++c) out[act_off(c * P + p, j)] = a[c];
+    for (int c = 0; c < C; ++c) out[jet_off<G::NR>(c * P + p, j)] = a[c];
   }
 }
 
@@ -168,7 +186,7 @@ template <int REGS> __device__ __forceinline__ void reg_inc() { asm volatile("se
 // lives for one K-chunk of 32 (12 MMAs, small lo-terms first): two TMEM buffers ping-pong by chunk and the
 // epilogue warps add each finished chunk into FP32 registers with round-to-nearest.  Warp roles (4 warp
 // groups, registers redistributed with setmaxnreg):
-//   WG0  warps 0-3    producers  global jets -> rna hi/lo split -> K-major stage blocks
+//   WG0  warps 0-3    producers  global jets -> hi/lo split -> K-major stage blocks (2 stages prefetched in registers)
 //   WG1-2 warps 4-11  epilogue   thread = neuron of lane quarter warp%4, half of the tile's points per group
 //   WG3  warp 12      MMA issuer (one lane); warps 13-15 idle
 constexpr int kProdWarps = 4;
@@ -183,7 +201,8 @@ constexpr int kChunks = kH / (kKC * kStagesPerChunk);
 template <int NR>
 struct LayerSmem {
   static constexpr int W_BYTES = 2 * kH * kH * 4;          // hi + lo images of the layer's A operand
-  static constexpr int HALF = NR * kKC * 4;                // one stage's hi (or lo) B block
+  static constexpr int SBO = (kKC / 4) * 128 + 16;         // padded row-group stride of a stage block (528 B)
+  static constexpr int HALF = (NR / 8) * SBO;              // one stage's hi (or lo) B block
   static constexpr int STAGE = 2 * HALF;
   static constexpr int BAR_OFF = W_BYTES + kStages * STAGE;
   static constexpr int TOTAL = BAR_OFF + 128;
@@ -223,47 +242,78 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer(const float* __rest
   const uint32_t tmem = *tslot;
 
   if (warp < kProdWarps) {
-    // ===== producers =====
-    reg_dec<96>();
+    // ===== producers: two stages of loads in flight in registers (HBM latency x 21 B/cycle/SM ~ 30 KB) =====
     if (tid == 0) {
       mbar_expect_tx(wbar, S::W_BYTES);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
         tma_bulk_g2s(sW + i * (S::W_BYTES / 4), reinterpret_cast<const uint8_t*>(w_img) + i * (S::W_BYTES / 4), S::W_BYTES / 4, wbar);
     }
+    constexpr int NKC = kH / kKC;
+    const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int T = my_tiles * NKC;                          // this CTA's stage sequence: t -> (tile, k-chunk)
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const uint8_t* src = reinterpret_cast<const uint8_t*>(act_in + (size_t)tile * NR * kH);
-#pragma unroll 1
-      for (int kc = 0; kc < kH / kKC; ++kc) {
-        mbar_wait(&empty[stage], phase ^ 1u);
-        uint8_t* dst = sStage + stage * S::STAGE;
-        float4 v[8];
+    // a stage = 16 neurons (2 groups of 8) x NR rows.  Block (rb, kb) = rows 4rb..4rb+3 x neurons 4kb..4kb+3 of
+    // the stage = 64 contiguous bytes; thread t, pass u: kb = (t>>3)&3, rb = (t&7) + 8*(t>>5) + 32u, so the 8 lanes
+    // of a 16-byte store phase hit 8 distinct bank groups (row-group stride 528 B).
+    constexpr int NRB = NR / 4;
+    const int kb = (tid >> 3) & 3, rb0 = (tid & 7) + 8 * (tid >> 5);
+    auto issue = [&](int t, float4 (&v)[8]) {
+      if (t >= T) return;
+      const int tile = (int)blockIdx.x + (t / NKC) * (int)gridDim.x, kc = t % NKC;
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(act_in + (size_t)tile * NR * kH) +
+                           (size_t)(kc * 2 + (kb >> 1)) * (NR * 32) + (kb & 1) * 64;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int x = tid + 128 * i;                       // 16-byte chunk: row-group x/32, (k-chunk, row) x%32
-          if (x < NR * 4) v[i] = __ldg(reinterpret_cast<const float4*>(src + (size_t)(x >> 5) * 4096 + kc * 512 + (x & 31) * 16));
+      for (int u = 0; u < 2; ++u) {
+        const int rb = rb0 + 32 * u;
+        if (rb < NRB) {
+          const float4* p = reinterpret_cast<const float4*>(src + rb * 128);
+#pragma unroll
+          for (int r = 0; r < 4; ++r) v[4 * u + r] = __ldg(p + r);       // v[4u + r] = neuron 4kb + r, rows 4rb..4rb+3
         }
+      }
+    };
+    auto consume = [&](const float4 (&v)[8]) {
+      mbar_wait(&empty[stage], phase ^ 1u);
+      uint8_t* dst = sStage + stage * S::STAGE;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int x = tid + 128 * i;
-          if (x < NR * 4) {
+      for (int u = 0; u < 2; ++u) {
+        const int rb = rb0 + 32 * u;
+        if (rb < NRB) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {                                   // row 4rb + r: the 4 neurons of this block
+            const float e0 = r == 0 ? v[4 * u + 0].x : r == 1 ? v[4 * u + 0].y : r == 2 ? v[4 * u + 0].z : v[4 * u + 0].w;
+            const float e1 = r == 0 ? v[4 * u + 1].x : r == 1 ? v[4 * u + 1].y : r == 2 ? v[4 * u + 1].z : v[4 * u + 1].w;
+            const float e2 = r == 0 ? v[4 * u + 2].x : r == 1 ? v[4 * u + 2].y : r == 2 ? v[4 * u + 2].z : v[4 * u + 2].w;
+            const float e3 = r == 0 ? v[4 * u + 3].x : r == 1 ? v[4 * u + 3].y : r == 2 ? v[4 * u + 3].z : v[4 * u + 3].w;
             float4 hi, lo;
-            tf32_split4(v[i], hi, lo);
-            *reinterpret_cast<float4*>(dst + x * 16) = hi;
-            *reinterpret_cast<float4*>(dst + S::HALF + x * 16) = lo;
+            tf32_split4(make_float4(e0, e1, e2, e3), hi, lo);
+            const int n = 4 * rb + r;
+            const uint32_t off = (uint32_t)(n >> 3) * S::SBO + (uint32_t)kb * 128u + (uint32_t)(n & 7) * 16u;
+            *reinterpret_cast<float4*>(dst + off) = hi;
+            *reinterpret_cast<float4*>(dst + S::HALF + off) = lo;
           }
         }
-        umma::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full[stage]);
-        if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
+      umma::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[stage]);
+      if (++stage == kStages) { stage = 0; phase ^= 1u; }
+    };
+    float4 va[8], vb[8], vc[8];
+    issue(0, va);
+    issue(1, vb);
+#pragma unroll 1
+    for (int t = 0; t < T; t += 3) {
+      issue(t + 2, vc);
+      consume(va);
+      if (t + 1 < T) { issue(t + 3, va); consume(vb); }
+      if (t + 2 < T) { issue(t + 4, vb); consume(vc); }
     }
   } else if (warp >= kMmaWarp) {
     // ===== MMA issuer =====
-    reg_dec<32>();
+    reg_dec<24>();
     if (warp == kMmaWarp && lane == 0) {
       mbar_wait(wbar, 0);
       const uint32_t idesc = umma::idesc_tf32(kH, NR);
@@ -290,8 +340,8 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer(const float* __rest
             for (int ks = 0; ks < kKC / 8; ++ks) {
               a_hi_d[ks] = umma::smem_desc(w_hi + ka + ks * 256, 128, 4096);
               a_lo_d[ks] = umma::smem_desc(w_lo + ka + ks * 256, 128, 4096);
-              b_hi_d[ks] = umma::smem_desc(b_hi + ks * 256, 128, (kKC / 4) * 128);
-              b_lo_d[ks] = umma::smem_desc(b_lo + ks * 256, 128, (kKC / 4) * 128);
+              b_hi_d[ks] = umma::smem_desc(b_hi + ks * 256, 128, S::SBO);
+              b_lo_d[ks] = umma::smem_desc(b_lo + ks * 256, 128, S::SBO);
             }
             // small terms first: they meet a small accumulator
 #pragma unroll
@@ -309,9 +359,12 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer(const float* __rest
     }
   } else {
     // ===== epilogue: chunk partial sums TMEM -> FP32 registers; tanh-jet (or its adjoint) -> global =====
-    reg_inc<184>();
+    // A thread owns neuron j and the points p = 8*g + 4*half + i (g < P/8, i < 4) of the tile: 4-point groups
+    // alternate between the two warp groups, so every global / TMEM offset below is base + compile-time constant.
+    reg_inc<176>();
     const int q = warp & 3, half = (warp - kProdWarps) >> 2;
     const int j = q * 32 + lane;
+    constexpr int NG = P / 8;                  // 4-point groups per thread
     float bj = 0.f;
     float k1[D];
 #pragma unroll
@@ -321,40 +374,40 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer(const float* __rest
 #pragma unroll
       for (int i = 0; i < D; ++i) k1[i] = __ldg(params + i * kH + j);
     }
+    const size_t thr_off = (size_t)(j >> 3) * (NR * 8) + (size_t)half * 32 + (size_t)(j & 7) * 4;
     int g = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      float* io = act_io + (size_t)tile * NR * kH;
-      float acc[C][PH];
+      float* io = act_io + (size_t)tile * NR * kH + thr_off;       // chunk (c, g) = 4 points at io[(c*P/4 + 2g)*32]
+      float acc[C][NG][4];
 #pragma unroll 1
       for (int ch = 0; ch < kChunks; ++ch, ++g) {
         const int buf = g & 1;
         mbar_wait(&tfull[buf], (uint32_t)((g >> 1) & 1));
         umma::fence_after_thread_sync();
-        const uint32_t tb = tmem + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * PH);
+        const uint32_t tb = tmem + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 4);
         if (ch == 0) {
 #pragma unroll
-          for (int c = 0; c < C; ++c) tmem_ld_span<PH>(tb + (uint32_t)(c * P), acc[c]);
+          for (int c = 0; c < C; ++c)
+#pragma unroll
+            for (int gg = 0; gg < NG; ++gg) tmem_ld_n<4>(tb + (uint32_t)(c * P + 8 * gg), acc[c][gg]);
           tmem_ld_wait();
         } else {
+          constexpr int GB = NG < 8 ? NG : 8;                      // groups per batch of loads (<= 32 registers)
 #pragma unroll
           for (int c = 0; c < C; ++c) {
 #pragma unroll
-            for (int o = 0; o < PH; o += 32) {
-              constexpr int W0 = PH < 32 ? PH : 32;
-              float t[W0];
-              if (PH - o >= W0) {
-                tmem_ld_span<W0>(tb + (uint32_t)(c * P + o), t);
-                tmem_ld_wait();
+            for (int g0 = 0; g0 < NG; g0 += GB) {
+              float t[GB][4];
 #pragma unroll
-                for (int i = 0; i < W0; ++i) acc[c][o + i] += t[i];
-              } else {
-                constexpr int W1 = PH % 32 == 0 ? 4 : PH % 32;    // tail of a span longer than 32 (PH = 40: 8)
-                float u[W1];
-                tmem_ld_span<W1>(tb + (uint32_t)(c * P + o), u);
-                tmem_ld_wait();
+              for (int gg = 0; gg < GB; ++gg)
+                if (g0 + gg < NG) tmem_ld_n<4>(tb + (uint32_t)(c * P + 8 * (g0 + gg)), t[gg]);
+              tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < W1; ++i) acc[c][o + i] += u[i];
-              }
+              for (int gg = 0; gg < GB; ++gg)
+                if (g0 + gg < NG) {
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) acc[c][g0 + gg][i] += t[gg][i];
+                }
             }
           }
         }
@@ -362,38 +415,42 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer(const float* __rest
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[buf]);
       }
-      // ---- elementwise: 4 points at a time ----
+      // ---- elementwise: one 4-point group at a time ----
 #pragma unroll
-      for (int i0 = 0; i0 < PH; i0 += 4) {
-        const int p0 = half * PH + i0;
+      for (int gg = 0; gg < NG; ++gg) {
         float aj[C][4];
         if constexpr (MODE == 1) {
 #pragma unroll
-          for (int c = 0; c < C; ++c)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) aj[c][i] = io[act_off(c * P + p0 + i, j)];
+          for (int c = 0; c < C; ++c) {
+            const float4 t4 = *reinterpret_cast<const float4*>(io + (c * (P / 4) + 2 * gg) * 32);
+            aj[c][0] = t4.x; aj[c][1] = t4.y; aj[c][2] = t4.z; aj[c][3] = t4.w;
+          }
         } else if constexpr (MODE == 2) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) aj[0][i] = io[act_off(p0 + i, j)];
+          const float4 t4 = *reinterpret_cast<const float4*>(io + (2 * gg) * 32);
+          aj[0][0] = t4.x; aj[0][1] = t4.y; aj[0][2] = t4.z; aj[0][3] = t4.w;
         }
+        float out4[C][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           float res[C];
           if constexpr (MODE == 0) {
             float zd[D], zxx = 0.f, zyy = 0.f;
 #pragma unroll
-            for (int t = 0; t < D; ++t) zd[t] = ORDER >= 1 ? acc[(ORDER >= 1) ? 1 + t : 0][i0 + i] : 0.f;
-            if constexpr (ORDER >= 2) { zxx = acc[(ORDER >= 2) ? 1 + D : 0][i0 + i]; zyy = acc[(ORDER >= 2) ? 2 + D : 0][i0 + i]; }
-            layered::jet_fwd<D, ORDER>(tanh_accurate(acc[0][i0 + i] + bj), zd, zxx, zyy, res);
+            for (int t = 0; t < D; ++t) zd[t] = ORDER >= 1 ? acc[(ORDER >= 1) ? 1 + t : 0][gg][i] : 0.f;
+            if constexpr (ORDER >= 2) { zxx = acc[(ORDER >= 2) ? 1 + D : 0][gg][i]; zyy = acc[(ORDER >= 2) ? 2 + D : 0][gg][i]; }
+            layered::jet_fwd<D, ORDER>(tanh_accurate(acc[0][gg][i] + bj), zd, zxx, zyy, res);
           } else {
             float a1[C], ab[C];
 #pragma unroll
-            for (int c = 0; c < C; ++c) { a1[c] = (MODE == 2 && c > 0) ? 0.f : aj[c][i]; ab[c] = acc[c][i0 + i]; }
+            for (int c = 0; c < C; ++c) { a1[c] = (MODE == 2 && c > 0) ? 0.f : aj[c][i]; ab[c] = acc[c][gg][i]; }
             layered::jet_bwd<D, ORDER, MODE == 2>(a1, k1, ab, res);
           }
 #pragma unroll
-          for (int c = 0; c < C; ++c) io[act_off(c * P + p0 + i, j)] = res[c];
+          for (int c = 0; c < C; ++c) out4[c][i] = res[c];
         }
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+          *reinterpret_cast<float4*>(io + (c * (P / 4) + 2 * gg) * 32) = make_float4(out4[c][0], out4[c][1], out4[c][2], out4[c][3]);
       }
     }
   }
@@ -404,38 +461,39 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer(const float* __rest
 
 // ---- tcgen05 weight gradient -----------------------------------------------------------------------
 // gK[i][j] += sum_rows a_prev[row][i] * zbar[row][j]; gb[j] += sum over value-channel rows of zbar[row][j].
-// The contraction runs over ROWS, so both operands are transposed on the way into shared memory: a
-// producer thread loads a 4-row x 4-neuron block (64 contiguous bytes) and stores four 16-byte K-chunks.
-// Row-group stride of the operand tiles is padded (1040 B) so those stores are bank-conflict free.
-// The TMEM accumulator lives for 4 stages (128 rows, 48 MMAs); drain warps add it into FP32 registers
+// The contraction runs over ROWS and the jet layout already is the K-major core-matrix tiling of the
+// transposed operands (16-byte chunk = 4 rows of a neuron), so the producers copy 16-row slabs
+// (16 neuron groups x 512 contiguous bytes) straight into the stage blocks, splitting hi/lo on the way.
+// The TMEM accumulator lives for 8 stages (128 rows, 48 MMAs); drain warps add it into FP32 registers
 // (same truncation argument as tc_layer) and flush the 128 x 128 block with atomics at the end.
 constexpr int kWgThreads = 288;           // 4 producer warps, 4 drain warps, 1 MMA warp
 constexpr int kWgMmaWarp = 8;
-constexpr int kWgRows = 32;               // rows (K) per stage
-constexpr int kWgStagesPerChunk = 4;
-constexpr int kWgSBO = (kWgRows / 4) * 128 + 16;
-constexpr int kWgOp = (kH / 8) * kWgSBO;  // bytes of one operand tile (128 x 32, padded): 16640
+constexpr int kWgRows = 16;               // rows (K) per stage
+constexpr int kWgStages = 6;
+constexpr int kWgStagesPerChunk = 8;
+constexpr int kWgOp = kH * kWgRows * 4;   // bytes of one operand block (128 neurons x 16 rows): 8192
 constexpr int kWgStage = 4 * kWgOp;       // A hi, A lo, Z hi, Z lo
-constexpr int kWgBarOff = kStages * kWgStage;
+constexpr int kWgBarOff = kWgStages * kWgStage;
 constexpr int kWgSmem = kWgBarOff + 128 + kH * 4;
 
+// slabs: 16-row slabs of the batch; a tile holds NR/16 of them (NR % 16 == 0); value-channel rows are the
+// first P rows of a tile = its first P/16 slabs when P % 16 == 0 -- in general rows [0, P): checked per chunk.
 __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad(const float* __restrict__ act_prev, const float* __restrict__ zbar,
-                                                          long long total_rg, int rg_per_tile, int val_rg, float* __restrict__ gK,
+                                                          long long n_slabs, int NR, int P, float* __restrict__ gK,
                                                           float* __restrict__ gb) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kWgBarOff);
-  uint64_t* empty = full + kStages;
-  uint64_t* tfull = empty + kStages;     // [2]
+  uint64_t* empty = full + kWgStages;
+  uint64_t* tfull = empty + kWgStages;   // [2]
   uint64_t* tempty = tfull + 2;          // [2]
   uint32_t* tslot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* sB = reinterpret_cast<float*>(smem + kWgBarOff + 128);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const long long n_stages = (total_rg + 3) / 4;             // 32-row stages in the batch
-  // this CTA's stages: s = blockIdx.x, blockIdx.x + gridDim.x, ...
-  const long long my_stages = n_stages > (long long)blockIdx.x ? (n_stages - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int slabs_per_tile = NR / kWgRows;
+  const long long my_stages = n_slabs > (long long)blockIdx.x ? (n_slabs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const long long my_chunks = (my_stages + kWgStagesPerChunk - 1) / kWgStagesPerChunk;
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 4); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kWgStages; ++s) { mbar_init(&full[s], 4); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
     fence_barrier_init();
   }
@@ -447,78 +505,63 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad(const float* __restric
   const uint32_t tmem = *tslot;
 
   if (warp < 4) {
-    // ===== producers (transposing) =====
-    float bsum[2][4];
+    // ===== producers: chunk x = tid + 128 u (u < 4) of a 512-chunk operand block: neuron group ig = x>>5,
+    // row chunk rc = (x>>3)&3, neuron-in-group i7 = x&7; shared-memory offset = 16 x (the block is compact) =====
+    float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+    const int rc = (tid >> 3) & 3, i7 = tid & 7, ig0 = tid >> 5;
+    const size_t kb_bytes = (size_t)NR * 32;                     // bytes between neuron groups of a tile
+    auto issue = [&](long long st, float4 (&v)[2][4], bool& val) {
+      val = false;
+      if (st >= n_slabs) return;
+      const long long tile = st / slabs_per_tile;
+      const int slab = (int)(st % slabs_per_tile);
+      const int row0 = slab * kWgRows + rc * 4;                  // first of this thread's 4 rows inside the tile
+      val = row0 < P;                                            // value-channel rows (P % 4 == 0)
+      const size_t base = (size_t)tile * NR * kH * 4 + (size_t)(row0 >> 2) * 128 + i7 * 16;
 #pragma unroll
-    for (int u = 0; u < 2; ++u)
+      for (int mat = 0; mat < 2; ++mat) {
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(mat == 0 ? act_prev : zbar) + base;
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) bsum[u][cc] = 0.f;
+        for (int u = 0; u < 4; ++u) v[mat][u] = *reinterpret_cast<const float4*>(src + (size_t)(ig0 + 4 * u) * kb_bytes);
+      }
+    };
     int stage = 0;
     uint32_t phase = 0;
-    for (long long st = blockIdx.x; st < n_stages; st += gridDim.x) {
+    auto consume = [&](const float4 (&v)[2][4], bool val) {
       mbar_wait(&empty[stage], phase ^ 1u);
       uint8_t* dst = smem + stage * kWgStage;
 #pragma unroll
-      for (int mat = 0; mat < 2; ++mat) {
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(mat == 0 ? act_prev : zbar);
-        float4 v[2][4];
-        int kcs[2], rgs[2], rhs[2];
-        bool valrow[2];
+      for (int mat = 0; mat < 2; ++mat)
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          // 64 blocks per row-group: lanes 0..15 -> neuron chunk, lane>>4 -> row half; second warp of a pair -> chunk + 16
-          const int b = tid + 128 * u;
-          const int rg = b >> 6, w = b & 63;
-          const int kc = (w & 15) + 16 * (w >> 5), rh = (w >> 4) & 1;
-          kcs[u] = kc; rgs[u] = rg; rhs[u] = rh;
-          const long long frg = st * 4 + rg;
-          valrow[u] = false;
-          if (frg < total_rg) {
-            const float4* p = reinterpret_cast<const float4*>(src + (size_t)frg * 4096 + kc * 128 + rh * 64);
-#pragma unroll
-            for (int r = 0; r < 4; ++r) v[u][r] = p[r];
-            valrow[u] = (int)(frg % rg_per_tile) < val_rg;
-          } else {
-#pragma unroll
-            for (int r = 0; r < 4; ++r) v[u][r] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+        for (int u = 0; u < 4; ++u) {
+          float4 hi, lo;
+          tf32_split4(v[mat][u], hi, lo);
+          const uint32_t off = (uint32_t)(tid + 128 * u) * 16u;
+          *reinterpret_cast<float4*>(dst + (mat * 2) * kWgOp + off) = hi;
+          *reinterpret_cast<float4*>(dst + (mat * 2 + 1) * kWgOp + off) = lo;
+          if (mat == 1 && val) bsum[u] += (v[mat][u].x + v[mat][u].y) + (v[mat][u].z + v[mat][u].w);
         }
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          if (mat == 1 && valrow[u]) {
-#pragma unroll
-            for (int r = 0; r < 4; ++r) { bsum[u][0] += v[u][r].x; bsum[u][1] += v[u][r].y; bsum[u][2] += v[u][r].z; bsum[u][3] += v[u][r].w; }
-          }
-          uint8_t* hi = dst + (mat * 2) * kWgOp;
-          uint8_t* lo = hi + kWgOp;
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            const int m = 4 * kcs[u] + cc;
-            const uint32_t off = (uint32_t)(m >> 3) * kWgSBO + (uint32_t)(rgs[u] * 2 + rhs[u]) * 128u + (uint32_t)(m & 7) * 16u;
-            const float e0 = cc == 0 ? v[u][0].x : cc == 1 ? v[u][0].y : cc == 2 ? v[u][0].z : v[u][0].w;
-            const float e1 = cc == 0 ? v[u][1].x : cc == 1 ? v[u][1].y : cc == 2 ? v[u][1].z : v[u][1].w;
-            const float e2 = cc == 0 ? v[u][2].x : cc == 1 ? v[u][2].y : cc == 2 ? v[u][2].z : v[u][2].w;
-            const float e3 = cc == 0 ? v[u][3].x : cc == 1 ? v[u][3].y : cc == 2 ? v[u][3].z : v[u][3].w;
-            float4 h4, l4;
-            tf32_split4(make_float4(e0, e1, e2, e3), h4, l4);
-            *reinterpret_cast<float4*>(hi + off) = h4;
-            *reinterpret_cast<float4*>(lo + off) = l4;
-          }
-        }
-      }
       umma::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[stage]);
-      if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
+    };
+    // three slabs of loads in flight
+    float4 va[2][4], vb[2][4], vc[2][4];
+    bool ra, rb, rcv;
+    const long long G = gridDim.x;
+    issue(blockIdx.x, va, ra);
+    issue(blockIdx.x + G, vb, rb);
+#pragma unroll 1
+    for (long long st = blockIdx.x; st < n_slabs; st += 3 * G) {
+      issue(st + 2 * G, vc, rcv);
+      consume(va, ra);
+      if (st + G < n_slabs) { issue(st + 3 * G, va, ra); consume(vb, rb); }
+      if (st + 2 * G < n_slabs) { issue(st + 4 * G, vb, rb); consume(vc, rcv); }
     }
-    // bias gradient: threads sharing a neuron chunk meet in shared memory
+    // bias gradient: thread (tid, u) always holds neuron 8*(ig0 + 4u) + i7
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int b = tid + 128 * u, w = b & 63;
-      const int kc = (w & 15) + 16 * (w >> 5);
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) atomicAdd(&sB[4 * kc + cc], bsum[u][cc]);
-    }
+    for (int u = 0; u < 4; ++u) atomicAdd(&sB[8 * (ig0 + 4 * u) + i7], bsum[u]);
     asm volatile("bar.sync 1, 128;" ::: "memory");
     if (my_stages > 0) atomicAdd(gb + tid, sB[tid]);
   } else if (warp < 8) {
@@ -552,6 +595,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad(const float* __restric
   } else if (warp == kWgMmaWarp && lane == 0) {
     const uint32_t idesc = umma::idesc_tf32(kH, kH);
     const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(smem);
+    constexpr uint32_t SBO = (kWgRows / 4) * 128;              // 512: neuron-group stride inside an operand block
     int stage = 0;
     uint32_t phase = 0;
     long long done_stages = 0;
@@ -567,17 +611,17 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad(const float* __restric
         const uint32_t a_hi = s0 + stage * kWgStage, a_lo = a_hi + kWgOp, z_hi = a_lo + kWgOp, z_lo = z_hi + kWgOp;
 #pragma unroll
         for (int ks = 0; ks < kWgRows / 8; ++ks) {
-          umma::mma_tf32_ss(d, umma::smem_desc(a_lo + ks * 256, 128, kWgSBO), umma::smem_desc(z_hi + ks * 256, 128, kWgSBO), idesc, acc);
+          umma::mma_tf32_ss(d, umma::smem_desc(a_lo + ks * 256, 128, SBO), umma::smem_desc(z_hi + ks * 256, 128, SBO), idesc, acc);
           acc = 1;
         }
 #pragma unroll
         for (int ks = 0; ks < kWgRows / 8; ++ks)
-          umma::mma_tf32_ss(d, umma::smem_desc(a_hi + ks * 256, 128, kWgSBO), umma::smem_desc(z_lo + ks * 256, 128, kWgSBO), idesc, 1);
+          umma::mma_tf32_ss(d, umma::smem_desc(a_hi + ks * 256, 128, SBO), umma::smem_desc(z_lo + ks * 256, 128, SBO), idesc, 1);
 #pragma unroll
         for (int ks = 0; ks < kWgRows / 8; ++ks)
-          umma::mma_tf32_ss(d, umma::smem_desc(a_hi + ks * 256, 128, kWgSBO), umma::smem_desc(z_hi + ks * 256, 128, kWgSBO), idesc, 1);
+          umma::mma_tf32_ss(d, umma::smem_desc(a_hi + ks * 256, 128, SBO), umma::smem_desc(z_hi + ks * 256, 128, SBO), idesc, 1);
         umma::commit(&empty[stage]);
-        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
       }
       umma::commit(&tfull[buf]);
     }
@@ -602,12 +646,12 @@ __global__ void __launch_bounds__(256) tc_out_layer(const float* __restrict__ pa
   const long long n = seg->n;
   const float* Ko = params + off_ko;
   const float* bo = Ko + H * O;
-  // lane owns k = 4*lane + q (q = 0..3): one 16-byte chunk of every row
+  // lane owns neurons k = lane + 32 q
   float ko[KL][O];
 #pragma unroll
   for (int q = 0; q < KL; ++q)
 #pragma unroll
-    for (int o = 0; o < O; ++o) ko[q][o] = __ldg(Ko + (4 * lane + q) * O + o);
+    for (int o = 0; o < O; ++o) ko[q][o] = __ldg(Ko + (lane + 32 * q) * O + o);
   float gko[KL][O];
 #pragma unroll
   for (int q = 0; q < KL; ++q)
@@ -631,8 +675,8 @@ __global__ void __launch_bounds__(256) tc_out_layer(const float* __restrict__ pa
     float J[C][O];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      const float4 av = *reinterpret_cast<const float4*>(base + act_off(c * P + p, 4 * lane));
-      a[c][0] = av.x; a[c][1] = av.y; a[c][2] = av.z; a[c][3] = av.w;
+#pragma unroll
+      for (int q = 0; q < KL; ++q) a[c][q] = base[jet_off<G::NR>(c * P + p, lane + 32 * q)];
 #pragma unroll
       for (int o = 0; o < O; ++o) J[c][o] = 0.f;
 #pragma unroll
@@ -727,14 +771,15 @@ __global__ void __launch_bounds__(256) tc_out_layer(const float* __restrict__ pa
       }
 #pragma unroll
       for (int c = 0; c < C; ++c)
-        *reinterpret_cast<float4*>(base + act_off(c * P + p, 4 * lane)) = make_float4(zout[c][0], zout[c][1], zout[c][2], zout[c][3]);
+#pragma unroll
+        for (int q = 0; q < KL; ++q) base[jet_off<G::NR>(c * P + p, lane + 32 * q)] = zout[c][q];
     }
   }
   if constexpr (TRAIN) {
 #pragma unroll
     for (int q = 0; q < KL; ++q)
 #pragma unroll
-      for (int o = 0; o < O; ++o) atomicAdd(grad + off_ko + (4 * lane + q) * O + o, gko[q][o]);
+      for (int o = 0; o < O; ++o) atomicAdd(grad + off_ko + (lane + 32 * q) * O + o, gko[q][o]);
     if (lane == 0) {
 #pragma unroll
       for (int o = 0; o < O; ++o) atomicAdd(grad + off_ko + H * O + o, gbo[o]);
@@ -766,12 +811,12 @@ __global__ void __launch_bounds__(256) tc_layer1_grad(const float* __restrict__ 
     for (int p = pj; p < P; p += 2) {
       long long gp = p_begin + (long long)tile * P + p;
       if (gp >= n) gp = n - 1;
-      const float z0 = zt[act_off(p, j)];
+      const float z0 = zt[jet_off<G::NR>(p, j)];
       gbv += z0;
 #pragma unroll
       for (int i = 0; i < D; ++i) {
         float v = __ldg(pts + gp * D + i) * z0;
-        if constexpr (ORDER >= 1) v += zt[act_off((1 + i) * P + p, j)];
+        if constexpr (ORDER >= 1) v += zt[jet_off<G::NR>((1 + i) * P + p, j)];
         gk[i] += v;
       }
     }

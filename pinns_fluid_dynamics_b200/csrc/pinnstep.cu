@@ -293,7 +293,7 @@ static int tc_alloc(pinn_plan* p) {
     const long long mb = atoll(e);
     if (mb > 0) budget = mb << 20;
   }
-  constexpr long long kAlign = 3840;   // lcm of the tile sizes (40, 48, 64, 80, 256 points)
+  constexpr long long kAlign = 1680;   // lcm of the tile sizes (40, 48, 56, 80, 240 points)
   long long batch = (budget / per_point / kAlign) * kAlign;
   const long long need = ((max_n + kAlign - 1) / kAlign) * kAlign;
   if (batch > need) batch = need;
@@ -351,12 +351,11 @@ static int tc_run_set(pinn_plan* p, const float* params, float* out, cudaStream_
       tc::tc_out_layer<D, O, ORDER, false><<<(int)grid_out, 256, 0, st>>>(params, off_ko, seg_dev, b0, tiles, act(L), out, out + p->P);
     *launches += L + 1;
     if (train) {
-      const long long total_rg = (long long)tiles * G::RG;
-      const long long chunks = (total_rg + 3) / 4;
-      const int gw = (int)(chunks < p->num_sms ? chunks : p->num_sms);
+      const long long n_slabs = (long long)tiles * (G::NR / tc::kWgRows);
+      const int gw = (int)(n_slabs < p->num_sms ? n_slabs : p->num_sms);
       for (int l = L; l >= 2; --l) {
         float* gK = out + D * H + H + (size_t)(l - 2) * (H * H + H);
-        tc::tc_wgrad<<<gw, tc::kWgThreads, tc::kWgSmem, st>>>(act(l - 1), act(l), total_rg, G::RG, G::P / 8, gK, gK + H * H);
+        tc::tc_wgrad<<<gw, tc::kWgThreads, tc::kWgSmem, st>>>(act(l - 1), act(l), n_slabs, G::NR, G::P, gK, gK + H * H);
         const float* img = p->wimg + (size_t)(l - 2) * tc::kLayerImgFloats + 2 * tc::kImgFloats;
         if (l > 2)
           tc::tc_layer<D, ORDER, 1><<<grid, tc::kLayerThreads, S::TOTAL, st>>>(img, nullptr, act(l), act(l - 1), params, tiles);

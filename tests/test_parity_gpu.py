@@ -250,7 +250,7 @@ def test_tensor_core_engine_two_dimensional_problems(name, kw):
 
 
 def test_tensor_core_engine_many_batches(monkeypatch):
-    """workspace squeezed to one 3840-point batch: 3 batches of collocation points, ragged last tile"""
+    """workspace squeezed to one 1680-point batch: 6 batches of collocation points, ragged last tile"""
     monkeypatch.setenv("PINN_TC_WORKSPACE_MB", "1")
     name, kw = LAYERED["unsteady_8x128"]
     kw = dict(kw, PDE=9001)

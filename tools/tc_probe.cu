@@ -242,6 +242,12 @@ __global__ void __launch_bounds__(160) rate_probe(int kind, int mn_swapped, int 
           bdh = umma::smem_desc(b0 + (kc * 4 + ks) * 256, 128, sbo_b); bdl = umma::smem_desc(b0 + 65536 + (kc * 4 + ks) * 256, 128, sbo_b);
         }
         const uint32_t d = tmem + (uint32_t)(s & 1) * (kind == 5 ? 256u : 128u);
+        if (kind == 6) {   // independent accumulators for consecutive MMAs (is the N=128 cost a dependent-accumulate latency?)
+          umma::mma_tf32_ss(tmem + 0, adl, bdh, idesc, 1);
+          umma::mma_tf32_ss(tmem + 128, adh, bdl, idesc, 1);
+          umma::mma_tf32_ss(tmem + 256, adh, bdh, idesc, 1);
+          continue;
+        }
         if (kind == 3) {
           // 128-byte swizzle: [128 rows x 32 k] atoms of 16 KB; row-group stride 1024 B; k-step = 32 B inside the row
           const uint64_t sah = with_swizzle128(umma::smem_desc(ah + ks * 32, 16, 1024)), sal = with_swizzle128(umma::smem_desc(al + ks * 32, 16, 1024));
@@ -346,7 +352,7 @@ int main() {
   struct Cfg { int kind, swapped, writers; const char* name; };
   Cfg cfgs[] = {{0, 0, 0, "SS K-major"}, {0, 0, 1, "SS K-major + smem writers"}, {1, 0, 0, "SS MN-major (cand.1)"},
                 {0, 0, 2, "SS K-major + paced writers"}, {1, 1, 0, "SS MN-major (cand.2)"}, {2, 0, 0, "TS (A in TMEM)"}, {2, 0, 1, "TS + smem writers"},
-                {0, 2, 0, "SS K-major, elect.sync issuer"}, {5, 2, 0, "SS tf32 N=256, elect.sync issuer"}, {3, 0, 0, "SS K-major SWIZZLE_128B"}, {4, 0, 0, "SS bf16 (kind::f16) no swizzle"}, {5, 0, 0, "SS K-major tf32 N=256"}};
+                {0, 2, 0, "SS K-major, elect.sync issuer"}, {5, 2, 0, "SS tf32 N=256, elect.sync issuer"}, {6, 2, 0, "SS tf32 N=128, 3 rotating accumulators"}, {3, 0, 0, "SS K-major SWIZZLE_128B"}, {4, 0, 0, "SS bf16 (kind::f16) no swizzle"}, {5, 0, 0, "SS K-major tf32 N=256"}};
   for (const Cfg& c : cfgs) {
     rate_probe<<<sms, 160, rsmem>>>(c.kind, c.swapped, 64, c.writers, sink, nullptr);   // warm-up
     CK(cudaDeviceSynchronize());

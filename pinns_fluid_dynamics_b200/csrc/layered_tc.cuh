@@ -359,12 +359,12 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer(const float* __rest
     }
   } else {
     // ===== epilogue: chunk partial sums TMEM -> FP32 registers; tanh-jet (or its adjoint) -> global =====
-    // A thread owns neuron j and the points p = 8*g + 4*half + i (g < P/8, i < 4) of the tile: 4-point groups
-    // alternate between the two warp groups, so every global / TMEM offset below is base + compile-time constant.
+    // A thread owns neuron j and the points [half*PH, half*PH + PH) of the tile (PH = P/2, a multiple of 4): its
+    // TMEM columns are C contiguous spans and its global data C*PH/4 whole 16-byte chunks at constant offsets.
     reg_inc<176>();
     const int q = warp & 3, half = (warp - kProdWarps) >> 2;
     const int j = q * 32 + lane;
-    constexpr int NG = P / 8;                  // 4-point groups per thread
+    constexpr int NG = PH / 4;                 // 4-point groups per thread
     float bj = 0.f;
     float k1[D];
 #pragma unroll
@@ -374,40 +374,41 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer(const float* __rest
 #pragma unroll
       for (int i = 0; i < D; ++i) k1[i] = __ldg(params + i * kH + j);
     }
-    const size_t thr_off = (size_t)(j >> 3) * (NR * 8) + (size_t)half * 32 + (size_t)(j & 7) * 4;
+    const size_t thr_off = (size_t)(j >> 3) * (NR * 8) + (size_t)half * (NG * 32) + (size_t)(j & 7) * 4;
     int g = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      float* io = act_io + (size_t)tile * NR * kH + thr_off;       // chunk (c, g) = 4 points at io[(c*P/4 + 2g)*32]
-      float acc[C][NG][4];
+      float* io = act_io + (size_t)tile * NR * kH + thr_off;       // chunk (c, g) = 4 points at io[(c*P/4 + g)*32]
+      float acc[C][PH];
 #pragma unroll 1
       for (int ch = 0; ch < kChunks; ++ch, ++g) {
         const int buf = g & 1;
         mbar_wait(&tfull[buf], (uint32_t)((g >> 1) & 1));
         umma::fence_after_thread_sync();
-        const uint32_t tb = tmem + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 4);
+        const uint32_t tb = tmem + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * PH);
         if (ch == 0) {
 #pragma unroll
-          for (int c = 0; c < C; ++c)
-#pragma unroll
-            for (int gg = 0; gg < NG; ++gg) tmem_ld_n<4>(tb + (uint32_t)(c * P + 8 * gg), acc[c][gg]);
+          for (int c = 0; c < C; ++c) tmem_ld_span<PH>(tb + (uint32_t)(c * P), acc[c]);
           tmem_ld_wait();
         } else {
-          constexpr int GB = NG < 8 ? NG : 8;                      // groups per batch of loads (<= 32 registers)
+          constexpr int W0 = PH < 32 ? PH : 32;
 #pragma unroll
           for (int c = 0; c < C; ++c) {
 #pragma unroll
-            for (int g0 = 0; g0 < NG; g0 += GB) {
-              float t[GB][4];
+            for (int o = 0; o < PH; o += 32) {
+              if (PH - o >= W0) {
+                float t[W0];
+                tmem_ld_span<W0>(tb + (uint32_t)(c * P + o), t);
+                tmem_ld_wait();
 #pragma unroll
-              for (int gg = 0; gg < GB; ++gg)
-                if (g0 + gg < NG) tmem_ld_n<4>(tb + (uint32_t)(c * P + 8 * (g0 + gg)), t[gg]);
-              tmem_ld_wait();
+                for (int i = 0; i < W0; ++i) acc[c][o + i] += t[i];
+              } else {
+                constexpr int W1 = PH % 32 == 0 ? 4 : PH % 32;    // tail of a span longer than 32 columns
+                float u[W1];
+                tmem_ld_span<W1>(tb + (uint32_t)(c * P + o), u);
+                tmem_ld_wait();
 #pragma unroll
-              for (int gg = 0; gg < GB; ++gg)
-                if (g0 + gg < NG) {
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) acc[c][g0 + gg][i] += t[gg][i];
-                }
+                for (int i = 0; i < W1; ++i) acc[c][o + i] += u[i];
+              }
             }
           }
         }
@@ -415,42 +416,42 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer(const float* __rest
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[buf]);
       }
-      // ---- elementwise: one 4-point group at a time ----
+      // ---- elementwise: one 4-point group (one 16-byte chunk per channel) at a time ----
 #pragma unroll
       for (int gg = 0; gg < NG; ++gg) {
         float aj[C][4];
         if constexpr (MODE == 1) {
 #pragma unroll
           for (int c = 0; c < C; ++c) {
-            const float4 t4 = *reinterpret_cast<const float4*>(io + (c * (P / 4) + 2 * gg) * 32);
+            const float4 t4 = *reinterpret_cast<const float4*>(io + (c * (P / 4) + gg) * 32);
             aj[c][0] = t4.x; aj[c][1] = t4.y; aj[c][2] = t4.z; aj[c][3] = t4.w;
           }
         } else if constexpr (MODE == 2) {
-          const float4 t4 = *reinterpret_cast<const float4*>(io + (2 * gg) * 32);
+          const float4 t4 = *reinterpret_cast<const float4*>(io + gg * 32);
           aj[0][0] = t4.x; aj[0][1] = t4.y; aj[0][2] = t4.z; aj[0][3] = t4.w;
         }
-        float out4[C][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           float res[C];
           if constexpr (MODE == 0) {
             float zd[D], zxx = 0.f, zyy = 0.f;
 #pragma unroll
-            for (int t = 0; t < D; ++t) zd[t] = ORDER >= 1 ? acc[(ORDER >= 1) ? 1 + t : 0][gg][i] : 0.f;
-            if constexpr (ORDER >= 2) { zxx = acc[(ORDER >= 2) ? 1 + D : 0][gg][i]; zyy = acc[(ORDER >= 2) ? 2 + D : 0][gg][i]; }
-            layered::jet_fwd<D, ORDER>(tanh_accurate(acc[0][gg][i] + bj), zd, zxx, zyy, res);
+            for (int t = 0; t < D; ++t) zd[t] = ORDER >= 1 ? acc[(ORDER >= 1) ? 1 + t : 0][4 * gg + i] : 0.f;
+            if constexpr (ORDER >= 2) { zxx = acc[(ORDER >= 2) ? 1 + D : 0][4 * gg + i]; zyy = acc[(ORDER >= 2) ? 2 + D : 0][4 * gg + i]; }
+            layered::jet_fwd<D, ORDER>(tanh_accurate(acc[0][4 * gg + i] + bj), zd, zxx, zyy, res);
           } else {
             float a1[C], ab[C];
 #pragma unroll
-            for (int c = 0; c < C; ++c) { a1[c] = (MODE == 2 && c > 0) ? 0.f : aj[c][i]; ab[c] = acc[c][gg][i]; }
+            for (int c = 0; c < C; ++c) { a1[c] = (MODE == 2 && c > 0) ? 0.f : aj[c][i]; ab[c] = acc[c][4 * gg + i]; }
             layered::jet_bwd<D, ORDER, MODE == 2>(a1, k1, ab, res);
           }
 #pragma unroll
-          for (int c = 0; c < C; ++c) out4[c][i] = res[c];
+          for (int c = 0; c < C; ++c) acc[c][4 * gg + i] = res[c];          // results replace the consumed sums
         }
 #pragma unroll
         for (int c = 0; c < C; ++c)
-          *reinterpret_cast<float4*>(io + (c * (P / 4) + 2 * gg) * 32) = make_float4(out4[c][0], out4[c][1], out4[c][2], out4[c][3]);
+          *reinterpret_cast<float4*>(io + (c * (P / 4) + gg) * 32) =
+              make_float4(acc[c][4 * gg], acc[c][4 * gg + 1], acc[c][4 * gg + 2], acc[c][4 * gg + 3]);
       }
     }
   }

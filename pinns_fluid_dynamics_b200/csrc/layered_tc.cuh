@@ -111,29 +111,33 @@ __global__ void tc_prep_weights(const float* __restrict__ params, int off0, int 
   }
 }
 
-// ---- layer 1 (SIMT) --------------------------------------------------------------------------------
+// ---- layer 1 (SIMT): thread = (neuron, 4-point group) -> one 16-byte chunk per channel ---------------------
 template <int D, int ORDER>
 __global__ void __launch_bounds__(256) tc_layer1(const float* __restrict__ params, const float* __restrict__ pts, long long n,
                                                  long long p_begin, float* __restrict__ act1) {
   using G = Geo<D, ORDER>;
-  constexpr int C = G::C, P = G::P;
-  const int j = threadIdx.x & (kH - 1), pj = threadIdx.x >> 7;
+  constexpr int C = G::C, P = G::P, NR = G::NR;
+  const int j = threadIdx.x & (kH - 1), gj = threadIdx.x >> 7;
   const long long tile = blockIdx.x;
   float zd[D];
 #pragma unroll
   for (int i = 0; i < D; ++i) zd[i] = __ldg(params + i * kH + j);
   const float b = __ldg(params + D * kH + j);
-  float* out = act1 + (size_t)tile * G::NR * kH;
-  for (int p = pj; p < P; p += 2) {
-    long long gp = p_begin + tile * P + p;
-    if (gp >= n) gp = n - 1;
-    float z = b;
+  float* out = act1 + (size_t)tile * NR * kH + (size_t)(j >> 3) * (NR * 8) + (size_t)(j & 7) * 4;
+  for (int g = gj; g < P / 4; g += 2) {
+    float a[4][C];
 #pragma unroll
-    for (int i = 0; i < D; ++i) z = fmaf(__ldg(pts + gp * D + i), zd[i], z);
-    float a[C];
-    layered::jet_fwd<D, ORDER>(tanh_accurate(z), zd, 0.f, 0.f, a);
+    for (int i = 0; i < 4; ++i) {
+      long long gp = p_begin + tile * P + 4 * g + i;
+      if (gp >= n) gp = n - 1;
+      float z = b;
 #pragma unroll
-    for (int c = 0; c < C; ++c) out[jet_off<G::NR>(c * P + p, j)] = a[c];
+      for (int t = 0; t < D; ++t) z = fmaf(__ldg(pts + gp * D + t), zd[t], z);
+      layered::jet_fwd<D, ORDER>(tanh_accurate(z), zd, 0.f, 0.f, a[i]);
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      *reinterpret_cast<float4*>(out + (size_t)(c * (P / 4) + g) * 32) = make_float4(a[0][c], a[1][c], a[2][c], a[3][c]);
   }
 }
 
@@ -794,31 +798,39 @@ __global__ void __launch_bounds__(256) tc_out_layer(const float* __restrict__ pa
   }
 }
 
-// ---- K1 / b1 gradients from z-bar_1 (SIMT): thread = neuron, block-strided over tiles ----------------
+// ---- K1 / b1 gradients from z-bar_1 (SIMT): thread = (neuron, 4-point group), block-strided over tiles ------
 template <int D, int ORDER>
 __global__ void __launch_bounds__(256) tc_layer1_grad(const float* __restrict__ zbar1, const float* __restrict__ pts, long long n,
                                                       long long p_begin, int n_tiles, float* __restrict__ grad) {
   using G = Geo<D, ORDER>;
-  constexpr int P = G::P;
+  constexpr int P = G::P, NR = G::NR;
   __shared__ float sG[(1 + D) * kH];
   for (int i = threadIdx.x; i < (1 + D) * kH; i += blockDim.x) sG[i] = 0.f;
   __syncthreads();
-  const int j = threadIdx.x & (kH - 1), pj = threadIdx.x >> 7;
+  const int j = threadIdx.x & (kH - 1), gj = threadIdx.x >> 7;
   float gk[D], gbv = 0.f;
 #pragma unroll
   for (int i = 0; i < D; ++i) gk[i] = 0.f;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const float* zt = zbar1 + (size_t)tile * G::NR * kH;
-    for (int p = pj; p < P; p += 2) {
-      long long gp = p_begin + (long long)tile * P + p;
-      if (gp >= n) gp = n - 1;
-      const float z0 = zt[jet_off<G::NR>(p, j)];
-      gbv += z0;
+    const float* zt = zbar1 + (size_t)tile * NR * kH + (size_t)(j >> 3) * (NR * 8) + (size_t)(j & 7) * 4;
+    for (int g = gj; g < P / 4; g += 2) {
+      const float4 z4 = *reinterpret_cast<const float4*>(zt + (size_t)g * 32);
+      const float z0[4] = {z4.x, z4.y, z4.z, z4.w};
+      gbv += (z0[0] + z0[1]) + (z0[2] + z0[3]);
 #pragma unroll
-      for (int i = 0; i < D; ++i) {
-        float v = __ldg(pts + gp * D + i) * z0;
-        if constexpr (ORDER >= 1) v += zt[jet_off<G::NR>((1 + i) * P + p, j)];
-        gk[i] += v;
+      for (int t = 0; t < D; ++t) {
+        float v = 0.f;
+        if constexpr (ORDER >= 1) {
+          const float4 d4 = *reinterpret_cast<const float4*>(zt + (size_t)((1 + t) * (P / 4) + g) * 32);
+          v = (d4.x + d4.y) + (d4.z + d4.w);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          long long gp = p_begin + (long long)tile * P + 4 * g + i;
+          if (gp >= n) gp = n - 1;
+          v = fmaf(__ldg(pts + gp * D + t), z0[i], v);
+        }
+        gk[t] += v;
       }
     }
   }

@@ -9,7 +9,7 @@ from typing import Optional
 MAX_OUT, MAX_CH, MAX_DIM, MAX_TERMS_PER_SET = 4, 6, 3, 8
 
 LIB_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib")
-LIB_PATH = os.path.join(LIB_DIR, "libpinnstep.so")
+LIB_PATH = os.environ.get("PINN_LIBPINNSTEP", os.path.join(LIB_DIR, "libpinnstep.so"))   # override: development builds only
 
 # every symbol include/pinnstep.h declares (tests/test_capi_symbols.py checks the header against this)
 EXPORTED_SYMBOLS = (

@@ -193,13 +193,22 @@ template <int REGS> __device__ __forceinline__ void reg_inc() { asm volatile("se
 //   WG0  warps 0-3    producers  global jets -> hi/lo split -> K-major stage blocks (2 stages prefetched in registers)
 //   WG1-2 warps 4-11  epilogue   thread = neuron of lane quarter warp%4, half of the tile's points per group
 //   WG3  warp 12      MMA issuer (one lane); warps 13-15 idle
+// -DPINN_TC_PROFILE: CTA 0 accumulates clock64 intervals per warp role (tools/tc_role_profile.py)
+#ifdef PINN_TC_PROFILE
+__device__ unsigned long long g_tc_prof[32];
+#define TCP_T0() const long long tcp_t0 = clock64()
+#define TCP_ADD(slot) do { if (blockIdx.x == 0 && lane == 0) atomicAdd(&g_tc_prof[slot], (unsigned long long)(clock64() - tcp_t0)); } while (0)
+#else
+#define TCP_T0() do {} while (0)
+#define TCP_ADD(slot) do {} while (0)
+#endif
 constexpr int kProdWarps = 4;
 constexpr int kEpiWarps = 8;
 constexpr int kLayerThreads = 512;
 constexpr int kMmaWarp = 12;
 constexpr int kStages = 3;
 constexpr int kKC = 16;                       // K per pipeline stage (2 MMA k-steps)
-constexpr int kStagesPerChunk = 2;            // accumulator lifetime: K = 32
+constexpr int kStagesPerChunk = 2;            // accumulator lifetime: K = 32 (tools/tc_accuracy.py: 4 drains per tile keep the worst loss term at 4-6e-6; 2 drains 1.1e-5, none 2.3e-5)
 constexpr int kChunks = kH / (kKC * kStagesPerChunk);
 
 template <int NR>
@@ -279,7 +288,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer(const float* __rest
       }
     };
     auto consume = [&](const float4 (&v)[8]) {
-      mbar_wait(&empty[stage], phase ^ 1u);
+      { TCP_T0(); mbar_wait(&empty[stage], phase ^ 1u); if (warp == 0) TCP_ADD(0); }
       uint8_t* dst = sStage + stage * S::STAGE;
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
@@ -306,6 +315,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer(const float* __rest
       if (++stage == kStages) { stage = 0; phase ^= 1u; }
     };
     float4 va[8], vb[8], vc[8];
+    TCP_T0();
     issue(0, va);
     issue(1, vb);
 #pragma unroll 1
@@ -315,6 +325,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer(const float* __rest
       if (t + 1 < T) { issue(t + 3, va); consume(vb); }
       if (t + 2 < T) { issue(t + 4, vb); consume(vc); }
     }
+    if (warp == 0) TCP_ADD(1);
   } else if (warp >= kMmaWarp) {
     // ===== MMA issuer =====
     reg_dec<24>();
@@ -325,17 +336,18 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer(const float* __rest
       const uint32_t st0 = (uint32_t)__cvta_generic_to_shared(sStage);
       int stage = 0, g = 0;
       uint32_t phase = 0;
+      TCP_T0();
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
 #pragma unroll 1
         for (int ch = 0; ch < kChunks; ++ch, ++g) {
           const int buf = g & 1;
-          if (g >= 2) mbar_wait(&tempty[buf], (uint32_t)(((g >> 1) - 1) & 1));
+          { TCP_T0(); if (g >= 2) mbar_wait(&tempty[buf], (uint32_t)(((g >> 1) - 1) & 1)); TCP_ADD(2); }
           umma::fence_after_thread_sync();
           const uint32_t d = tmem + (uint32_t)buf * 256u;
           uint32_t acc = 0;
 #pragma unroll 1
           for (int s = 0; s < kStagesPerChunk; ++s) {
-            mbar_wait(&full[stage], phase);
+            { TCP_T0(); mbar_wait(&full[stage], phase); TCP_ADD(3); }
             umma::fence_after_thread_sync();
             const uint32_t b_hi = st0 + stage * S::STAGE, b_lo = b_hi + S::HALF;
             const uint32_t ka = (uint32_t)((ch * kStagesPerChunk + s) * (kKC / 8)) * 256u;
@@ -360,6 +372,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer(const float* __rest
           umma::commit(&tfull[buf]);
         }
       }
+      TCP_ADD(4);
     }
   } else {
     // ===== epilogue: chunk partial sums TMEM -> FP32 registers; tanh-jet (or its adjoint) -> global =====
@@ -386,7 +399,8 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer(const float* __rest
 #pragma unroll 1
       for (int ch = 0; ch < kChunks; ++ch, ++g) {
         const int buf = g & 1;
-        mbar_wait(&tfull[buf], (uint32_t)((g >> 1) & 1));
+        { TCP_T0(); mbar_wait(&tfull[buf], (uint32_t)((g >> 1) & 1)); if (warp == kProdWarps) TCP_ADD(5); }
+        TCP_T0();
         umma::fence_after_thread_sync();
         const uint32_t tb = tmem + (uint32_t)buf * 256u + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * PH);
         if (ch == 0) {
@@ -419,8 +433,10 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer(const float* __rest
         umma::fence_before_thread_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[buf]);
+        if (warp == kProdWarps) TCP_ADD(6);
       }
       // ---- elementwise: one 4-point group (one 16-byte chunk per channel) at a time ----
+      TCP_T0();
 #pragma unroll
       for (int gg = 0; gg < NG; ++gg) {
         float aj[C][4];
@@ -457,6 +473,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer(const float* __rest
           *reinterpret_cast<float4*>(io + (c * (P / 4) + gg) * 32) =
               make_float4(acc[c][4 * gg], acc[c][4 * gg + 1], acc[c][4 * gg + 2], acc[c][4 * gg + 3]);
       }
+      if (warp == kProdWarps) TCP_ADD(7);
     }
   }
   umma::fence_before_thread_sync();

@@ -407,6 +407,14 @@ static int run_tc(pinn_plan* p, const float* params, float* out, cudaStream_t st
   return rc;
 }
 
+#ifdef PINN_TC_PROFILE
+extern "C" int pinn_debug_tc_prof(unsigned long long* out32, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out32, tc::g_tc_prof, sizeof(unsigned long long) * 32);
+  if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(tc::g_tc_prof, z, sizeof(z)); }
+  return 0;
+}
+#endif
 extern "C" int pinn_version(void) { return PINN_VERSION; }
 extern "C" const char* pinn_last_error(void) { return g_err; }
 

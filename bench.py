@@ -12,9 +12,10 @@ Printed keys (one JSON line on rank 0):
   value      whole-job pts/s with inputs resident in HBM (device-timed per step, L2 flushed between steps)
   e2e        the same through the public facade with HOST inputs: every step copies all point / target
              arrays from pinned host memory, runs the step, and reads the per-term sums back
-  roofline   the collocation kernel (fused_step_kernel<...,ORDER=2,TRAIN>) against the MEASURED FP32
-             FFMA peak of this pool's B200 (profiles/fp32_peak_r01.json; MEASURED_PEAKS.json holds no
-             FP32 figure)
+  roofline   the collocation kernel(s) against the pipe that bounds them: fused_step_kernel<...,ORDER=2,TRAIN>
+             against the MEASURED FP32 FFMA peak of this pool's B200 (profiles/fp32_peak_r01.json), the
+             tensor-core engine of the 8x128 network against the MEASURED tcgen05 kind::tf32 rate / 3 passes
+             (profiles/tf32_peak_r01.json); MEASURED_PEAKS.json holds neither figure
   cpu_baseline   oracle/reference_step.py (torch float64 nested autodiff, the reference's step
              structure) timed on this box's host cores on a bounded sample
 `--impl reference` times that CPU restatement alone (the real nisaba/TensorFlow stack cannot be
@@ -224,20 +225,36 @@ def run_ours(args):
     C = 3 + d
     flop_launch = n_local_pde * flops_per_point(d, H, L, O, C)
     achieved = flop_launch / (k_ms * 1e-3) * 1e-12
-    peak, peak_src = 71.7, "fallback"
-    try:
-        with open(os.path.join(ROOT, "profiles", "fp32_peak_r01.json")) as fh:
-            pk = json.load(fh)
-        peak, peak_src = max(pk["ffma_chain_tflops"], pk["ffma2_chain_tflops"]), "profiles/fp32_peak_r01.json (tools/fp32_peak.cu on this pool)"
-    except Exception:
-        pass
     traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")) as fh:
-            tr = json.load(fh)
-        traffic = tr["dram_bytes_per_point"] * n_local_pde
-    except Exception:
-        pass
+    if plan.engine == "layered_tf32x3":
+        # hidden-layer contractions on tcgen05 kind::tf32, 3 MMA passes per algorithmic product (hi/lo split)
+        bound, peak, peak_src = "tensor", 368.4, "fallback"
+        kernel_name = ("collocation pipeline of the layered engine: tc_layer1, tc_layer<fwd> x(L-1), tc_out_layer, "
+                       "(tc_wgrad, tc_layer<bwd>) x(L-1), tc_layer1_grad per batch; timed as one event pair")
+        try:
+            with open(os.path.join(ROOT, "profiles", "tf32_peak_r01.json")) as fh:
+                pk = json.load(fh)
+            peak = pk["tf32_mma_tflops_n256"] / pk["passes_per_product"]
+            peak_src = ("profiles/tf32_peak_r01.json: measured tcgen05 kind::tf32 MMA rate (tools/tc_probe.cu) / 3 passes; "
+                        "MEASURED_PEAKS.json holds no TF32 figure")
+        except Exception:
+            pass
+    else:
+        bound, peak, peak_src = "fp32_fma", 71.7, "fallback"
+        kernel_name = "fused_step_kernel<D,H,L,O,ORDER=2,TRAIN>" if plan.engine == "fused_fp32" else "layered_fp32 collocation pipeline"
+        try:
+            with open(os.path.join(ROOT, "profiles", "fp32_peak_r01.json")) as fh:
+                pk = json.load(fh)
+            peak, peak_src = max(pk["ffma_chain_tflops"], pk["ffma2_chain_tflops"]), "profiles/fp32_peak_r01.json (tools/fp32_peak.cu on this pool)"
+        except Exception:
+            pass
+        if plan.engine == "fused_fp32":
+            try:
+                with open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")) as fh:
+                    tr = json.load(fh)
+                traffic = tr["dram_bytes_per_point"] * n_local_pde
+            except Exception:
+                pass
 
     # ---- e2e: host-resident inputs, H2D every step, D2H of the per-term sums every step ----------
     h2d = plan.pin_host_inputs()
@@ -283,8 +300,8 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "pts/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(T * 4),
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches_per_step * args.steps),
-            "roofline": {"bound": "fp32_fma", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "fused_step_kernel<D,H,L,O,ORDER=2,TRAIN>", "kernel_ms": k_ms,
+            "roofline": {"bound": bound, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": kernel_name, "kernel_ms": k_ms,
                          "flop_per_point": flops_per_point(d, H, L, O, C), "points_per_launch": n_local_pde,
                          "peak_source": peak_src,
                          "hbm_GBps": (n_local_pde * 4 * d) / (k_ms * 1e-3) * 1e-9},

@@ -72,8 +72,31 @@ __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 
-// tanh accurate to ~1 ulp over the whole range (libdevice tanhf: polynomial below 0.55, exp-based
-// above); the loss tolerance (1e-5 relative) rules out tanh.approx.f32 (2^-11).
-__device__ __forceinline__ float tanh_accurate(float z) { return tanhf(z); }
+// tanh to ~2 ulp over the whole range, BRANCH-FREE (libdevice tanhf takes a data-dependent branch at |x| = 0.55,
+// which serialises both sides in a warp and stops the compiler from interleaving the tanh of neighbouring
+// neurons).  |x| < 0.55: odd minimax polynomial x + x^3 q(x^2), relative error 7e-8 (fit in tools/ notes);
+// otherwise 1 - 2/(exp(2|x|) + 1) with ex2.approx and a Newton-refined rcp.approx.  The loss tolerance (1e-5
+// relative) rules out tanh.approx.f32 (2^-11).
+__device__ __forceinline__ float tanh_accurate(float z) {
+#ifdef PINN_TANH_LIBDEVICE
+  return tanhf(z);
+#else
+  const float az = fabsf(z);
+  const float u = z * z;
+  float q = fmaf(u, -0.006615748628973961f, 0.021312739700078964f);
+  q = fmaf(q, u, -0.053910065442323685f);
+  q = fmaf(q, u, 0.13333117961883545f);
+  q = fmaf(q, u, -0.3333333134651184f);
+  const float small = fmaf(z * u, q, z);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(az * -2.885390081777927f));   // exp(-2|z|)
+  const float d = 1.0f + e;
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+  r = r * fmaf(-d, r, 2.0f);                         // one Newton step: r = 1/(1+e) to ~1 ulp
+  const float big = copysignf(fmaf(-2.0f * e, r, 1.0f), z);
+  return az < 0.55f ? small : big;
+#endif
+}
 
 }  // namespace pinn

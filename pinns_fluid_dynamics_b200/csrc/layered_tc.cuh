@@ -256,6 +256,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer(const float* __rest
 
   if (warp < kProdWarps) {
     // ===== producers: two stages of loads in flight in registers (HBM latency x 21 B/cycle/SM ~ 30 KB) =====
+    reg_dec<120>();
     if (tid == 0) {
       mbar_expect_tx(wbar, S::W_BYTES);
 #pragma unroll
@@ -378,7 +379,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer(const float* __rest
     // ===== epilogue: chunk partial sums TMEM -> FP32 registers; tanh-jet (or its adjoint) -> global =====
     // A thread owns neuron j and the points [half*PH, half*PH + PH) of the tile (PH = P/2, a multiple of 4): its
     // TMEM columns are C contiguous spans and its global data C*PH/4 whole 16-byte chunks at constant offsets.
-    reg_inc<176>();
+    reg_inc<184>();
     const int q = warp & 3, half = (warp - kProdWarps) >> 2;
     const int j = q * 32 + lane;
     constexpr int NG = PH / 4;                 // 4-point groups per thread

@@ -267,7 +267,7 @@ def run_ours(args):
     sampler.active.set()
     e0.record()
     for _ in range(args.steps):
-        plan.upload_inputs()
+        plan.upload_inputs()                           # one pinned-arena copy: every point / target array of the step
         s = pb.training_step(opt)
         host_out.copy_(s[:T], non_blocking=True)
         torch.cuda.current_stream().synchronize()      # the caller reads the loss every step

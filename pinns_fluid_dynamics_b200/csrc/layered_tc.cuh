@@ -68,6 +68,13 @@ __device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, float (&v)[4]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr) : "memory");
   v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
 }
+// pull a contiguous global range into L2 ahead of use (no registers, no shared memory)
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+#ifndef PINN_TC_L2PF
+#define PINN_TC_L2PF 4
+#endif
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // round-to-nearest split: hi and lo are both exact TF32 values, so the tensor core's own truncation of its
 // operands loses nothing and the residual x - hi - lo (<= 2^-22 |x|) has no sign bias.  (A truncating split
@@ -274,6 +281,15 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer(const float* __rest
     constexpr int NRB = NR / 4;
     const int kb = (tid >> 3) & 3, rb0 = (tid & 7) + 8 * (tid >> 5);
     auto issue = [&](int t, float4 (&v)[8]) {
+      if constexpr (PINN_TC_L2PF > 0) {        // steady L2 prefetch PINN_TC_L2PF stages ahead of the register loads
+        const int tp = t + PINN_TC_L2PF;
+        if (tid < 2 && tp < T) {
+          const int ptile = (int)blockIdx.x + (tp / NKC) * (int)gridDim.x, pkc = tp % NKC;
+          l2_prefetch_bulk(reinterpret_cast<const uint8_t*>(act_in + (size_t)ptile * NR * kH) + (size_t)(pkc * 2 + tid) * (NR * 32), NR * 32);
+          if constexpr (MODE == 1)
+            l2_prefetch_bulk(reinterpret_cast<const uint8_t*>(act_io + (size_t)ptile * NR * kH) + (size_t)(pkc * 2 + tid) * (NR * 32), NR * 32);
+        }
+      }
       if (t >= T) return;
       const int tile = (int)blockIdx.x + (t / NKC) * (int)gridDim.x, kc = t % NKC;
       const uint8_t* src = reinterpret_cast<const uint8_t*>(act_in + (size_t)tile * NR * kH) +
@@ -284,7 +300,12 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer(const float* __rest
         if (rb < NRB) {
           const float4* p = reinterpret_cast<const float4*>(src + rb * 128);
 #pragma unroll
+#ifdef PINN_TC_EXP_NOLOAD   // experiment: how much of the layer kernels is the HBM read stream?
+          for (int r = 0; r < 4; ++r) v[4 * u + r] = make_float4(0.25f, -0.5f, 0.125f, 1.f);
+          (void)p;
+#else
           for (int r = 0; r < 4; ++r) v[4 * u + r] = __ldg(p + r);       // v[4u + r] = neuron 4kb + r, rows 4rb..4rb+3
+#endif
         }
       }
     };
@@ -436,7 +457,8 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer(const float* __rest
         if (lane == 0) mbar_arrive(&tempty[buf]);
         if (warp == kProdWarps) TCP_ADD(6);
       }
-      // ---- elementwise: one 4-point group (one 16-byte chunk per channel) at a time ----
+      // ---- elementwise: one 4-point group (one 16-byte chunk per channel) at a time.  (Keeping the next group's
+      //      stored a-jets in flight was measured twice and is slower: the extra 24 registers spill.) ----
       TCP_T0();
 #pragma unroll
       for (int gg = 0; gg < NG; ++gg) {
@@ -471,6 +493,9 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer(const float* __rest
         }
 #pragma unroll
         for (int c = 0; c < C; ++c)
+#ifdef PINN_TC_EXP_NOSTORE  // experiment: results are computed but (practically) never written
+          if (acc[c][4 * gg] == 12345.678f)
+#endif
           *reinterpret_cast<float4*>(io + (c * (P / 4) + gg) * 32) =
               make_float4(acc[c][4 * gg], acc[c][4 * gg + 1], acc[c][4 * gg + 2], acc[c][4 * gg + 3]);
       }

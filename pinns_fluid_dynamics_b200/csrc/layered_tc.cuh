@@ -679,166 +679,189 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad(const float* __restric
   if (warp == kWgMmaWarp) umma::tmem_dealloc<256>(tmem);
 }
 
-// ---- output layer + residuals + adjoint, one warp per point (SIMT) ----------------------------------
+// ---- output layer + residuals + adjoint (SIMT), one tile per CTA iteration ---------------------------
+// phase 1  thread = (point, k-slice): partial output jets J[c][o] over its slice of the 128 neurons (consecutive
+//          lanes = consecutive points = consecutive 4-byte words of the 16-byte chunks), slices summed through
+//          shared memory; one thread per point then forms the residuals, sum r^2 and the adjoint Jb[c][o].
+// phase 2  thread = (neuron, half of the 4-point groups): a-bar = Jb . K_out^T, tanh-jet adjoint, z-bar_L stored
+//          in place as whole 16-byte chunks; K_out gradients accumulate in registers (the neuron is fixed).
 template <int D, int O, int ORDER, bool TRAIN>
 __global__ void __launch_bounds__(256) tc_out_layer(const float* __restrict__ params, int off_ko, const SegDev* __restrict__ seg_ptr,
                                                     long long p_begin, int n_tiles, float* __restrict__ actL,
                                                     float* __restrict__ grad, float* __restrict__ sumsq) {
   using G = Geo<D, ORDER>;
-  constexpr int C = G::C, P = G::P, H = kH;
-  constexpr int KL = H / 32;
+  constexpr int C = G::C, P = G::P, NR = G::NR, H = kH, CO = C * O;
   constexpr int SX = D - 2, SY = D - 1;
+  constexpr int NS = 256 / P;                       // k-slices in phase 1
+  constexpr int KS = (H + NS - 1) / NS;
+  __shared__ float sKo[H * 4];
+  __shared__ float sJp[NS * P * CO];
+  __shared__ float sJb[P * CO];
+  __shared__ float sSq[kMaxTerms];
+  __shared__ float sGbo[kMaxOut];
   const SegDev* __restrict__ seg = seg_ptr;
-  const int lane = threadIdx.x & 31;
-  const int warps_per_block = blockDim.x >> 5;
+  const int tid = threadIdx.x;
   const long long n = seg->n;
   const float* Ko = params + off_ko;
   const float* bo = Ko + H * O;
-  // lane owns neurons k = lane + 32 q
-  float ko[KL][O];
+  for (int i = tid; i < H * 4; i += 256) sKo[i] = (i & 3) < O ? __ldg(Ko + (i >> 2) * O + (i & 3)) : 0.f;
+  if (tid < kMaxTerms) sSq[tid] = 0.f;
+  if (tid < kMaxOut) sGbo[tid] = 0.f;
+  __syncthreads();
+  const int n_terms = seg->n_terms;
+  // phase-2 identity
+  const int k2 = tid & (H - 1), h2 = tid >> 7;
+  float ko2[O], gko[O];
 #pragma unroll
-  for (int q = 0; q < KL; ++q)
+  for (int o = 0; o < O; ++o) { ko2[o] = sKo[k2 * 4 + o]; gko[o] = 0.f; }
+  // phase-1 identity
+  const int p1 = tid % P, s1 = tid / P;
+  const bool act1 = tid < NS * P;
+
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    float* base = actL + (size_t)tile * NR * H;
+    // ---- phase 1 ----
+    if (act1) {
+      float J[C][O];
 #pragma unroll
-    for (int o = 0; o < O; ++o) ko[q][o] = __ldg(Ko + (lane + 32 * q) * O + o);
-  float gko[KL][O];
+      for (int c = 0; c < C; ++c)
 #pragma unroll
-  for (int q = 0; q < KL; ++q)
-#pragma unroll
-    for (int o = 0; o < O; ++o) gko[q][o] = 0.f;
-  float gbo[O];
-#pragma unroll
-  for (int o = 0; o < O; ++o) gbo[o] = 0.f;
-  float sq[kMaxTerms];
-#pragma unroll
-  for (int t = 0; t < kMaxTerms; ++t) sq[t] = 0.f;
-  const long long total_pts = (long long)n_tiles * P;
-  for (long long lp = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); lp < total_pts;
-       lp += (long long)gridDim.x * warps_per_block) {
-    const long long gp = p_begin + lp;
-    const bool valid = gp < n;
-    const long long tile = lp / P;
-    const int p = (int)(lp % P);
-    float* base = actL + (size_t)tile * G::NR * H;
-    float a[C][KL];
-    float J[C][O];
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-#pragma unroll
-      for (int q = 0; q < KL; ++q) a[c][q] = base[jet_off<G::NR>(c * P + p, lane + 32 * q)];
-#pragma unroll
-      for (int o = 0; o < O; ++o) J[c][o] = 0.f;
-#pragma unroll
-      for (int q = 0; q < KL; ++q)
-#pragma unroll
-        for (int o = 0; o < O; ++o) J[c][o] = fmaf(a[c][q], ko[q][o], J[c][o]);
-    }
-#pragma unroll
-    for (int c = 0; c < C; ++c)
-#pragma unroll
-      for (int o = 0; o < O; ++o) {
-        float v = J[c][o];
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-        J[c][o] = v + (c == 0 ? __ldg(bo + o) : 0.f);
-      }
-    if (seg->y_out != nullptr && valid && lane == 0) {
-#pragma unroll
-      for (int o = 0; o < O; ++o) seg->y_out[gp * O + o] = J[0][o];
-    }
-    float Jb[C][O];
-#pragma unroll
-    for (int c = 0; c < C; ++c)
-#pragma unroll
-      for (int o = 0; o < O; ++o) Jb[c][o] = 0.f;
-    const int n_terms = seg->n_terms;
-#pragma unroll
-    for (int t = 0; t < kMaxTerms; ++t) {
-      if (t >= n_terms) break;
-      const TermDev* __restrict__ T = seg->terms + t;
-      if (TRAIN && !T->train) continue;
-      float r = 0.f;
-#pragma unroll
-      for (int o = 0; o < O; ++o)
-#pragma unroll
-        for (int c = 0; c < C; ++c) r = fmaf(__ldg(&T->coef[o][c]), J[c][o], r);
-      float cv = 0.f;
-      int ck = 0;
-      if constexpr (ORDER >= 1 && O >= 2) {
-        cv = __ldg(&T->conv);
-        ck = __ldg(&T->conv_k);
-        const float ukx = ck == 0 ? J[1 + SX][0] : J[1 + SX][1];
-        const float uky = ck == 0 ? J[1 + SY][0] : J[1 + SY][1];
-        r = fmaf(cv, fmaf(J[0][0], ukx, J[0][1] * uky), r);
-      }
-      if (T->rhs != nullptr && valid) r = fmaf(-__ldg(&T->rhs_scale), __ldg(T->rhs + gp), r);
-      if (!valid) r = 0.f;
-      sq[t] = fmaf(r, r, sq[t]);
-      if constexpr (TRAIN) {
-        const float rb = __ldg(&T->scale) * r;
-#pragma unroll
-        for (int o = 0; o < O; ++o)
-#pragma unroll
-          for (int c = 0; c < C; ++c) Jb[c][o] = fmaf(__ldg(&T->coef[o][c]), rb, Jb[c][o]);
-        if constexpr (ORDER >= 1 && O >= 2) {
-          const float ukx = ck == 0 ? J[1 + SX][0] : J[1 + SX][1];
-          const float uky = ck == 0 ? J[1 + SY][0] : J[1 + SY][1];
-          const float m = cv * rb;
-          Jb[0][0] = fmaf(m, ukx, Jb[0][0]);
-          Jb[0][1] = fmaf(m, uky, Jb[0][1]);
-          const float m0 = ck == 0 ? m : 0.f, m1 = ck == 0 ? 0.f : m;
-          Jb[1 + SX][0] = fmaf(m0, J[0][0], Jb[1 + SX][0]);
-          Jb[1 + SY][0] = fmaf(m0, J[0][1], Jb[1 + SY][0]);
-          Jb[1 + SX][1] = fmaf(m1, J[0][0], Jb[1 + SX][1]);
-          Jb[1 + SY][1] = fmaf(m1, J[0][1], Jb[1 + SY][1]);
-        }
-      }
-    }
-    if constexpr (TRAIN) {
-#pragma unroll
-      for (int o = 0; o < O; ++o) gbo[o] += Jb[0][o];
-      float zout[C][KL];
-#pragma unroll
-      for (int q = 0; q < KL; ++q) {
-        float aj[C], ab[C], zb[C], k1[D];
-#pragma unroll
-        for (int i = 0; i < D; ++i) k1[i] = 0.f;
+        for (int o = 0; o < O; ++o) J[c][o] = 0.f;
+      const int k_end = (s1 + 1) * KS < H ? (s1 + 1) * KS : H;
+      for (int k = s1 * KS; k < k_end; ++k) {
+        const float4 kv = *reinterpret_cast<const float4*>(sKo + k * 4);
+        const float kov[4] = {kv.x, kv.y, kv.z, kv.w};
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-          aj[c] = a[c][q];
-          float b = 0.f;
+          const float a = base[jet_off<NR>(c * P + p1, k)];
 #pragma unroll
-          for (int o = 0; o < O; ++o) {
-            b = fmaf(Jb[c][o], ko[q][o], b);
-            gko[q][o] = fmaf(aj[c], Jb[c][o], gko[q][o]);
-          }
-          ab[c] = b;
+          for (int o = 0; o < O; ++o) J[c][o] = fmaf(a, kov[o], J[c][o]);
         }
-        layered::jet_bwd<D, ORDER, false>(aj, k1, ab, zb);
-#pragma unroll
-        for (int c = 0; c < C; ++c) zout[c][q] = zb[c];
       }
 #pragma unroll
       for (int c = 0; c < C; ++c)
 #pragma unroll
-        for (int q = 0; q < KL; ++q) base[jet_off<G::NR>(c * P + p, lane + 32 * q)] = zout[c][q];
+        for (int o = 0; o < O; ++o) sJp[(s1 * P + p1) * CO + c * O + o] = J[c][o];
     }
+    __syncthreads();
+    if (tid < P) {
+      const long long gp = p_begin + (long long)tile * P + tid;
+      const bool valid = gp < n;
+      float J[C][O], Jb[C][O];
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+#pragma unroll
+        for (int o = 0; o < O; ++o) {
+          float v = c == 0 ? __ldg(bo + o) : 0.f;
+#pragma unroll
+          for (int s = 0; s < NS; ++s) v += sJp[(s * P + tid) * CO + c * O + o];
+          J[c][o] = v;
+          Jb[c][o] = 0.f;
+        }
+      if (seg->y_out != nullptr && valid) {
+#pragma unroll
+        for (int o = 0; o < O; ++o) seg->y_out[gp * O + o] = J[0][o];
+      }
+      float gb[O];
+#pragma unroll
+      for (int o = 0; o < O; ++o) gb[o] = 0.f;
+#pragma unroll 1
+      for (int t = 0; t < n_terms; ++t) {
+        const TermDev* __restrict__ T = seg->terms + t;
+        if (TRAIN && !T->train) continue;
+        float r = 0.f;
+#pragma unroll
+        for (int o = 0; o < O; ++o)
+#pragma unroll
+          for (int c = 0; c < C; ++c) r = fmaf(__ldg(&T->coef[o][c]), J[c][o], r);
+        float cv = 0.f;
+        int ck = 0;
+        if constexpr (ORDER >= 1 && O >= 2) {
+          cv = __ldg(&T->conv);
+          ck = __ldg(&T->conv_k);
+          const float ukx = ck == 0 ? J[1 + SX][0] : J[1 + SX][1];
+          const float uky = ck == 0 ? J[1 + SY][0] : J[1 + SY][1];
+          r = fmaf(cv, fmaf(J[0][0], ukx, J[0][1] * uky), r);
+        }
+        if (T->rhs != nullptr && valid) r = fmaf(-__ldg(&T->rhs_scale), __ldg(T->rhs + gp), r);
+        if (!valid) r = 0.f;
+        atomicAdd(&sSq[t], r * r);
+        if constexpr (TRAIN) {
+          const float rb = __ldg(&T->scale) * r;
+#pragma unroll
+          for (int o = 0; o < O; ++o)
+#pragma unroll
+            for (int c = 0; c < C; ++c) Jb[c][o] = fmaf(__ldg(&T->coef[o][c]), rb, Jb[c][o]);
+          if constexpr (ORDER >= 1 && O >= 2) {
+            const float ukx = ck == 0 ? J[1 + SX][0] : J[1 + SX][1];
+            const float uky = ck == 0 ? J[1 + SY][0] : J[1 + SY][1];
+            const float m = cv * rb;
+            Jb[0][0] = fmaf(m, ukx, Jb[0][0]);
+            Jb[0][1] = fmaf(m, uky, Jb[0][1]);
+            const float m0 = ck == 0 ? m : 0.f, m1 = ck == 0 ? 0.f : m;
+            Jb[1 + SX][0] = fmaf(m0, J[0][0], Jb[1 + SX][0]);
+            Jb[1 + SY][0] = fmaf(m0, J[0][1], Jb[1 + SY][0]);
+            Jb[1 + SX][1] = fmaf(m1, J[0][0], Jb[1 + SX][1]);
+            Jb[1 + SY][1] = fmaf(m1, J[0][1], Jb[1 + SY][1]);
+          }
+        }
+      }
+      if constexpr (TRAIN) {
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+#pragma unroll
+          for (int o = 0; o < O; ++o) sJb[tid * CO + c * O + o] = Jb[c][o];
+#pragma unroll
+        for (int o = 0; o < O; ++o) atomicAdd(&sGbo[o], Jb[0][o]);
+      }
+    }
+    if constexpr (TRAIN) {
+      __syncthreads();
+      // ---- phase 2 ----
+      float* io = base + (size_t)(k2 >> 3) * (NR * 8) + (size_t)(k2 & 7) * 4;
+      for (int g = h2; g < P / 4; g += 2) {
+        float a[C][4];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float4 t4 = *reinterpret_cast<const float4*>(io + (size_t)(c * (P / 4) + g) * 32);
+          a[c][0] = t4.x; a[c][1] = t4.y; a[c][2] = t4.z; a[c][3] = t4.w;
+        }
+        float z[C][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float* jb = sJb + (4 * g + i) * CO;
+          float aj[C], ab[C], zb[C], k1[D];
+#pragma unroll
+          for (int t = 0; t < D; ++t) k1[t] = 0.f;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            aj[c] = a[c][i];
+            float b = 0.f;
+#pragma unroll
+            for (int o = 0; o < O; ++o) {
+              const float w = jb[c * O + o];
+              b = fmaf(w, ko2[o], b);
+              gko[o] = fmaf(aj[c], w, gko[o]);
+            }
+            ab[c] = b;
+          }
+          layered::jet_bwd<D, ORDER, false>(aj, k1, ab, zb);
+#pragma unroll
+          for (int c = 0; c < C; ++c) z[c][i] = zb[c];
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+          *reinterpret_cast<float4*>(io + (size_t)(c * (P / 4) + g) * 32) = make_float4(z[c][0], z[c][1], z[c][2], z[c][3]);
+      }
+    }
+    __syncthreads();      // sJp / sJb are reused by the next tile
   }
   if constexpr (TRAIN) {
 #pragma unroll
-    for (int q = 0; q < KL; ++q)
-#pragma unroll
-      for (int o = 0; o < O; ++o) atomicAdd(grad + off_ko + (lane + 32 * q) * O + o, gko[q][o]);
-    if (lane == 0) {
-#pragma unroll
-      for (int o = 0; o < O; ++o) atomicAdd(grad + off_ko + H * O + o, gbo[o]);
-    }
+    for (int o = 0; o < O; ++o) atomicAdd(grad + off_ko + k2 * O + o, gko[o]);
+    if (tid < O) atomicAdd(grad + off_ko + H * O + tid, sGbo[tid]);
   }
-  if (lane == 0) {
-    const int n_terms = seg->n_terms;
-#pragma unroll
-    for (int t = 0; t < kMaxTerms; ++t)
-      if (t < n_terms && (!TRAIN || seg->terms[t].train)) atomicAdd(sumsq + seg->terms[t].out_index, sq[t]);
-  }
+  if (tid < n_terms && (!TRAIN || seg->terms[tid].train)) atomicAdd(sumsq + seg->terms[tid].out_index, sSq[tid]);
 }
 
 // ---- K1 / b1 gradients from z-bar_1 (SIMT): thread = (neuron, 4-point group), block-strided over tiles ------

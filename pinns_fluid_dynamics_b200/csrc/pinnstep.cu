@@ -343,12 +343,11 @@ static int tc_run_set(pinn_plan* p, const float* params, float* out, cudaStream_
       const float* img = p->wimg + (size_t)(l - 2) * tc::kLayerImgFloats;
       tc::tc_layer<D, ORDER, 0><<<grid, tc::kLayerThreads, S::TOTAL, st>>>(img, bias, act(l - 1), act(l), params, tiles);
     }
-    long long grid_out = ((long long)tiles * G::P + 7) / 8;
-    if (grid_out > 8LL * p->num_sms) grid_out = 8LL * p->num_sms;
+    const int grid_out = tiles < 4 * p->num_sms ? tiles : 4 * p->num_sms;
     if (train)
-      tc::tc_out_layer<D, O, ORDER, true><<<(int)grid_out, 256, 0, st>>>(params, off_ko, seg_dev, b0, tiles, act(L), out, out + p->P);
+      tc::tc_out_layer<D, O, ORDER, true><<<grid_out, 256, 0, st>>>(params, off_ko, seg_dev, b0, tiles, act(L), out, out + p->P);
     else
-      tc::tc_out_layer<D, O, ORDER, false><<<(int)grid_out, 256, 0, st>>>(params, off_ko, seg_dev, b0, tiles, act(L), out, out + p->P);
+      tc::tc_out_layer<D, O, ORDER, false><<<grid_out, 256, 0, st>>>(params, off_ko, seg_dev, b0, tiles, act(L), out, out + p->P);
     *launches += L + 1;
     if (train) {
       const long long n_slabs = (long long)tiles * (G::NR / tc::kWgRows);

@@ -155,6 +155,97 @@ __device__ __forceinline__ void tanh_jet_bwd_l1(float a0, const float (&zd)[Cfg:
   }
 }
 
+// ---- packed versions: a lane's two points travel as the halves of a float2 through fma.rn.f32x2 / mul / add
+// (one issue slot and one dependent-chain step for both points; the tanh-jet phases are latency-bound) -------
+__device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
+__device__ __forceinline__ float2 tanh2(float2 z) {          // tanh_accurate on both halves
+  const float2 u = mul2(z, z);
+  float2 q = fma2(u, bc2(-0.006615748628973961f), bc2(0.021312739700078964f));
+  q = fma2(q, u, bc2(-0.053910065442323685f));
+  q = fma2(q, u, bc2(0.13333117961883545f));
+  q = fma2(q, u, bc2(-0.3333333134651184f));
+  const float2 small = fma2(mul2(z, u), q, z);
+  const float2 az = make_float2(fabsf(z.x), fabsf(z.y));
+  const float2 arg = mul2(az, bc2(-2.885390081777927f));
+  float2 e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(arg.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(arg.y));
+  const float2 d = add2(e, bc2(1.0f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(d.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(d.y));
+  const float2 t = fma2(d, r, bc2(-2.0f));                   // d r - 2 = -(2 - d r)
+  const float2 m2e = mul2(e, bc2(2.0f));
+  const float2 big = fma2(m2e, mul2(r, t), bc2(1.0f));       // 1 - 2 e r (2 - d r)
+  return make_float2(az.x < 0.55f ? small.x : copysignf(big.x, z.x), az.y < 0.55f ? small.y : copysignf(big.y, z.y));
+}
+
+template <class Cfg>
+__device__ __forceinline__ void jet2_from_a0(float2 a0, const float2 (&zd)[Cfg::D], float2 zxx, float2 zyy,
+                                             float2 (&a)[Cfg::C]) {
+  constexpr int D = Cfg::D;
+  a[0] = a0;
+  if constexpr (Cfg::ORDER >= 1) {
+    const float2 na0 = mul2(a0, bc2(-1.0f));
+    const float2 s = fma2(na0, a0, bc2(1.0f));
+#pragma unroll
+    for (int i = 0; i < D; ++i) a[1 + i] = mul2(s, zd[i]);
+    if constexpr (Cfg::ORDER >= 2) {
+      const float2 m = mul2(na0, s);
+      const float2 q = add2(m, m);                           // -2 a0 s
+      a[1 + D] = fma2(mul2(q, zd[Cfg::SX]), zd[Cfg::SX], mul2(s, zxx));
+      a[2 + D] = fma2(mul2(q, zd[Cfg::SY]), zd[Cfg::SY], mul2(s, zyy));
+    }
+  }
+}
+
+// z-bar from a-bar given the STORED a-jets (LAYER1: the pre-activation jet is (z, zd1[i], 0, 0) instead)
+template <class Cfg, bool LAYER1>
+__device__ __forceinline__ void tanh_jet2_bwd(const float2 (&aj)[Cfg::C], const float2 (&zd1)[Cfg::D],
+                                              const float2 (&ab)[Cfg::C], float2 (&zb)[Cfg::C]) {
+  constexpr int D = Cfg::D;
+  const float2 a0 = aj[0];
+  const float2 na0 = mul2(a0, bc2(-1.0f));
+  const float2 s = fma2(na0, a0, bc2(1.0f));
+  zb[0] = mul2(s, ab[0]);
+  if constexpr (Cfg::ORDER >= 1) {
+    const float2 m = mul2(na0, s);
+    const float2 q = add2(m, m);
+    float2 rs = bc2(0.f);
+    if constexpr (!LAYER1) rs = make_float2(s.x > 0.0f ? __frcp_rn(s.x) : 0.0f, s.y > 0.0f ? __frcp_rn(s.y) : 0.0f);
+    float2 zd[D];
+    float2 acc = bc2(0.f);
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      zd[i] = LAYER1 ? zd1[i] : mul2(aj[(Cfg::ORDER >= 1) ? 1 + i : 0], rs);
+      zb[1 + i] = mul2(s, ab[1 + i]);
+      acc = fma2(zd[i], ab[1 + i], acc);
+    }
+    if constexpr (Cfg::ORDER >= 2) {
+      const float2 zx2 = mul2(zd[Cfg::SX], zd[Cfg::SX]), zy2 = mul2(zd[Cfg::SY], zd[Cfg::SY]);
+      const float2 nq = mul2(q, bc2(-1.0f));
+      // q' = -2 s (1 - 3 a0^2)
+      const float2 qp = mul2(mul2(s, bc2(-2.0f)), fma2(mul2(a0, bc2(-3.0f)), a0, bc2(1.0f)));
+      zb[1 + D] = mul2(s, ab[1 + D]);
+      zb[2 + D] = mul2(s, ab[2 + D]);
+      const float2 q2 = add2(q, q);
+      zb[1 + Cfg::SX] = fma2(mul2(q2, zd[Cfg::SX]), ab[1 + D], zb[1 + Cfg::SX]);
+      zb[1 + Cfg::SY] = fma2(mul2(q2, zd[Cfg::SY]), ab[2 + D], zb[1 + Cfg::SY]);
+      if constexpr (!LAYER1) {
+        const float2 zxx = mul2(fma2(nq, zx2, aj[(Cfg::ORDER >= 2) ? 1 + D : 0]), rs);
+        const float2 zyy = mul2(fma2(nq, zy2, aj[(Cfg::ORDER >= 2) ? 2 + D : 0]), rs);
+        acc = fma2(zxx, ab[1 + D], acc);
+        acc = fma2(zyy, ab[2 + D], acc);
+      }
+      zb[0] = fma2(qp, fma2(zx2, ab[1 + D], mul2(zy2, ab[2 + D])), zb[0]);
+    }
+    zb[0] = fma2(q, acc, zb[0]);
+  }
+}
+
 // ---- register-tiled GEMM over one warp's 16 points --------------------------------------------
 // acc[c][jj] (x: point 2lr, y: point 2lr+1) += sum_k in[k][c][p] * W[k][lc*TC + jj]
 template <class Cfg>
@@ -238,15 +329,12 @@ __device__ __forceinline__ void write_a1_jets(float* __restrict__ dst, const flo
   for (int jj = 0; jj < TC; ++jj) {
     const int j = lc + 4 * jj;
     const float2 a0 = *reinterpret_cast<const float2*>(a1buf + j * kChunk + 2 * lr);
-    float zd[D];
+    float2 zd[D], a[C];
 #pragma unroll
-    for (int i = 0; i < D; ++i) zd[i] = sK1[i * H + j];
-    float ax[C], ay[C];
-    jet_from_a0<Cfg>(a0.x, zd, 0.f, 0.f, ax);
-    jet_from_a0<Cfg>(a0.y, zd, 0.f, 0.f, ay);
+    for (int i = 0; i < D; ++i) zd[i] = bc2(sK1[i * H + j]);
+    jet2_from_a0<Cfg>(a0, zd, bc2(0.f), bc2(0.f), a);
 #pragma unroll
-    for (int c = 0; c < C; ++c)
-      *reinterpret_cast<float2*>(dst + j * RS + c * kChunk + 2 * lr) = make_float2(ax[c], ay[c]);
+    for (int c = 0; c < C; ++c) *reinterpret_cast<float2*>(dst + j * RS + c * kChunk + 2 * lr) = a[c];
   }
 }
 
@@ -348,14 +436,10 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
 #pragma unroll
     for (int jj = 0; jj < TC; ++jj) {
       const int j = lc + 4 * jj;
-      float z0 = sB[j], z1 = z0;
+      float2 z = bc2(sB[j]);
 #pragma unroll
-      for (int i = 0; i < D; ++i) {
-        const float w = sK1[i * H + j];
-        z0 = fmaf(x0[i], w, z0);
-        z1 = fmaf(x1[i], w, z1);
-      }
-      *reinterpret_cast<float2*>(a1buf + j * kChunk + 2 * lr) = make_float2(tanh_accurate(z0), tanh_accurate(z1));
+      for (int i = 0; i < D; ++i) z = fma2(make_float2(x0[i], x1[i]), bc2(sK1[i * H + j]), z);
+      *reinterpret_cast<float2*>(a1buf + j * kChunk + 2 * lr) = tanh2(z);
     }
     write_a1_jets<Cfg>(bufL, a1buf, sK1, lr, lc);
     __syncwarp();
@@ -383,34 +467,21 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
 #pragma unroll
       for (int jj = 0; jj < TC; ++jj) {
         const int j = lc + 4 * jj;
-        float zx[C], zy[C], ax[C], ay[C];
+        float2 zd[D], a[C];
+        float2 zxx = bc2(0.f), zyy = bc2(0.f);
 #pragma unroll
-        for (int c = 0; c < C; ++c) { zx[c] = acc[c][jj].x; zy[c] = acc[c][jj].y; }
-        float zdx[D], zdy[D];
-        float zxx0 = 0.f, zyy0 = 0.f, zxx1 = 0.f, zyy1 = 0.f;
-        if constexpr (ORDER >= 1) {
+        for (int i = 0; i < D; ++i) zd[i] = ORDER >= 1 ? acc[(ORDER >= 1) ? 1 + i : 0][jj] : bc2(0.f);
+        if constexpr (ORDER >= 2) { zxx = acc[(ORDER >= 2) ? 1 + D : 0][jj]; zyy = acc[(ORDER >= 2) ? 2 + D : 0][jj]; }
+        jet2_from_a0<Cfg>(tanh2(acc[0][jj]), zd, zxx, zyy, a);
 #pragma unroll
-          for (int i = 0; i < D; ++i) { zdx[i] = zx[1 + i]; zdy[i] = zy[1 + i]; }
-        } else {
-#pragma unroll
-          for (int i = 0; i < D; ++i) { zdx[i] = 0.f; zdy[i] = 0.f; }
-        }
-        if constexpr (ORDER >= 2) { zxx0 = zx[1 + D]; zyy0 = zx[2 + D]; zxx1 = zy[1 + D]; zyy1 = zy[2 + D]; }
-        jet_from_a0<Cfg>(tanh_accurate(zx[0]), zdx, zxx0, zyy0, ax);
-        jet_from_a0<Cfg>(tanh_accurate(zy[0]), zdy, zxx1, zyy1, ay);
-#pragma unroll
-        for (int c = 0; c < C; ++c)
-          *reinterpret_cast<float2*>(out + j * RS + c * kChunk + 2 * lr) = make_float2(ax[c], ay[c]);
+        for (int c = 0; c < C; ++c) *reinterpret_cast<float2*>(out + j * RS + c * kChunk + 2 * lr) = a[c];
         if (l == L) {
           const float4 ko = *reinterpret_cast<const float4*>(sKo + j * 4);
           const float kov[4] = {ko.x, ko.y, ko.z, ko.w};
 #pragma unroll
           for (int c = 0; c < C; ++c)
 #pragma unroll
-            for (int o = 0; o < O; ++o) {
-              J[c][o].x = fmaf(ax[c], kov[o], J[c][o].x);
-              J[c][o].y = fmaf(ay[c], kov[o], J[c][o].y);
-            }
+            for (int o = 0; o < O; ++o) J[c][o] = fma2(a[c], bc2(kov[o]), J[c][o]);
         }
       }
       __syncwarp();
@@ -515,35 +586,33 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
 #pragma unroll
         for (int jj = 0; jj < TC; ++jj) {
           const int j = lc + 4 * jj;
-          float ajx[C], ajy[C], abx[C], aby[C], zbx[C], zby[C];
+          float2 aj[C], ab[C], zb[C], zdummy[D];
+#pragma unroll
+          for (int i = 0; i < D; ++i) zdummy[i] = bc2(0.f);
           const float4 ko = *reinterpret_cast<const float4*>(sKo + j * 4);
           const float kov[4] = {ko.x, ko.y, ko.z, ko.w};
-          float pk[O];
+          float2 pk[O];
 #pragma unroll
-          for (int o = 0; o < O; ++o) pk[o] = 0.f;
+          for (int o = 0; o < O; ++o) pk[o] = bc2(0.f);
 #pragma unroll
           for (int c = 0; c < C; ++c) {
-            const float2 a = *reinterpret_cast<const float2*>(bufL + j * RS + c * kChunk + 2 * lr);
-            ajx[c] = a.x; ajy[c] = a.y;
-            float bx = 0.f, by = 0.f;
+            aj[c] = *reinterpret_cast<const float2*>(bufL + j * RS + c * kChunk + 2 * lr);
+            float2 b = bc2(0.f);
 #pragma unroll
             for (int o = 0; o < O; ++o) {
-              bx = fmaf(Jb[c][o].x, kov[o], bx);
-              by = fmaf(Jb[c][o].y, kov[o], by);
-              pk[o] = fmaf(a.x, Jb[c][o].x, fmaf(a.y, Jb[c][o].y, pk[o]));
+              b = fma2(Jb[c][o], bc2(kov[o]), b);
+              pk[o] = fma2(aj[c], Jb[c][o], pk[o]);
             }
-            abx[c] = bx; aby[c] = by;
+            ab[c] = b;
           }
 #pragma unroll
           for (int o = 0; o < O; ++o) {
-            const float v = reduce_over_lr(pk[o]);
+            const float v = reduce_over_lr(pk[o].x + pk[o].y);
             if (lr == 0) sg[Cfg::G_KO + j * 4 + o] += v;
           }
-          tanh_jet_bwd<Cfg>(ajx, abx, zbx);
-          tanh_jet_bwd<Cfg>(ajy, aby, zby);
+          tanh_jet2_bwd<Cfg, false>(aj, zdummy, ab, zb);
 #pragma unroll
-          for (int c = 0; c < C; ++c)
-            *reinterpret_cast<float2*>(bufL + j * RS + c * kChunk + 2 * lr) = make_float2(zbx[c], zby[c]);
+          for (int c = 0; c < C; ++c) *reinterpret_cast<float2*>(bufL + j * RS + c * kChunk + 2 * lr) = zb[c];
         }
         __syncwarp();
       }
@@ -571,18 +640,17 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
 #pragma unroll
           for (int jj = 0; jj < TC; ++jj) {
             const int j = lc + 4 * jj;
-            float ajx[C], ajy[C], abx[C], aby[C], zbx[C], zby[C];
+            float2 aj[C], ab[C], zb[C], zdummy[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) zdummy[i] = bc2(0.f);
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-              const float2 a = *reinterpret_cast<const float2*>(Aprev + j * RS + c * kChunk + 2 * lr);
-              ajx[c] = a.x; ajy[c] = a.y;
-              abx[c] = acc[c][jj].x; aby[c] = acc[c][jj].y;
+              aj[c] = *reinterpret_cast<const float2*>(Aprev + j * RS + c * kChunk + 2 * lr);
+              ab[c] = acc[c][jj];
             }
-            tanh_jet_bwd<Cfg>(ajx, abx, zbx);
-            tanh_jet_bwd<Cfg>(ajy, aby, zby);
+            tanh_jet2_bwd<Cfg, false>(aj, zdummy, ab, zb);
 #pragma unroll
-            for (int c = 0; c < C; ++c)
-              *reinterpret_cast<float2*>(Aprev + j * RS + c * kChunk + 2 * lr) = make_float2(zbx[c], zby[c]);
+            for (int c = 0; c < C; ++c) *reinterpret_cast<float2*>(Aprev + j * RS + c * kChunk + 2 * lr) = zb[c];
           }
           __syncwarp();
         } else {
@@ -590,20 +658,21 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
 #pragma unroll
           for (int jj = 0; jj < TC; ++jj) {
             const int j = lc + 4 * jj;
-            const float2 a0 = *reinterpret_cast<const float2*>(a1buf + j * kChunk + 2 * lr);
-            float zd[D], abx[C], aby[C], zbx[C], zby[C];
+            float2 aj[C], ab[C], zb[C], zd[D];
+            aj[0] = *reinterpret_cast<const float2*>(a1buf + j * kChunk + 2 * lr);
 #pragma unroll
-            for (int i = 0; i < D; ++i) zd[i] = sK1[i * H + j];
+            for (int c = 1; c < C; ++c) aj[c] = bc2(0.f);
 #pragma unroll
-            for (int c = 0; c < C; ++c) { abx[c] = acc[c][jj].x; aby[c] = acc[c][jj].y; }
-            tanh_jet_bwd_l1<Cfg>(a0.x, zd, abx, zbx);
-            tanh_jet_bwd_l1<Cfg>(a0.y, zd, aby, zby);
-            const float vb = reduce_over_lr(zbx[0] + zby[0]);
+            for (int i = 0; i < D; ++i) zd[i] = bc2(sK1[i * H + j]);
+#pragma unroll
+            for (int c = 0; c < C; ++c) ab[c] = acc[c][jj];
+            tanh_jet2_bwd<Cfg, true>(aj, zd, ab, zb);
+            const float vb = reduce_over_lr(zb[0].x + zb[0].y);
             if (lr == 0) sg[Cfg::G_B1 + j] += vb;
 #pragma unroll
             for (int i = 0; i < D; ++i) {
-              float v = fmaf(x0[i], zbx[0], x1[i] * zby[0]);
-              if constexpr (ORDER >= 1) v += zbx[1 + i] + zby[1 + i];
+              float v = fmaf(x0[i], zb[0].x, x1[i] * zb[0].y);
+              if constexpr (ORDER >= 1) v += zb[(ORDER >= 1) ? 1 + i : 0].x + zb[(ORDER >= 1) ? 1 + i : 0].y;
               v = reduce_over_lr(v);
               if (lr == 0) sg[Cfg::G_K1 + i * H + j] += v;
             }

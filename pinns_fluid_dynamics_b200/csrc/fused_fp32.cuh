@@ -215,7 +215,13 @@ __device__ __forceinline__ void tanh_jet2_bwd(const float2 (&aj)[Cfg::C], const 
     const float2 m = mul2(na0, s);
     const float2 q = add2(m, m);
     float2 rs = bc2(0.f);
-    if constexpr (!LAYER1) rs = make_float2(s.x > 0.0f ? __frcp_rn(s.x) : 0.0f, s.y > 0.0f ? __frcp_rn(s.y) : 0.0f);
+    if constexpr (!LAYER1) {      // 1/s: rcp.approx + one packed Newton step (s in (0,1]; s == 0 only when tanh saturated)
+      float2 r0;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0.x) : "f"(s.x));
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0.y) : "f"(s.y));
+      r0 = mul2(r0, fma2(mul2(s, bc2(-1.0f)), r0, bc2(2.0f)));
+      rs = make_float2(s.x > 0.0f ? r0.x : 0.0f, s.y > 0.0f ? r0.y : 0.0f);
+    }
     float2 zd[D];
     float2 acc = bc2(0.f);
 #pragma unroll

@@ -57,7 +57,10 @@ __device__ __forceinline__ void jet_bwd(const float (&aj)[Jet<D, ORDER>::C], con
   zb[0] = s * ab[0];
   if constexpr (ORDER >= 1) {
     const float q = -2.0f * a0 * s;
-    const float rs = s > 0.0f ? __frcp_rn(s) : 0.0f;
+    float rs;                                            // 1/s: rcp.approx + one Newton step (s in (0, 1])
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(s));
+    rs = rs * fmaf(-s, rs, 2.0f);
+    rs = s > 0.0f ? rs : 0.0f;
     float zd[D];
     float acc = 0.0f;
 #pragma unroll

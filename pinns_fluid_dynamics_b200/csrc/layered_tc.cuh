@@ -34,6 +34,7 @@
 //   tc_layer1_grad      K_1-bar, b_1-bar from z-bar_1 (SIMT)
 #pragma once
 #include "common.cuh"
+#include "fused_fp32.cuh"     // packed (f32x2) tanh-jet math: tanh2, jet2_from_a0, tanh_jet2_bwd
 #include "layered_fp32.cuh"   // Jet, jet_fwd, jet_bwd
 #include "umma.cuh"
 
@@ -41,6 +42,11 @@ namespace pinn {
 namespace tc {
 
 constexpr int kH = 128;
+
+template <int D_, int ORDER_>
+struct JetCfg {            // what the packed jet functions of fused_fp32.cuh need to know
+  static constexpr int D = D_, ORDER = ORDER_, C = n_channels(D_, ORDER_), SX = D_ - 2, SY = D_ - 1;
+};
 
 template <int D, int ORDER>
 struct Geo {
@@ -67,6 +73,13 @@ __device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, float (&v)[4]) {
   uint32_t r0, r1, r2, r3;
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr) : "memory");
   v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+}
+// 256-bit read-only global load (sm_100 LDG.E.256): one whole 32-byte sector per lane.  The producers read 64
+// contiguous bytes per lane; as four LDG.128 every sector was requested twice (no L1 is left beside 226 KB of
+// shared memory) -- measured 298 -> 246 us per forward layer with sector-clean loads.
+__device__ __forceinline__ void ldg256(const void* p, float4& a, float4& b) {
+  asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
 }
 // pull a contiguous global range into L2 ahead of use (no registers, no shared memory)
 __device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, uint32_t bytes) {
@@ -304,7 +317,8 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer(const float* __rest
           for (int r = 0; r < 4; ++r) v[4 * u + r] = make_float4(0.25f, -0.5f, 0.125f, 1.f);
           (void)p;
 #else
-          for (int r = 0; r < 4; ++r) v[4 * u + r] = __ldg(p + r);       // v[4u + r] = neuron 4kb + r, rows 4rb..4rb+3
+          ldg256(p, v[4 * u], v[4 * u + 1]);                             // v[4u + r] = neuron 4kb + r, rows 4rb..4rb+3
+          ldg256(p + 2, v[4 * u + 2], v[4 * u + 3]);
 #endif
         }
       }
@@ -473,23 +487,36 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer(const float* __rest
           const float4 t4 = *reinterpret_cast<const float4*>(io + gg * 32);
           aj[0][0] = t4.x; aj[0][1] = t4.y; aj[0][2] = t4.z; aj[0][3] = t4.w;
         }
+        // two points per instruction (fma.rn.f32x2): the elementwise phase is a latency-bound dependent chain and
+        // it is what keeps the TMEM buffers from being handed back to the MMA warp
+        using JC = JetCfg<D, ORDER>;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float res[C];
+        for (int h = 0; h < 2; ++h) {
+          const int i0 = 4 * gg + 2 * h;
+          float2 res[C];
           if constexpr (MODE == 0) {
-            float zd[D], zxx = 0.f, zyy = 0.f;
+            float2 zd[D], zxx = bc2(0.f), zyy = bc2(0.f);
 #pragma unroll
-            for (int t = 0; t < D; ++t) zd[t] = ORDER >= 1 ? acc[(ORDER >= 1) ? 1 + t : 0][4 * gg + i] : 0.f;
-            if constexpr (ORDER >= 2) { zxx = acc[(ORDER >= 2) ? 1 + D : 0][4 * gg + i]; zyy = acc[(ORDER >= 2) ? 2 + D : 0][4 * gg + i]; }
-            layered::jet_fwd<D, ORDER>(tanh_accurate(acc[0][4 * gg + i] + bj), zd, zxx, zyy, res);
+            for (int t = 0; t < D; ++t)
+              zd[t] = ORDER >= 1 ? make_float2(acc[(ORDER >= 1) ? 1 + t : 0][i0], acc[(ORDER >= 1) ? 1 + t : 0][i0 + 1]) : bc2(0.f);
+            if constexpr (ORDER >= 2) {
+              zxx = make_float2(acc[(ORDER >= 2) ? 1 + D : 0][i0], acc[(ORDER >= 2) ? 1 + D : 0][i0 + 1]);
+              zyy = make_float2(acc[(ORDER >= 2) ? 2 + D : 0][i0], acc[(ORDER >= 2) ? 2 + D : 0][i0 + 1]);
+            }
+            jet2_from_a0<JC>(tanh2(add2(make_float2(acc[0][i0], acc[0][i0 + 1]), bc2(bj))), zd, zxx, zyy, res);
           } else {
-            float a1[C], ab[C];
+            float2 a1[C], ab[C], zd1[D];
 #pragma unroll
-            for (int c = 0; c < C; ++c) { a1[c] = (MODE == 2 && c > 0) ? 0.f : aj[c][i]; ab[c] = acc[c][4 * gg + i]; }
-            layered::jet_bwd<D, ORDER, MODE == 2>(a1, k1, ab, res);
+            for (int t = 0; t < D; ++t) zd1[t] = bc2(k1[t]);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              a1[c] = (MODE == 2 && c > 0) ? bc2(0.f) : make_float2(aj[c][2 * h], aj[c][2 * h + 1]);
+              ab[c] = make_float2(acc[c][i0], acc[c][i0 + 1]);
+            }
+            tanh_jet2_bwd<JC, MODE == 2>(a1, zd1, ab, res);
           }
 #pragma unroll
-          for (int c = 0; c < C; ++c) acc[c][4 * gg + i] = res[c];          // results replace the consumed sums
+          for (int c = 0; c < C; ++c) { acc[c][i0] = res[c].x; acc[c][i0 + 1] = res[c].y; }   // results replace the consumed sums
         }
 #pragma unroll
         for (int c = 0; c < C; ++c)

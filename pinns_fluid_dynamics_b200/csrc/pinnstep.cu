@@ -633,7 +633,10 @@ extern "C" int pinn_forward(const pinn_mlp_desc* mlp, const float* params_dev, c
     if (!layered_supported(*mlp))
       return fail(PINN_E_INVALID, "no engine for MLP d=%d H=%d L=%d O=%d", mlp->in_dim, mlp->width, mlp->n_hidden,
                   mlp->out_dim);
-    // wide/deep network: run the layered forward kernels over a temporary workspace (synchronous free)
+    // wide/deep network: run the layered forward kernels (tensor-core engine for H = 128) over a temporary
+    // workspace (synchronous free)
+    const char* force = getenv("PINN_ENGINE");
+    const bool use_tc = tc_supported(*mlp) && !(force && strcmp(force, "layered_fp32") == 0);
     pinn_plan tmp;
     tmp.mlp = *mlp;
     tmp.device = device;
@@ -643,7 +646,7 @@ extern "C" int pinn_forward(const pinn_mlp_desc* mlp, const float* params_dev, c
     memset(&fake, 0, sizeof(fake));
     fake.n_local = n;
     tmp.sets.push_back(fake);
-    int rc = layered_alloc(&tmp);
+    int rc = use_tc ? tc_alloc(&tmp) : layered_alloc(&tmp);
     SegDev* sd_dev = nullptr;
     if (rc == PINN_OK && cudaMalloc(&sd_dev, sizeof(SegDev)) != cudaSuccess) rc = fail(PINN_E_ALLOC, "segment descriptor");
     if (rc == PINN_OK) {
@@ -660,14 +663,16 @@ extern "C" int pinn_forward(const pinn_mlp_desc* mlp, const float* params_dev, c
       tmp.eval[0] = lt;
       float* dummy = nullptr;   // no terms: nothing is written through `out`
       if (cudaMalloc(&dummy, sizeof(float) * (size_t)(tmp.P + 1)) != cudaSuccess) rc = fail(PINN_E_ALLOC, "scratch");
-      if (rc == PINN_OK) rc = run_layered(&tmp, params_dev, dummy, st, false);
+      if (rc == PINN_OK) rc = use_tc ? run_tc(&tmp, params_dev, dummy, st, false) : run_layered(&tmp, params_dev, dummy, st, false);
       cudaStreamSynchronize(st);
       if (dummy) cudaFree(dummy);
     }
     if (sd_dev) cudaFree(sd_dev);
     if (tmp.act) cudaFree(tmp.act);
     if (tmp.wt) cudaFree(tmp.wt);
-    tmp.act = tmp.wt = nullptr;
+    if (tmp.wimg) cudaFree(tmp.wimg);
+    tmp.act = tmp.wt = tmp.wimg = nullptr;
+    tmp.eval[0].segs_dev = nullptr;
     return rc;
   }
   int num_sms = 0;

@@ -288,3 +288,64 @@ def test_layered_model_forward():
     y = model(x.cuda()).double().cpu()
     ref = KerasMLP(var)(x.double()).detach()
     assert torch.allclose(y, ref, rtol=0, atol=5e-6)
+
+
+# ---- the callers of the path: optimiser rounds --------------------------------
+
+def test_adam_round_follows_float64_oracle():
+    """ns.minimize(pb, 'keras', Adam(1e-2), n) (cavity_steady.py:246): device Adam kernel + fused loss step vs the
+    float64 restatement driven by the same Keras update rule, same weights and points."""
+    from oracle import reference_step
+    data, var, model, pb = _setup("cavity_steady", SMALL["cavity_steady"])
+    ref = reference_step.build(data, var)
+    n_steps = 10
+    ns.minimize(pb, "keras", ns.optimizers.Adam(learning_rate=1e-2), num_epochs=n_steps)
+    m = [torch.zeros_like(v) for v in ref.variables]
+    v2 = [torch.zeros_like(v) for v in ref.variables]
+    for t in range(1, n_steps + 1):
+        _, _, grad = ref.loss_and_grad()
+        off = 0
+        with torch.no_grad():
+            for i, p in enumerate(ref.variables):
+                g = grad[off:off + p.numel()].view_as(p); off += p.numel()
+                m[i].mul_(0.9).add_(g, alpha=0.1)
+                v2[i].mul_(0.999).addcmul_(g, g, value=0.001)
+                step = 1e-2 * (1 - 0.999 ** t) ** 0.5 / (1 - 0.9 ** t)
+                p.addcdiv_(m[i], v2[i].sqrt().add_(1e-7), value=-step)
+    theta_ref = torch.cat([p.detach().reshape(-1) for p in ref.variables]).numpy()
+    theta = pb.flat.double().cpu().numpy()
+    assert np.linalg.norm(theta - theta_ref) / np.linalg.norm(theta_ref) < 1e-4
+    total, _, _ = pb.evaluate()
+    _, ref_total, _ = ref.loss_and_grad()
+    assert _rel(total, ref_total) < 1e-3          # 10 steps of 1e-2 amplify the FP32 rounding of the first gradients
+    assert pb.history["log"]["iter"][:2] == [0, 10]    # the reference's cadence: every 10 iterations (History_Loss.json)
+
+
+def test_scipy_bfgs_round_runs_on_the_device_step():
+    """ns.minimize(pb, 'scipy', 'BFGS', n) (cavity_steady.py:247): SciPy drives, every evaluation is one CUDA step."""
+    data, var, model, pb = _setup("colliding_flow", SMALL["colliding_flow"])
+    t0, _, _ = pb.evaluate()
+    ns.minimize(pb, "scipy", "BFGS", num_epochs=6)
+    t1, _, _ = pb.evaluate()
+    assert t1 < t0
+    assert pb.history["log_rounds"]["rounds"][-1] == "scipy_BFGS"
+
+
+def test_tensor_core_engine_linearity_over_several_batches(monkeypatch):
+    """size-independent property on the 8x128 network over 3 workspace batches (100 k points, 64 MB workspace ->
+    2 520-point batches would be 40; use 1 GB -> 43 680-point batches): the gradient is linear in the term weights."""
+    monkeypatch.setenv("PINN_TC_WORKSPACE_MB", "1024")
+    kw = dict(PDE=100_000, BC=200, IC=100, Vel=1, Pres=1, Test=50, noise_bnd=0.05, noise_fit=0.05, n_times=4, hidden=(128,) * 8)
+    data = problems.cavity_unsteady(seed=1, **kw)
+    model = ns.TanhMLP(3, [128] * 8, 3, device="cuda", seed=3)
+    losses, ltest = loss_tables.build_loss_table(data)
+    pb1 = ns.OptimizationProblem(model.variables, losses, ltest)
+    assert pb1.plan.engine == "layered_tf32x3"
+    _, vals1, g1 = pb1.evaluate()
+    g1 = g1.clone()
+    for l in losses:
+        l.weight *= 2.0
+    pb2 = ns.OptimizationProblem(model.variables, losses, ltest)
+    _, vals2, g2 = pb2.evaluate()
+    assert np.allclose(vals1, vals2, rtol=2e-5)
+    assert float((2.0 * g1 - g2).norm() / g2.norm()) < 1e-4

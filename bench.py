@@ -259,7 +259,7 @@ def run_ours(args):
     # ---- e2e: host-resident inputs, H2D every step, D2H of the per-term sums every step ----------
     h2d = plan.pin_host_inputs()
     T = max(1, pb.compiled.n_out_terms)
-    host_out = torch.empty(T, dtype=torch.float32).pin_memory()
+    host_out = torch.empty(T, dtype=torch.float32, pin_memory=True)
     for _ in range(3):
         plan.upload_inputs(); s = pb.training_step(opt); host_out.copy_(s[:T], non_blocking=True); torch.cuda.synchronize()
     barrier()

@@ -17,6 +17,7 @@ test losses excluded from the total, rounds named ``keras_<Optimizer>`` / ``scip
 from __future__ import annotations
 
 import json
+import os
 import math
 from typing import Callable, List, Optional, Sequence, Union
 
@@ -323,8 +324,14 @@ def minimize(pb: OptimizationProblem, backend: str, optimizer, num_epochs: int) 
             pb.step_done()
 
         x0 = pb.flat.detach().double().cpu().numpy()
-        res = scipy.optimize.minimize(fun, x0, jac=True, method=method, callback=cb,
-                                      options={"maxiter": int(num_epochs)})
+        if method.upper() == "BFGS" and os.environ.get("PINN_BFGS", "device") != "scipy":
+            # SciPy's BFGS algorithm and line search, inverse-Hessian update in its O(P^2) form on the device
+            # (scipy.optimize.minimize spends 133 ms per iteration in two P^3 products for P = 2307): bfgs.py
+            from .bfgs import minimize_bfgs
+            res = minimize_bfgs(fun, x0, maxiter=int(num_epochs), callback=cb, device=pb.flat.device)
+        else:
+            res = scipy.optimize.minimize(fun, x0, jac=True, method=method, callback=cb,
+                                          options={"maxiter": int(num_epochs)})
         pb.flat.copy_(torch.as_tensor(res.x, dtype=torch.float32))
     else:
         raise ValueError(f"unknown backend {backend!r} (expected 'keras' or 'scipy')")

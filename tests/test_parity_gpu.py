@@ -349,3 +349,18 @@ def test_tensor_core_engine_linearity_over_several_batches(monkeypatch):
     _, vals2, g2 = pb2.evaluate()
     assert np.allclose(vals1, vals2, rtol=2e-5)
     assert float((2.0 * g1 - g2).norm() / g2.norm()) < 1e-4
+
+
+def test_device_bfgs_round_follows_scipy_round(monkeypatch):
+    """the BFGS round with the inverse Hessian on the device vs the same round driven by scipy.optimize.minimize
+    (what nisaba calls): same algorithm and line search, so the loss after a few iterations agrees closely even
+    though every evaluation is an FP32 device step."""
+    def run(mode):
+        monkeypatch.setenv("PINN_BFGS", mode)
+        data, var, model, pb = _setup("colliding_flow", SMALL["colliding_flow"])
+        ns.minimize(pb, "scipy", "BFGS", num_epochs=8)
+        return pb.evaluate()[0], pb.flat.double().cpu().numpy()
+    t_dev, x_dev = run("device")
+    t_ref, x_ref = run("scipy")
+    assert _rel(t_dev, t_ref) < 5e-3
+    assert np.linalg.norm(x_dev - x_ref) / np.linalg.norm(x_ref) < 1e-3

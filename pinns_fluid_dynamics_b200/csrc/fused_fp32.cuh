@@ -260,7 +260,7 @@ __device__ __forceinline__ void warp_gemm(const float* __restrict__ in, const fl
   constexpr int C = Cfg::C, TC = Cfg::TC, H = Cfg::H, RS = Cfg::RS;
   const float* arow = in + 2 * lr;
   const float* wrow = W + lc * TC;
-#pragma unroll 2
+#pragma unroll 4
   for (int k = 0; k < H; ++k) {
     float2 a[C];
 #pragma unroll
@@ -291,7 +291,7 @@ template <class Cfg>
 __device__ __forceinline__ void warp_wgrad(const float* __restrict__ A, const float* __restrict__ Z,
                                            float (&gK)[Cfg::TI][Cfg::TC], float (&gb)[Cfg::TC], int li, int lj) {
   constexpr int C = Cfg::C, TC = Cfg::TC, TI = Cfg::TI, H = Cfg::H, RS = Cfg::RS;
-#pragma unroll 1
+#pragma unroll 2
   for (int cq = 0; cq < C * 4; ++cq) {      // (channel, point quad): offset cq*4 floats within a row
     float4 av[TI];
 #pragma unroll

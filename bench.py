@@ -239,6 +239,11 @@ def run_ours(args):
                         "MEASURED_PEAKS.json holds no TF32 figure")
         except Exception:
             pass
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic_tc_r01.json")) as fh:
+                traffic = json.load(fh)["dram_bytes_per_point"] * n_local_pde
+        except Exception:
+            pass
     else:
         bound, peak, peak_src = "fp32_fma", 71.7, "fallback"
         kernel_name = "fused_step_kernel<D,H,L,O,ORDER=2,TRAIN>" if plan.engine == "fused_fp32" else "layered_fp32 collocation pipeline"

@@ -3,6 +3,8 @@
 // 64-byte blocks, LDG.256) and 256 "epilogue" threads write a 120 KB tile as 16-byte chunks (30 STG.128 each).
 // mode 0: readers and writers run freely (perfect overlap)   mode 1: the writers of tile i wait for its readers
 // (the burst structure of the real kernel)                   mode 2: reads only   mode 3: writes only
+// mode 4/5: as 2/0 with a per-lane prefetch.global.L2 of the same bytes one tile (gridDim tiles) ahead
+// mode 6/7: as 2/0 with one cp.async.bulk.prefetch.L2 of the whole next tile per tile
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
@@ -19,6 +21,8 @@ __global__ void __launch_bounds__(384) pattern(const float* __restrict__ in, flo
   float acc = 0.f;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     if (tid < 128) {
+      if (mode >= 6 && tid == 0 && tile + gridDim.x < n_tiles)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(in + (size_t)(tile + gridDim.x) * NR * H), "r"(NR * H * 4) : "memory");
       if (mode != 3) {
         const int kb = (tid >> 3) & 3, rb0 = (tid & 7) + 8 * (tid >> 5);
         for (int kc = 0; kc < 8; ++kc) {
@@ -28,6 +32,8 @@ __global__ void __launch_bounds__(384) pattern(const float* __restrict__ in, flo
             const int rb = rb0 + 32 * u;
             if (rb < NR / 4) {
               float4 a, b, c, d;
+              if ((mode == 4 || mode == 5) && tile + gridDim.x < n_tiles)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(src + rb * 128 + (size_t)gridDim.x * NR * H * 4));
               ldg256(src + rb * 128, a, b);
               ldg256(src + rb * 128 + 32, c, d);
               acc += a.x + b.y + c.z + d.w;
@@ -38,7 +44,7 @@ __global__ void __launch_bounds__(384) pattern(const float* __restrict__ in, flo
       if (mode == 1) asm volatile("bar.arrive 1, 384;");
     } else {
       if (mode == 1) asm volatile("bar.sync 1, 384;");
-      if (mode != 2) {
+      if (mode != 2 && mode != 4 && mode != 6) {
         const int t = tid - 128, j = t & 127, half = t >> 7;
         float* io = out + (size_t)tile * NR * H + (size_t)(j >> 3) * (NR * 8) + (size_t)half * (5 * 32) + (size_t)(j & 7) * 4;
 #pragma unroll
@@ -58,8 +64,9 @@ int main() {
   CK(cudaMalloc(&in, bytes)); CK(cudaMalloc(&out, bytes)); CK(cudaMalloc(&sink, 4));
   CK(cudaMemset(in, 0, bytes));
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-  const char* names[4] = {"read + write, free running", "read then write per tile (burst)", "read only", "write only"};
-  for (int mode = 0; mode < 4; ++mode) {
+  const char* names[8] = {"read + write, free running", "read then write per tile (burst)", "read only", "write only",
+                          "read only + per-lane L2 prefetch", "read + write + per-lane L2 prefetch", "read only + bulk L2 prefetch", "read + write + bulk L2 prefetch"};
+  for (int mode = 0; mode < 8; ++mode) {
     pattern<<<148, 384>>>(in, out, n_tiles, mode, sink);
     CK(cudaDeviceSynchronize());
     CK(cudaEventRecord(e0));
@@ -67,7 +74,7 @@ int main() {
     CK(cudaEventRecord(e1));
     CK(cudaDeviceSynchronize());
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
-    const double moved = (mode <= 1 ? 2.0 : 1.0) * bytes;
+    const double moved = ((mode <= 1 || mode == 5 || mode == 7) ? 2.0 : 1.0) * bytes;
     printf("%-36s: %.3f ms, %.2f TB/s\n", names[mode], ms, moved / ms * 1e-9);
   }
   return 0;

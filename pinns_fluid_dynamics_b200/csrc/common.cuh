@@ -35,6 +35,14 @@ struct SegDev {
   TermDev terms[kMaxTerms];
 };
 
+// One tile of the layered tensor-core engine: P consecutive points of ONE point set (tiles never straddle sets, so all
+// sets of a derivative order share one pipeline run).
+struct TileDev {
+  int seg;              // index into the launch table's segments
+  int pad_;
+  long long p_begin;    // first point of the tile inside its set
+};
+
 __host__ __device__ constexpr int n_channels(int d, int order) {
   return order == 0 ? 1 : (order == 1 ? 1 + d : 3 + d);
 }

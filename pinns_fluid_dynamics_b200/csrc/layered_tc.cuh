@@ -133,12 +133,15 @@ __global__ void tc_prep_weights(const float* __restrict__ params, int off0, int 
 
 // ---- layer 1 (SIMT): thread = (neuron, 4-point group) -> one 16-byte chunk per channel ---------------------
 template <int D, int ORDER>
-__global__ void __launch_bounds__(256) tc_layer1(const float* __restrict__ params, const float* __restrict__ pts, long long n,
-                                                 long long p_begin, float* __restrict__ act1) {
+__global__ void __launch_bounds__(256) tc_layer1(const float* __restrict__ params, const SegDev* __restrict__ segs,
+                                                 const TileDev* __restrict__ tiles, float* __restrict__ act1) {
   using G = Geo<D, ORDER>;
   constexpr int C = G::C, P = G::P, NR = G::NR;
   const int j = threadIdx.x & (kH - 1), gj = threadIdx.x >> 7;
   const long long tile = blockIdx.x;
+  const SegDev* __restrict__ seg = segs + tiles[tile].seg;
+  const float* __restrict__ pts = seg->pts;
+  const long long n = seg->n, p_begin = tiles[tile].p_begin;
   float zd[D];
 #pragma unroll
   for (int i = 0; i < D; ++i) zd[i] = __ldg(params + i * kH + j);
@@ -148,7 +151,7 @@ __global__ void __launch_bounds__(256) tc_layer1(const float* __restrict__ param
     float a[4][C];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      long long gp = p_begin + tile * P + 4 * g + i;
+      long long gp = p_begin + 4 * g + i;
       if (gp >= n) gp = n - 1;
       float z = b;
 #pragma unroll
@@ -713,8 +716,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad(const float* __restric
 // phase 2  thread = (neuron, half of the 4-point groups): a-bar = Jb . K_out^T, tanh-jet adjoint, z-bar_L stored
 //          in place as whole 16-byte chunks; K_out gradients accumulate in registers (the neuron is fixed).
 template <int D, int O, int ORDER, bool TRAIN>
-__global__ void __launch_bounds__(256) tc_out_layer(const float* __restrict__ params, int off_ko, const SegDev* __restrict__ seg_ptr,
-                                                    long long p_begin, int n_tiles, float* __restrict__ actL,
+__global__ void __launch_bounds__(256) tc_out_layer(const float* __restrict__ params, int off_ko, const SegDev* __restrict__ segs,
+                                                    const TileDev* __restrict__ tiles, int n_tiles, float* __restrict__ actL,
                                                     float* __restrict__ grad, float* __restrict__ sumsq) {
   using G = Geo<D, ORDER>;
   constexpr int C = G::C, P = G::P, NR = G::NR, H = kH, CO = C * O;
@@ -726,16 +729,13 @@ __global__ void __launch_bounds__(256) tc_out_layer(const float* __restrict__ pa
   __shared__ float sJb[P * CO];
   __shared__ float sSq[kMaxTerms];
   __shared__ float sGbo[kMaxOut];
-  const SegDev* __restrict__ seg = seg_ptr;
   const int tid = threadIdx.x;
-  const long long n = seg->n;
   const float* Ko = params + off_ko;
   const float* bo = Ko + H * O;
   for (int i = tid; i < H * 4; i += 256) sKo[i] = (i & 3) < O ? __ldg(Ko + (i >> 2) * O + (i & 3)) : 0.f;
   if (tid < kMaxTerms) sSq[tid] = 0.f;
   if (tid < kMaxOut) sGbo[tid] = 0.f;
   __syncthreads();
-  const int n_terms = seg->n_terms;
   // phase-2 identity
   const int k2 = tid & (H - 1), h2 = tid >> 7;
   float ko2[O], gko[O];
@@ -747,6 +747,9 @@ __global__ void __launch_bounds__(256) tc_out_layer(const float* __restrict__ pa
 
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     float* base = actL + (size_t)tile * NR * H;
+    const SegDev* __restrict__ seg = segs + tiles[tile].seg;
+    const long long n = seg->n, p_begin = tiles[tile].p_begin;
+    const int n_terms = seg->n_terms;
     // ---- phase 1 ----
     if (act1) {
       float J[C][O];
@@ -772,7 +775,7 @@ __global__ void __launch_bounds__(256) tc_out_layer(const float* __restrict__ pa
     }
     __syncthreads();
     if (tid < P) {
-      const long long gp = p_begin + (long long)tile * P + tid;
+      const long long gp = p_begin + tid;
       const bool valid = gp < n;
       float J[C][O], Jb[C][O];
 #pragma unroll
@@ -842,8 +845,13 @@ __global__ void __launch_bounds__(256) tc_out_layer(const float* __restrict__ pa
         for (int o = 0; o < O; ++o) atomicAdd(&sGbo[o], Jb[0][o]);
       }
     }
+    __syncthreads();
+    // this tile's sums of squares go to its own set's slots (tiles of several sets share the launch)
+    if (tid < n_terms && (!TRAIN || seg->terms[tid].train)) {
+      atomicAdd(sumsq + seg->terms[tid].out_index, sSq[tid]);
+      sSq[tid] = 0.f;
+    }
     if constexpr (TRAIN) {
-      __syncthreads();
       // ---- phase 2 ----
       float* io = base + (size_t)(k2 >> 3) * (NR * 8) + (size_t)(k2 & 7) * 4;
       for (int g = h2; g < P / 4; g += 2) {
@@ -888,13 +896,12 @@ __global__ void __launch_bounds__(256) tc_out_layer(const float* __restrict__ pa
     for (int o = 0; o < O; ++o) atomicAdd(grad + off_ko + k2 * O + o, gko[o]);
     if (tid < O) atomicAdd(grad + off_ko + H * O + tid, sGbo[tid]);
   }
-  if (tid < n_terms && (!TRAIN || seg->terms[tid].train)) atomicAdd(sumsq + seg->terms[tid].out_index, sSq[tid]);
 }
 
 // ---- K1 / b1 gradients from z-bar_1 (SIMT): thread = (neuron, 4-point group), block-strided over tiles ------
 template <int D, int ORDER>
-__global__ void __launch_bounds__(256) tc_layer1_grad(const float* __restrict__ zbar1, const float* __restrict__ pts, long long n,
-                                                      long long p_begin, int n_tiles, float* __restrict__ grad) {
+__global__ void __launch_bounds__(256) tc_layer1_grad(const float* __restrict__ zbar1, const SegDev* __restrict__ segs,
+                                                      const TileDev* __restrict__ tiles, int n_tiles, float* __restrict__ grad) {
   using G = Geo<D, ORDER>;
   constexpr int P = G::P, NR = G::NR;
   __shared__ float sG[(1 + D) * kH];
@@ -906,6 +913,9 @@ __global__ void __launch_bounds__(256) tc_layer1_grad(const float* __restrict__ 
   for (int i = 0; i < D; ++i) gk[i] = 0.f;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const float* zt = zbar1 + (size_t)tile * NR * kH + (size_t)(j >> 3) * (NR * 8) + (size_t)(j & 7) * 4;
+    const SegDev* __restrict__ seg = segs + tiles[tile].seg;
+    const float* __restrict__ pts = seg->pts;
+    const long long n = seg->n, p_begin = tiles[tile].p_begin;
     for (int g = gj; g < P / 4; g += 2) {
       const float4 z4 = *reinterpret_cast<const float4*>(zt + (size_t)g * 32);
       const float z0[4] = {z4.x, z4.y, z4.z, z4.w};
@@ -919,7 +929,7 @@ __global__ void __launch_bounds__(256) tc_layer1_grad(const float* __restrict__ 
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          long long gp = p_begin + (long long)tile * P + 4 * g + i;
+          long long gp = p_begin + 4 * g + i;
           if (gp >= n) gp = n - 1;
           v = fmaf(__ldg(pts + gp * D + t), z0[i], v);
         }

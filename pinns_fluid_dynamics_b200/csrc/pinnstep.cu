@@ -46,6 +46,9 @@ struct LaunchTable {
   int total_chunks = 0;
   SegDev* segs_dev = nullptr;
   std::vector<SegDev> segs_host;
+  // layered tensor-core engine: the tiles of every segment of this order, set after set
+  TileDev* tiles_dev = nullptr;
+  std::vector<TileDev> tiles_host;
 };
 
 struct pinn_plan {
@@ -318,9 +321,33 @@ static int tc_set_attrs() {
   return PINN_OK;
 }
 
+static int tc_points_per_tile(int d, int order) {
+  const int C = n_channels(d, order);
+  return C == 6 ? 40 : C == 5 ? 48 : C == 4 ? 56 : C == 3 ? 80 : 240;   // tc::Geo<D, ORDER>::P
+}
+
+// (re)build the tile table of one launch table: tiles never straddle point sets
+static int tc_build_tiles(LaunchTable* lt, int d) {
+  if (lt->tiles_dev) { cudaFree(lt->tiles_dev); lt->tiles_dev = nullptr; }
+  lt->tiles_host.clear();
+  const int P = tc_points_per_tile(d, lt->order);
+  for (int s = 0; s < lt->n_segs; ++s)
+    for (long long b = 0; b < lt->segs_host[s].n; b += P) {
+      TileDev t;
+      t.seg = s; t.pad_ = 0; t.p_begin = b;
+      lt->tiles_host.push_back(t);
+    }
+  if (!lt->tiles_host.empty()) {
+    CUDA_TRY(cudaMalloc(&lt->tiles_dev, lt->tiles_host.size() * sizeof(TileDev)));
+    CUDA_TRY(cudaMemcpy(lt->tiles_dev, lt->tiles_host.data(), lt->tiles_host.size() * sizeof(TileDev), cudaMemcpyHostToDevice));
+  }
+  return PINN_OK;
+}
+
+// one pipeline run over ALL point sets of a derivative order (batches of tiles that fit the workspace)
 template <int D, int O, int ORDER>
-static int tc_run_set(pinn_plan* p, const float* params, float* out, cudaStream_t st, bool train, const SegDev& seg,
-                      const SegDev* seg_dev, int* launches) {
+static int tc_run_order(pinn_plan* p, const float* params, float* out, cudaStream_t st, bool train, const LaunchTable& lt,
+                        int* launches) {
   using G = tc::Geo<D, ORDER>;
   using S = tc::LayerSmem<G::NR>;
   constexpr int H = tc::kH;
@@ -332,12 +359,14 @@ static int tc_run_set(pinn_plan* p, const float* params, float* out, cudaStream_
     attr_done = true;
   }
   const int off_ko = D * H + H + (L - 1) * (H * H + H);
-  for (long long b0 = 0; b0 < seg.n; b0 += p->batch) {
-    const long long nb = (seg.n - b0 < p->batch) ? seg.n - b0 : p->batch;
-    const int tiles = (int)((nb + G::P - 1) / G::P);
+  const long long total_tiles = (long long)lt.tiles_host.size();
+  const long long batch_tiles = p->batch / G::P;
+  for (long long t0 = 0; t0 < total_tiles; t0 += batch_tiles) {
+    const int tiles = (int)(total_tiles - t0 < batch_tiles ? total_tiles - t0 : batch_tiles);
+    const TileDev* td = lt.tiles_dev + t0;
     const int grid = tiles < p->num_sms ? tiles : p->num_sms;
     auto act = [&](int l) { return p->act + (size_t)(l - 1) * p->layer_stride; };   // jets of layer l (1-based)
-    tc::tc_layer1<D, ORDER><<<tiles, 256, 0, st>>>(params, seg.pts, seg.n, b0, act(1));
+    tc::tc_layer1<D, ORDER><<<tiles, 256, 0, st>>>(params, lt.segs_dev, td, act(1));
     for (int l = 2; l <= L; ++l) {
       const float* bias = params + D * H + H + (size_t)(l - 2) * (H * H + H) + H * H;
       const float* img = p->wimg + (size_t)(l - 2) * tc::kLayerImgFloats;
@@ -345,9 +374,9 @@ static int tc_run_set(pinn_plan* p, const float* params, float* out, cudaStream_
     }
     const int grid_out = tiles < 4 * p->num_sms ? tiles : 4 * p->num_sms;
     if (train)
-      tc::tc_out_layer<D, O, ORDER, true><<<grid_out, 256, 0, st>>>(params, off_ko, seg_dev, b0, tiles, act(L), out, out + p->P);
+      tc::tc_out_layer<D, O, ORDER, true><<<grid_out, 256, 0, st>>>(params, off_ko, lt.segs_dev, td, tiles, act(L), out, out + p->P);
     else
-      tc::tc_out_layer<D, O, ORDER, false><<<grid_out, 256, 0, st>>>(params, off_ko, seg_dev, b0, tiles, act(L), out, out + p->P);
+      tc::tc_out_layer<D, O, ORDER, false><<<grid_out, 256, 0, st>>>(params, off_ko, lt.segs_dev, td, tiles, act(L), out, out + p->P);
     *launches += L + 1;
     if (train) {
       const long long n_slabs = (long long)tiles * (G::NR / tc::kWgRows);
@@ -363,7 +392,7 @@ static int tc_run_set(pinn_plan* p, const float* params, float* out, cudaStream_
         *launches += 2;
       }
       const int g1 = tiles < 2 * p->num_sms ? tiles : 2 * p->num_sms;
-      tc::tc_layer1_grad<D, ORDER><<<g1, 256, 0, st>>>(act(1), seg.pts, seg.n, b0, tiles, out);
+      tc::tc_layer1_grad<D, ORDER><<<g1, 256, 0, st>>>(act(1), lt.segs_dev, td, tiles, out);
       ++*launches;
     }
     CUDA_TRY(cudaGetLastError());
@@ -375,15 +404,14 @@ template <int D, int O>
 static int tc_run_t(pinn_plan* p, const float* params, float* out, cudaStream_t st, bool train, int* launches) {
   for (int o = 2; o >= 0; --o) {
     const LaunchTable& lt = train ? p->train[o] : p->eval[o];
-    if (p->timing && lt.n_segs > 0) CUDA_TRY(cudaEventRecord(p->ev0[o], st));
-    for (int s = 0; s < lt.n_segs; ++s) {
-      int rc;
-      if (o == 2) rc = tc_run_set<D, O, 2>(p, params, out, st, train, lt.segs_host[s], lt.segs_dev + s, launches);
-      else if (o == 1) rc = tc_run_set<D, O, 1>(p, params, out, st, train, lt.segs_host[s], lt.segs_dev + s, launches);
-      else rc = tc_run_set<D, O, 0>(p, params, out, st, train, lt.segs_host[s], lt.segs_dev + s, launches);
-      if (rc != PINN_OK) return rc;
-    }
-    if (p->timing && lt.n_segs > 0) {
+    if (lt.n_segs == 0) continue;
+    if (p->timing) CUDA_TRY(cudaEventRecord(p->ev0[o], st));
+    int rc;
+    if (o == 2) rc = tc_run_order<D, O, 2>(p, params, out, st, train, lt, launches);
+    else if (o == 1) rc = tc_run_order<D, O, 1>(p, params, out, st, train, lt, launches);
+    else rc = tc_run_order<D, O, 0>(p, params, out, st, train, lt, launches);
+    if (rc != PINN_OK) return rc;
+    if (p->timing) {
       CUDA_TRY(cudaEventRecord(p->ev1[o], st));
       p->ev_valid[o] = true;
     }
@@ -474,6 +502,10 @@ extern "C" int pinn_plan_create(const pinn_mlp_desc* mlp, const pinn_pointset_de
     p->tc = true;
     p->engine = "layered_tf32x3";
     int rc = tc_alloc(p);
+    for (int o = 0; o < 3 && rc == PINN_OK; ++o) {
+      rc = tc_build_tiles(&p->train[o], mlp->in_dim);
+      if (rc == PINN_OK) rc = tc_build_tiles(&p->eval[o], mlp->in_dim);
+    }
     if (rc != PINN_OK) {
       pinn_plan_destroy(p);
       return rc;
@@ -519,6 +551,8 @@ extern "C" int pinn_plan_destroy(pinn_plan* p) {
   for (int o = 0; o < 3; ++o) {
     if (p->train[o].segs_dev) cudaFree(p->train[o].segs_dev);
     if (p->eval[o].segs_dev) cudaFree(p->eval[o].segs_dev);
+    if (p->train[o].tiles_dev) cudaFree(p->train[o].tiles_dev);
+    if (p->eval[o].tiles_dev) cudaFree(p->eval[o].tiles_dev);
   }
   if (p->ws) cudaFree(p->ws);
   if (p->act) cudaFree(p->act);
@@ -571,6 +605,10 @@ extern "C" int pinn_plan_set_rhs(pinn_plan* p, int32_t set_index, int32_t term_i
   if (p->eval[o].segs_dev) { cudaFree(p->eval[o].segs_dev); p->eval[o].segs_dev = nullptr; }
   int rc = build_table(p, o, true, &p->train[o]);
   if (rc == PINN_OK) rc = build_table(p, o, false, &p->eval[o]);
+  if (rc == PINN_OK && p->tc) {
+    rc = tc_build_tiles(&p->train[o], p->mlp.in_dim);
+    if (rc == PINN_OK) rc = tc_build_tiles(&p->eval[o], p->mlp.in_dim);
+  }
   return rc;
 }
 
@@ -661,6 +699,7 @@ extern "C" int pinn_forward(const pinn_mlp_desc* mlp, const float* params_dev, c
       lt.segs_host.push_back(sd);
       lt.segs_dev = sd_dev;
       tmp.eval[0] = lt;
+      if (use_tc) rc = tc_build_tiles(&tmp.eval[0], mlp->in_dim);
       float* dummy = nullptr;   // no terms: nothing is written through `out`
       if (cudaMalloc(&dummy, sizeof(float) * (size_t)(tmp.P + 1)) != cudaSuccess) rc = fail(PINN_E_ALLOC, "scratch");
       if (rc == PINN_OK) rc = use_tc ? run_tc(&tmp, params_dev, dummy, st, false) : run_layered(&tmp, params_dev, dummy, st, false);
@@ -672,6 +711,8 @@ extern "C" int pinn_forward(const pinn_mlp_desc* mlp, const float* params_dev, c
     if (tmp.wt) cudaFree(tmp.wt);
     if (tmp.wimg) cudaFree(tmp.wimg);
     tmp.act = tmp.wt = tmp.wimg = nullptr;
+    if (tmp.eval[0].tiles_dev) cudaFree(tmp.eval[0].tiles_dev);
+    tmp.eval[0].tiles_dev = nullptr;
     tmp.eval[0].segs_dev = nullptr;
     return rc;
   }

@@ -431,11 +431,23 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
     const long long i0 = valid0 ? p0 : n - 1, i1 = valid1 ? p0 + 1 : n - 1;
     float x0[D], x1[D];
     {
+      // a lane's two consecutive points are 2*D contiguous floats: one 16-byte (D = 2) or three 8-byte (D = 3)
+      // read-only loads, the 8 row-lanes of a chunk reading 128 / 192 contiguous bytes
       const float* pts = seg->pts;
+      const bool vec = valid1 && ((reinterpret_cast<uintptr_t>(pts) & 15u) == 0);
+      if (vec && D == 2) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(pts + p0 * 2));
+        x0[0] = v.x; x0[1] = v.y; x1[0] = v.z; x1[D - 1] = v.w;
+      } else if (vec && D == 3) {
+        const float2* q = reinterpret_cast<const float2*>(pts + p0 * 3);
+        const float2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+        x0[0] = a.x; x0[1] = a.y; x0[D - 1] = b.x; x1[0] = b.y; x1[1] = c.x; x1[D - 1] = c.y;
+      } else {
 #pragma unroll
-      for (int i = 0; i < D; ++i) {
-        x0[i] = __ldg(pts + i0 * D + i);
-        x1[i] = __ldg(pts + i1 * D + i);
+        for (int i = 0; i < D; ++i) {
+          x0[i] = __ldg(pts + i0 * D + i);
+          x1[i] = __ldg(pts + i1 * D + i);
+        }
       }
     }
 

@@ -88,6 +88,9 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, uint32_t byte
 #ifndef PINN_TC_L2PF
 #define PINN_TC_L2PF 4
 #endif
+#ifndef PINN_TC_PFWARPS
+#define PINN_TC_PFWARPS 0
+#endif
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // round-to-nearest split: hi and lo are both exact TF32 values, so the tensor core's own truncation of its
 // operands loses nothing and the residual x - hi - lo (<= 2^-22 |x|) has no sign bias.  (A truncating split
@@ -263,9 +266,11 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer(const float* __rest
   uint64_t* tempty = tfull + 2;                                      // [2]
   uint64_t* wbar = tempty + 2;
   uint32_t* tslot = reinterpret_cast<uint32_t*>(wbar + 1);
+  volatile int* prog = reinterpret_cast<volatile int*>(tslot + 1);   // tile index the producers are working on
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
+    *prog = 0;
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], kProdWarps); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], kEpiWarps); }
     mbar_init(wbar, 1);
@@ -326,7 +331,10 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer(const float* __rest
         }
       }
     };
+    int t_cons = 0;
     auto consume = [&](const float4 (&v)[8]) {
+      if (tid == 0 && t_cons % NKC == 0) *prog = t_cons / NKC;
+      ++t_cons;
       { TCP_T0(); mbar_wait(&empty[stage], phase ^ 1u); if (warp == 0) TCP_ADD(0); }
       uint8_t* dst = sStage + stage * S::STAGE;
 #pragma unroll
@@ -368,6 +376,20 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer(const float* __rest
   } else if (warp >= kMmaWarp) {
     // ===== MMA issuer =====
     reg_dec<24>();
+#if PINN_TC_PFWARPS
+    if (warp == kMmaWarp + 1 || (MODE == 1 && warp == kMmaWarp + 2)) {
+      // ===== experiment (off): L2 prefetch warps one tile ahead of the producers, one 128-byte line per lane and
+      // instruction.  Measured SLOWER: forward 264 -> 275 us, backward 354 -> 448 us per batch -- the layer kernels are
+      // limited by the HBM system itself, not by the latency of their own loads =====
+      const float* base = warp == kMmaWarp + 1 ? act_in : act_io;
+      const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+      for (int it = 1; it < my_tiles; ++it) {
+        while (*prog + 1 < it) __nanosleep(200);
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(base + (size_t)((int)blockIdx.x + it * (int)gridDim.x) * NR * kH);
+        for (int ln = lane; ln < NR * kH * 4 / 128; ln += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (size_t)ln * 128));
+      }
+    }
+#endif
     if (warp == kMmaWarp && lane == 0) {
       mbar_wait(wbar, 0);
       const uint32_t idesc = umma::idesc_tf32(kH, NR);

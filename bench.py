@@ -167,7 +167,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    per_gpu = args.pde_per_gpu or problems.BASELINE_CONFIGS[args.config]["PDE"]
+    per_gpu = args.pde_per_gpu or problems.BASELINE_CONFIGS[args.config].get("PDE", 200)   # Poisson: 200 (poisson_misto.py:49)
     data = problems.build_baseline_config(args.config, seed=1, PDE=per_gpu * world)
     model = ns.TanhMLP(data.dim, data.hidden, data.out_dim, device=dev, seed=3)
     # benchmark the full Navier-Stokes residual: in-tape mass term everywhere

@@ -321,10 +321,14 @@ static int tc_set_attrs() {
   return PINN_OK;
 }
 
-static int tc_points_per_tile(int d, int order) {
+static constexpr int tc_points_per_tile(int d, int order) {
   const int C = n_channels(d, order);
   return C == 6 ? 40 : C == 5 ? 48 : C == 4 ? 56 : C == 3 ? 80 : 240;   // tc::Geo<D, ORDER>::P
 }
+static_assert(tc_points_per_tile(3, 2) == tc::Geo<3, 2>::P && tc_points_per_tile(3, 1) == tc::Geo<3, 1>::P &&
+              tc_points_per_tile(3, 0) == tc::Geo<3, 0>::P && tc_points_per_tile(2, 2) == tc::Geo<2, 2>::P &&
+              tc_points_per_tile(2, 1) == tc::Geo<2, 1>::P && tc_points_per_tile(2, 0) == tc::Geo<2, 0>::P,
+              "host tile table and kernel tile geometry disagree");
 
 // (re)build the tile table of one launch table: tiles never straddle point sets
 static int tc_build_tiles(LaunchTable* lt, int d) {

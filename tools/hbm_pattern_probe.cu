@@ -23,7 +23,16 @@ __global__ void __launch_bounds__(384) pattern(const float* __restrict__ in, flo
     if (tid < 128) {
       if (mode >= 6 && tid == 0 && tile + gridDim.x < n_tiles)
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(in + (size_t)(tile + gridDim.x) * NR * H), "r"(NR * H * 4) : "memory");
-      if (mode != 3) {
+      if (mode == 8) {   // same bytes, fully coalesced: lane l of a warp reads chunk l of a 512-byte run
+        for (int kc = 0; kc < 8; ++kc) {
+          const float4* src = reinterpret_cast<const float4*>(in + (size_t)tile * NR * H + (size_t)kc * (NR * 16));
+          float4 v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { const int x = tid + 128 * i; if (x < NR * 4) v[i] = __ldg(src + x); else v[i] = make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc += v[i].x + v[i].w;
+        }
+      } else if (mode != 3) {
         const int kb = (tid >> 3) & 3, rb0 = (tid & 7) + 8 * (tid >> 5);
         for (int kc = 0; kc < 8; ++kc) {
           const unsigned char* src = reinterpret_cast<const unsigned char*>(in + (size_t)tile * NR * H) + (size_t)(kc * 2 + (kb >> 1)) * (NR * 32) + (kb & 1) * 64;
@@ -44,7 +53,7 @@ __global__ void __launch_bounds__(384) pattern(const float* __restrict__ in, flo
       if (mode == 1) asm volatile("bar.arrive 1, 384;");
     } else {
       if (mode == 1) asm volatile("bar.sync 1, 384;");
-      if (mode != 2 && mode != 4 && mode != 6) {
+      if (mode != 2 && mode != 4 && mode != 6 && mode != 8) {
         const int t = tid - 128, j = t & 127, half = t >> 7;
         float* io = out + (size_t)tile * NR * H + (size_t)(j >> 3) * (NR * 8) + (size_t)half * (5 * 32) + (size_t)(j & 7) * 4;
 #pragma unroll
@@ -64,9 +73,9 @@ int main() {
   CK(cudaMalloc(&in, bytes)); CK(cudaMalloc(&out, bytes)); CK(cudaMalloc(&sink, 4));
   CK(cudaMemset(in, 0, bytes));
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-  const char* names[8] = {"read + write, free running", "read then write per tile (burst)", "read only", "write only",
-                          "read only + per-lane L2 prefetch", "read + write + per-lane L2 prefetch", "read only + bulk L2 prefetch", "read + write + bulk L2 prefetch"};
-  for (int mode = 0; mode < 8; ++mode) {
+  const char* names[9] = {"read + write, free running", "read then write per tile (burst)", "read only", "write only",
+                          "read only + per-lane L2 prefetch", "read + write + per-lane L2 prefetch", "read only + bulk L2 prefetch", "read + write + bulk L2 prefetch", "read only, fully coalesced LDG.128"};
+  for (int mode = 0; mode < 9; ++mode) {
     pattern<<<148, 384>>>(in, out, n_tiles, mode, sink);
     CK(cudaDeviceSynchronize());
     CK(cudaEventRecord(e0));

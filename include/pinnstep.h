@@ -156,6 +156,11 @@ int pinn_allreduce_sum(void* comm, float* buf_dev, int64_t count, void* stream);
  * (tf.keras.optimizers.Adam(learning_rate=1e-2), cavity_steady.py:246). step is 1-based. */
 int pinn_adam_step(float* params_dev, const float* grad_dev, float* m_dev, float* v_dev, int64_t count,
                    float lr, float beta1, float beta2, float eps, int64_t step, void* stream);
+/* Same update with the 1-based step number kept in device memory (*step_dev holds the number of steps already
+ * taken and is incremented by the call): no host-side value changes between steps, so a whole training step
+ * (pinn_loss_and_grad + this) can be captured once in a CUDA graph and replayed. */
+int pinn_adam_step_dev(float* params_dev, const float* grad_dev, float* m_dev, float* v_dev, int64_t count,
+                       float lr, float beta1, float beta2, float eps, int64_t* step_dev, void* stream);
 
 #ifdef __cplusplus
 }

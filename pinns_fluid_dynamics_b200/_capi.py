@@ -16,7 +16,7 @@ EXPORTED_SYMBOLS = (
     "pinn_version", "pinn_last_error", "pinn_plan_create", "pinn_plan_destroy", "pinn_plan_param_count",
     "pinn_plan_term_count", "pinn_plan_workspace_bytes", "pinn_plan_engine", "pinn_plan_last_launch_count",
     "pinn_plan_set_rhs", "pinn_plan_enable_timing", "pinn_plan_kernel_time_ms", "pinn_loss_and_grad", "pinn_loss", "pinn_forward", "pinn_nccl_unique_id",
-    "pinn_comm_create", "pinn_comm_destroy", "pinn_allreduce_sum", "pinn_adam_step",
+    "pinn_comm_create", "pinn_comm_destroy", "pinn_allreduce_sum", "pinn_adam_step", "pinn_adam_step_dev",
 )
 
 
@@ -89,6 +89,7 @@ def load(path: Optional[str] = None) -> C.CDLL:
     lib.pinn_comm_destroy.argtypes = [vp]
     lib.pinn_allreduce_sum.argtypes = [vp, vp, i64, vp]
     lib.pinn_adam_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i64, vp]
+    lib.pinn_adam_step_dev.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, vp, vp]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("pinn_version", "pinn_last_error", "pinn_plan_param_count", "pinn_plan_term_count",

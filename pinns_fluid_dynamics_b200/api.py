@@ -172,6 +172,7 @@ class OptimizationProblem:
         self.compiled: CompiledProblem = compile_problem([tuple(v.shape) for v in self.variables],
                                                          self.losses, self.losses_test, self.rank, self.world)
         self.plan = (engine_factory or CudaPlan)(self.compiled)
+        self._graph, self._graph_opt, self._graph_sumsq, self._eager_steps = None, None, None, 0
         self.iteration = 0
         self.history = {
             "log": {"iter": [], "round": [], "iter_round": [], "loss_global": []},
@@ -210,9 +211,38 @@ class OptimizationProblem:
 
     def training_step(self, optimizer):
         """One full training step, asynchronous: loss step (+ all-reduce) + optimiser update.
-        Returns the device vector of per-term sums of squares (table order)."""
+        Returns the device vector of per-term sums of squares (table order).
+
+        On one GPU the step is the same launch sequence every time (fixed point sets, device-side Adam step
+        number), so after three eager steps it is captured once in a CUDA graph and replayed: the small configs
+        (Poiseuille 10 k, Colliding 100 k points) are launch-bound otherwise.  ``PINN_CUDA_GRAPH=0`` disables it."""
+        if self._graph is not None and optimizer is self._graph_opt and not self.plan.timing_enabled:
+            self._graph.replay()
+            optimizer.t += 1
+            return self._graph_sumsq
+        if self._graph_eligible(optimizer):
+            self._eager_steps += 1
+            if self._eager_steps > 3:
+                return self._capture_step(optimizer)
         grad, sumsq = self.loss_and_grad_device()
         optimizer.apply(self.flat, grad)
+        return sumsq
+
+    def _graph_eligible(self, optimizer) -> bool:
+        return (self.flat.is_cuda and self.world == 1 and isinstance(optimizer, Adam) and isinstance(self.plan, CudaPlan)
+                and not self.plan.timing_enabled and os.environ.get("PINN_CUDA_GRAPH", "1") != "0"
+                and (self._graph_opt is None or self._graph_opt is optimizer))
+
+    def _capture_step(self, optimizer):
+        torch.cuda.synchronize(self.flat.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            grad, sumsq = self.loss_and_grad_device()
+            optimizer.apply(self.flat, grad)
+        optimizer.t -= 1                 # capture launches nothing: the step is taken by the replay below
+        self._graph, self._graph_opt, self._graph_sumsq = g, optimizer, sumsq
+        g.replay()
+        optimizer.t += 1
         return sumsq
 
     def evaluate(self):
@@ -282,14 +312,17 @@ class Adam:
         import ctypes as C
         if self.m is None:
             self.m, self.v = torch.zeros_like(flat), torch.zeros_like(flat)
+            if flat.is_cuda:      # step number on the device: the update launches with the same arguments every step
+                self.step_dev = torch.full((1,), self.t, dtype=torch.int64, device=flat.device)
         self.t += 1
         if flat.is_cuda:
             lib = _capi.load()
             stream = C.c_void_p(torch.cuda.current_stream(flat.device).cuda_stream)
-            _capi.check(lib.pinn_adam_step(C.c_void_p(flat.data_ptr()), C.c_void_p(grad.data_ptr()),
-                                           C.c_void_p(self.m.data_ptr()), C.c_void_p(self.v.data_ptr()),
-                                           flat.numel(), self.lr, self.b1, self.b2, self.eps, self.t, stream),
-                        "pinn_adam_step")
+            _capi.check(lib.pinn_adam_step_dev(C.c_void_p(flat.data_ptr()), C.c_void_p(grad.data_ptr()),
+                                               C.c_void_p(self.m.data_ptr()), C.c_void_p(self.v.data_ptr()),
+                                               flat.numel(), self.lr, self.b1, self.b2, self.eps,
+                                               C.c_void_p(self.step_dev.data_ptr()), stream),
+                        "pinn_adam_step_dev")
         else:  # host tensors: only reached with an injected (test) engine
             self.m.mul_(self.b1).add_(grad, alpha=1 - self.b1)
             self.v.mul_(self.b2).addcmul_(grad, grad, value=1 - self.b2)
@@ -306,8 +339,7 @@ def minimize(pb: OptimizationProblem, backend: str, optimizer, num_epochs: int) 
         pb.begin_round(f"keras_{getattr(optimizer, 'name', type(optimizer).__name__)}")
         pb.log_state()
         for _ in range(num_epochs):
-            grad, _ = pb.loss_and_grad_device()
-            optimizer.apply(pb.flat, grad)
+            pb.training_step(optimizer)
             pb.step_done()
     elif backend == "scipy":
         import scipy.optimize

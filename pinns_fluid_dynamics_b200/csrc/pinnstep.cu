@@ -847,3 +847,32 @@ extern "C" int pinn_adam_step(float* params_dev, const float* grad_dev, float* m
   CUDA_TRY(cudaGetLastError());
   return PINN_OK;
 }
+
+// graph-capturable variant: the step number lives on the device
+__global__ void adam_dev_kernel(float* __restrict__ theta, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
+                                const int64_t* __restrict__ step) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double t = (double)(*step + 1);
+  const float step_size = (float)((double)lr * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t)));
+  const float gi = g[i];
+  const float mi = fmaf(b1, m[i], (1.f - b1) * gi);
+  const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+  m[i] = mi;
+  v[i] = vi;
+  theta[i] -= step_size * mi / (sqrtf(vi) + eps);
+}
+__global__ void bump_step_kernel(int64_t* step) { *step += 1; }
+
+extern "C" int pinn_adam_step_dev(float* params_dev, const float* grad_dev, float* m_dev, float* v_dev, int64_t count,
+                                  float lr, float beta1, float beta2, float eps, int64_t* step_dev, void* stream) {
+  if (!params_dev || !grad_dev || !m_dev || !v_dev || !step_dev || count < 0) return fail(PINN_E_INVALID, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (count > 0)
+    adam_dev_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(params_dev, grad_dev, m_dev, v_dev, count, lr, beta1, beta2,
+                                                                     eps, step_dev);
+  bump_step_kernel<<<1, 1, 0, st>>>(step_dev);
+  CUDA_TRY(cudaGetLastError());
+  return PINN_OK;
+}

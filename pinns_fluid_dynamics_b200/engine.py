@@ -272,8 +272,11 @@ class CudaPlan:
             self.pin_host_inputs()
         self._arena.copy_(self._pinned, non_blocking=True)
 
+    timing_enabled = False
+
     def enable_timing(self, on: bool = True) -> None:
         _capi.check(self.lib.pinn_plan_enable_timing(self.handle, 1 if on else 0), "pinn_plan_enable_timing")
+        self.timing_enabled = bool(on)
 
     def kernel_time_ms(self, deriv_order: int = 2) -> float:
         ms = C.c_float()

@@ -364,3 +364,19 @@ def test_device_bfgs_round_follows_scipy_round(monkeypatch):
     t_ref, x_ref = run("scipy")
     assert _rel(t_dev, t_ref) < 5e-3
     assert np.linalg.norm(x_dev - x_ref) / np.linalg.norm(x_ref) < 1e-3
+
+
+def test_graph_replayed_training_steps_equal_eager_steps(monkeypatch):
+    """the CUDA-graph replay of the Adam training step (single GPU) takes exactly the eager steps"""
+    def run(flag):
+        monkeypatch.setenv("PINN_CUDA_GRAPH", flag)
+        data, var, model, pb = _setup("colliding_flow", SMALL["colliding_flow"])
+        opt = ns.optimizers.Adam(learning_rate=1e-2)
+        for _ in range(12):
+            s = pb.training_step(opt)
+        return pb.flat.clone(), s.clone(), pb._graph is not None, opt.t
+    x_g, s_g, used_g, t_g = run("1")
+    x_e, s_e, used_e, t_e = run("0")
+    assert used_g and not used_e and t_g == t_e == 12
+    assert torch.equal(x_g, x_e)
+    assert torch.equal(s_g, s_e)

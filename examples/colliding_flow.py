@@ -60,6 +60,7 @@ total, train_vals, test_vals = pb.evaluate_all()
 recap = {"engine": pb.plan.engine, "adam_seconds": t1 - t0, "bfgs_seconds": t2 - t1, "bfgs_iterations": pb.history["log"]["iter"][-1] - 100,
          "loss_global": total, "losses": {l.name: v for l, v in zip(pb.losses, train_vals)},
          "losses_test": {l.name: v for l, v in zip(pb.losses_test, test_vals)}}
-with open(os.path.join(args.out, "Test_Options.txt"), "w") as fh:
-    fh.write(json.dumps({"epochs": epochs, "n_pts": opt.n_pts, **recap}, indent=2))
+options.write_recap(os.path.join(args.out, "Test_Options.txt"), "Colliding_Flow", opt)     # colliding_flow.py:362-379
+with open(os.path.join(args.out, "Run_Summary.json"), "w") as fh:
+    json.dump({"epochs": epochs, "n_pts": opt.n_pts, **recap}, fh, indent=2)
 print(json.dumps(recap, indent=1))

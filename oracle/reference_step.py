@@ -274,6 +274,95 @@ def poiseuille_flow(data, variables, in_tape_divergence: bool = False) -> Optimi
 
 
 # --------------------------------------------------------------------------------------------
+# Coronary_Flow  (Examples/Coronary_Flow/coronary_flow_steady.py)
+# --------------------------------------------------------------------------------------------
+
+def coronary_flow(data, variables, in_tape_neumann: bool = False) -> OptimizationProblem:
+    model = KerasMLP(variables)
+    norm_vel, norm_pre, ni = data.norm_vel, data.norm_pre, data.consts["ni"]
+    x_pde = _t(data.x_pde)
+    bnd_pts = {k: _t(v) for k, v in data.bnd_pts.items()}
+    bnd_val = [{k: _t(v) for k, v in d.items()} for d in data.bnd_val]
+    sol_noise = [_t(v) for v in data.sol_noise]
+    sol_test = [_t(v) for v in data.sol_test]
+    x_vel, x_test = _t(data.x_vel), _t(data.x_test)
+    gradient = gradient_scalar
+
+    def PDE_MASS():  # coronary_flow_steady.py:163-170
+        x = _watch(x_pde)
+        with GradientTape(persistent=True) as tape:
+            tape.watch(x)
+            u_vect = model(x)[:, 0:2]
+            du_x = gradient(tape, u_vect[:, 0], x)[:, 0]
+            dv_y = gradient(tape, u_vect[:, 1], x)[:, 1]
+        return du_x + dv_y
+
+    def PDE_MOM(k):  # :172-192
+        x = _watch(x_pde)
+        with GradientTape(persistent=True) as tape:
+            tape.watch(x)
+            u_vect = model(x)
+            p = u_vect[:, 2] * norm_pre
+            u_eq = u_vect[:, k] * norm_vel
+            dp = gradient(tape, p, x)[:, k]
+            du_x = gradient(tape, u_eq, x)[:, 0]
+            du_y = gradient(tape, u_eq, x)[:, 1]
+            du_xx = gradient(tape, du_x, x)[:, 0]
+            du_yy = gradient(tape, du_y, x)[:, 1]
+            conv1 = torch.mul(norm_vel * u_vect[:, 0], du_x)
+            conv2 = torch.mul(norm_vel * u_vect[:, 1], du_y)
+            unnormed_lhs = - ni * (du_xx + du_yy) + dp + conv1 + conv2
+            norm_const = 1 / max(norm_pre, norm_vel)
+        return unnormed_lhs * norm_const
+
+    def dir_loss(points, component, rhs):  # :196-199
+        uk = model(points)[:, component]
+        return uk - rhs
+
+    def neu_loss(edge, k, rhs):  # :201-215
+        x = _watch(bnd_pts[edge])
+        n = torch.tensor([2.0, 1.0] if edge == 'OUT1' else [1.0, 0.0], dtype=DTYPE).reshape(2, 1)
+        with GradientTape(persistent=True) as tape:
+            tape.watch(x)
+            if in_tape_neumann:      # the intended traction condition
+                u_vect = model(x)
+        if not in_tape_neumann:
+            # the script calls the model AFTER the tape closed (:209): TF records nothing, so the gradient below
+            # is unconnected.  torch has no tape, so the same is stated by cutting x out of the graph.
+            u_vect = model(x.detach())
+        u_eq = u_vect[:, k] * norm_vel
+        p_eq = u_vect[:, 2] * norm_pre
+        grad = gradient(tape, u_eq, x)[:, 0:2]
+        # the script subtracts an [N] vector from the [N,1] product (:215), which broadcasts to [N,N]; with the zero
+        # gradient every row of that matrix is the same vector, so its mean square is the vector's.
+        return ni * torch.matmul(grad, n).reshape(-1) - p_eq * n[k] - rhs
+
+    BC_D = lambda edge, component: dir_loss(bnd_pts[edge], component, bnd_val[component][edge])
+    BC_N = lambda edge, component: neu_loss(edge, component, bnd_val[component][edge])
+    fit_velocity = lambda component: dir_loss(x_vel, component, sol_noise[component])
+    exact_value = lambda component: dir_loss(x_test, component, sol_test[component])
+
+    LMS = LossMeanSquares
+    o = data.options
+    losses: List[LossMeanSquares] = []
+    if o.use_collloss:
+        losses += [LMS('PDE_MASS', lambda: PDE_MASS(), weight=1e2),
+                   LMS('PDE_MOMU', lambda: PDE_MOM(0), weight=1e1),
+                   LMS('PDE_MOMV', lambda: PDE_MOM(1), weight=1e1)]
+    if o.use_boundary:
+        losses += [LMS('BCD_u_NS', lambda: BC_D("NOSL", 0)), LMS('BCD_v_NS', lambda: BC_D("NOSL", 1)),
+                   LMS('BCD_u_IN', lambda: BC_D("INF", 0)), LMS('BCD_v_IN', lambda: BC_D("INF", 1)),
+                   LMS('BCN_u_OUT1', lambda: BC_N("OUT1", 0), weight=1e-3),
+                   LMS('BCN_v_OUT1', lambda: BC_N("OUT1", 1), weight=1e-3),
+                   LMS('BCN_u_OUT2', lambda: BC_N("OUT2", 0), weight=1e-3),
+                   LMS('BCN_v_OUT2', lambda: BC_N("OUT2", 1), weight=1e-3)]
+    losses += [LMS('Fit_u', lambda: fit_velocity(0)), LMS('Fit_v', lambda: fit_velocity(1))]   # Q3; Fit_p commented out
+    loss_test = [LMS('u_test', lambda: exact_value(0)), LMS('v_test', lambda: exact_value(1)),
+                 LMS('p_test', lambda: exact_value(2))]
+    return OptimizationProblem(model.variables, losses, loss_test)
+
+
+# --------------------------------------------------------------------------------------------
 # Poisson  (Examples/Poisson_Problem/poisson.py, poisson_misto.py)
 # --------------------------------------------------------------------------------------------
 
@@ -324,6 +413,7 @@ BUILDERS = {
     "poiseuille_flow": poiseuille_flow,
     "poisson": poisson,
     "poisson_misto": poisson,
+    "coronary_flow": coronary_flow,
 }
 
 

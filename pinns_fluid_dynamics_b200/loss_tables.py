@@ -1,4 +1,4 @@
-"""The loss tables of the five in-scope example scripts, written against the facade.
+"""The loss tables of the in-scope example scripts (the five BASELINE configs and Coronary_Flow), written against the facade.
 
 Each function is the "Loss Building" + "Model's Setup" section of one script with the closures
 replaced by their declarative forms; names, weights and order are the script's.  ``faithful=True``
@@ -132,6 +132,32 @@ def poiseuille_flow(data: ProblemData, faithful: bool = True):
     return losses, test
 
 
+def coronary_flow(data: ProblemData, faithful: bool = True):
+    """coronary_flow_steady.py:159-246"""
+    s = _common_sets(data)
+    nv, npr, o, ni = data.norm_vel, data.norm_pre, data.options, data.consts["ni"]
+    mom = lambda k: R.momentum(s["PDE"], k, nv, npr, conv_scale=nv, visc_xx=-ni, visc_yy=-ni)
+    normal = {"OUT1": (2.0, 1.0), "OUT2": (1.0, 0.0)}     # :199-204
+    bcn = lambda e, k: R.outflow_stress(s[e], k, normal[e], data.bnd_val[k][e], nv, npr, ni, in_tape=not faithful)
+    losses: List[LMS] = []
+    if o.use_collloss:
+        losses += [LMS("PDE_MASS", lambda: R.mass(s["PDE"]), weight=1e2),
+                   LMS("PDE_MOMU", lambda: mom(0), weight=1e1),
+                   LMS("PDE_MOMV", lambda: mom(1), weight=1e1)]
+    if o.use_boundary:
+        losses += [LMS("BCD_u_NS", lambda: R.dirichlet(s["NOSL"], 0, data.bnd_val[0]["NOSL"]), weight=1e0),
+                   LMS("BCD_v_NS", lambda: R.dirichlet(s["NOSL"], 1, data.bnd_val[1]["NOSL"]), weight=1e0),
+                   LMS("BCD_u_IN", lambda: R.dirichlet(s["INF"], 0, data.bnd_val[0]["INF"]), weight=1e0),
+                   LMS("BCD_v_IN", lambda: R.dirichlet(s["INF"], 1, data.bnd_val[1]["INF"]), weight=1e0),
+                   LMS("BCN_u_OUT1", lambda: bcn("OUT1", 0), weight=1e-3),
+                   LMS("BCN_v_OUT1", lambda: bcn("OUT1", 1), weight=1e-3),
+                   LMS("BCN_u_OUT2", lambda: bcn("OUT2", 0), weight=1e-3),
+                   LMS("BCN_v_OUT2", lambda: bcn("OUT2", 1), weight=1e-3)]
+    fit, test = _fit_and_test(data, s, with_fit_p=False)    # Fit_p commented out (:240)
+    losses += fit if faithful else (fit if o.fit_velocity else [])
+    return losses, test
+
+
 def poisson(data: ProblemData, faithful: bool = True):
     """poisson.py:58-69 / poisson_misto.py:62-88"""
     pde = PointSet(data.x_pde, "PDE")
@@ -154,6 +180,7 @@ TABLES = {
     "cavity_unsteady": cavity_unsteady,
     "colliding_flow": colliding_flow,
     "poiseuille_flow": poiseuille_flow,
+    "coronary_flow": coronary_flow,
     "poisson": poisson,
     "poisson_misto": poisson,
 }

@@ -84,3 +84,28 @@ def write_simulation_options(path: str, opt: SimulationOptions) -> None:
     ]
     with open(path, "w") as fh:
         fh.write("\n".join(rows))
+
+
+def recap_lines(problem_name: str, opt: SimulationOptions, fit_velocity: bool = True, fit_pressure: bool = True,
+                with_initial_conditions: bool = True):
+    """The "Final Recap" rows of the scripts (cavity_steady.py:366-375).  ``fit_velocity`` / ``fit_pressure`` default to
+    True because the scripts' booleans are shadowed by the lambdas of the same name (:198-199, quirk Q3), so the
+    reference always prints the requested counts; coronary_flow_steady.py has no initial-condition row."""
+    rows = ["Problem Name    -> {}".format(problem_name),
+            "Training Epochs -> {} epochs".format(opt.epochs),
+            "Pyhsical PDE Losses  -> {} points".format(opt.n_pts["PDE"]),
+            "Boundary Conditions  -> {} points".format(opt.n_pts["BC"])]
+    if with_initial_conditions:
+        rows.append("Initial  Conditions  -> {} points".format(opt.n_pts["IC"]))
+    rows += ["Fitting Velocity  -> {} points".format(opt.n_pts["Vel"] if fit_velocity else 0),
+             "Fitting Pressure  -> {} points".format(opt.n_pts["Pres"] if fit_pressure else 0),
+             "Noise on Boundary -> {} times a gaussian N(0,1)".format(opt.noise_factor_bnd),
+             "Noise on Domain   -> {} times a gaussian N(0,1)".format(opt.noise_factor_fit)]
+    return rows
+
+
+def write_recap(path: str, problem_name: str, opt: SimulationOptions, **kw) -> None:
+    """``Test_Options.txt`` (cavity_steady.py:377-383): one row per line, each newline-terminated."""
+    with open(path, "w") as fh:
+        for row in recap_lines(problem_name, opt, **kw):
+            fh.write(row + "\n")

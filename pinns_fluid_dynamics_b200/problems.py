@@ -222,6 +222,45 @@ def load_fem_fields(path: str):
     return vel[:, 0], vel[:, 1], pre - np.mean(pre)
 
 
+def read_gmsh_nodes(path: str) -> np.ndarray:
+    """Node coordinates ``[n, 3]`` (ordered by node tag) of an ASCII gmsh 4.x mesh -- the ``$Nodes`` section of
+    Examples/Coronary_Flow/coroParam.msh.  dolfin keeps this order: the arrays of sol_pinn.h5
+    (coronary_flow_steady.py:297-301, written at ``Mesh/0/mesh/geometry``) vanish on the no-slip nodes found here."""
+    with open(path) as fh:
+        lines = fh.read().split("\n")
+    if not lines[1].startswith("4."):
+        raise ValueError(f"{path}: gmsh format {lines[1]!r} is not 4.x ASCII")
+    i = lines.index("$Nodes") + 1
+    n_blocks, n_nodes = (int(t) for t in lines[i].split()[:2])
+    xyz = np.zeros((n_nodes, 3))
+    i += 1
+    for _ in range(n_blocks):
+        n = int(lines[i].split()[3])
+        tags = [int(t) for t in lines[i + 1:i + 1 + n]]
+        for k, tag in enumerate(tags):
+            xyz[tag - 1] = [float(c) for c in lines[i + 1 + n + k].split()]
+        i += 1 + 2 * n
+    return xyz
+
+
+def load_coronary_geometry(source) -> Dict[str, np.ndarray]:
+    """``source``: a dict, an ``.npz`` (tests/golden/coronary_geometry.npz layout: nodes, bpoints_xy, bpoints_label,
+    u, v, p) or a tuple ``(fem_h5, bpoints_npy)`` naming the DataGeneration outputs the script reads
+    (coronary_flow_steady.py:92-117,134: ``Mesh/0/mesh/geometry``, ``VisualisationVector/0,1`` and the
+    ``[x, y, 0, label]`` rows of bpoints.npy)."""
+    if isinstance(source, dict):
+        return source
+    if isinstance(source, (tuple, list)):
+        from .h5lite import H5File
+        f = H5File(source[0])
+        vel, pre = f["VisualisationVector/0"], f["VisualisationVector/1"].reshape(-1)
+        b = np.load(source[1])
+        return {"nodes": f["Mesh/0/mesh/geometry"][:, :2], "bpoints_xy": b[:, :2], "bpoints_label": b[:, 3].astype(np.int8),
+                "u": vel[:, 0], "v": vel[:, 1], "p": pre}
+    with np.load(source) as z:
+        return {k: z[k] for k in z.files}
+
+
 # --------------------------------------------------------------------------------------------
 # the test cases
 # --------------------------------------------------------------------------------------------
@@ -322,6 +361,52 @@ def poiseuille_flow(options: Optional[SimulationOptions] = None, seed: int = 1, 
     return _round_all(d)
 
 
+CORONARY_EDGES = ("NOSL", "INF", "OUT1", "OUT2")   # bpoints.npy labels 0..3 (DataGeneration/coronary.py:64)
+
+
+def coronary_flow(geometry, options: Optional[SimulationOptions] = None, seed: int = 1, norm_vel: Optional[float] = None,
+                  norm_pre: Optional[float] = None, **counts) -> ProblemData:
+    """Examples/Coronary_Flow/coronary_flow_steady.py:60-150: collocation / fit / test points are a permutation split of
+    the mesh nodes, boundary points come labelled from ``bpoints.npy`` (all of them are used; the BC count of the
+    options file only switches the boundary terms on), the inlet carries the parabolic profile u_inf / v_inf.
+    ``norm_vel`` / ``norm_pre`` override the spreads of the supplied fields (tests replay Test_Case_#123 with the FEM
+    spreads recovered from sol_pinn.h5 = trained model x norm)."""
+    g = load_coronary_geometry(geometry)
+    o = _opts(options, **counts)
+    rng = np.random.default_rng(seed)
+    d = ProblemData("coronary_flow", 2, [32, 32, 32], 3, o)
+    H, U, x0, y0 = np.sqrt(0.4 ** 2 + 0.1 ** 2), 20.0, -1.4, -0.8
+    mu, rho = 1e-2, 1.06e3
+    ni = 1e4 * mu / rho
+    cos_t, sin_t = np.cos(np.arctan(1 / 4)), np.sin(np.arctan(1 / 4))
+    r_in = lambda x: np.sqrt((x[:, 0] - x0) ** 2 + (x[:, 1] - y0) ** 2) / H
+    u_inf = lambda x: U * cos_t * r_in(x) * (1 - r_in(x))
+    v_inf = lambda x: U * sin_t * r_in(x) * (1 - r_in(x))
+    grid = np.asarray(g["nodes"], dtype=np.float64)[:, :2]
+    split = {k: o.n_pts[k] for k in ("PDE", "Vel", "Pres", "Test")}      # key_subset (:100)
+    idx = split_indices(grid.shape[0], _split_counts(split, grid.shape[0]), rng)
+    u_ex, v_ex, p_ex = (np.asarray(g[k], dtype=np.float64) for k in ("u", "v", "p"))   # no mean subtraction here (:112)
+    d.consts = {"norm_vel": max(spread(u_ex), spread(v_ex)) if norm_vel is None else float(norm_vel),
+                "norm_pre": spread(p_ex) if norm_pre is None else float(norm_pre), "ni": ni, "rho": rho, "mu": mu}
+    fields_norm = [u_ex / d.norm_vel, v_ex / d.norm_vel, p_ex / d.norm_pre]
+    if o.n_pts["PDE"] > grid.shape[0]:
+        raise ValueError("Coronary_Flow draws its collocation points from the mesh nodes")
+    d.x_pde = grid[idx["PDE"]]
+    bxy, lab = np.asarray(g["bpoints_xy"], dtype=np.float64), np.asarray(g["bpoints_label"]).astype(int)
+    d.bnd_pts = {e: bxy[lab == i] for i, e in enumerate(CORONARY_EDGES)}
+    bnd_raw = [{"NOSL": 0, "INF": u_inf, "OUT1": 0, "OUT2": 0}, {"NOSL": 0, "INF": v_inf, "OUT1": 0, "OUT2": 0}]
+    nv = d.norm_vel
+    for comp in (0, 1):      # :141-146
+        for edge, value in bnd_raw[comp].items():
+            zero = np.zeros(len(d.bnd_pts[edge]))
+            d.bnd_val[comp][edge] = zero + (value / nv if isinstance(value, (int, float)) else value(d.bnd_pts[edge]) / nv)
+    for edge in bnd_raw[0].keys():   # :154-156
+        d.bnd_val[0][edge] = d.bnd_val[0][edge] + generate_noise(rng, len(d.bnd_pts[edge]), o.noise_factor_bnd)
+        d.bnd_val[1][edge] = d.bnd_val[1][edge] + generate_noise(rng, len(d.bnd_pts[edge]), o.noise_factor_bnd)
+    _fit_targets(d, grid, fields_norm, idx, rng)
+    return _round_all(d)
+
+
 def poisson(mixed: bool = True, seed: int = 1, num_pde: int = 200, num_bc: int = 20,
             num_test: int = 1000) -> ProblemData:
     """Examples/Poisson_Problem/poisson_misto.py:21-60 (mixed=True) / poisson.py:20-56."""
@@ -355,6 +440,7 @@ BUILDERS: Dict[str, Callable[..., ProblemData]] = {
     "colliding_flow": colliding_flow,
     "cavity_steady": cavity_steady,
     "cavity_unsteady": cavity_unsteady,
+    "coronary_flow": coronary_flow,
 }
 
 # BASELINE.json configs: name -> builder kwargs

@@ -167,6 +167,21 @@ def neumann(pointset: PointSet, k: int, j: int, rhs, norm_vel: float, norm_pre: 
     return ResidualForm(pointset, coef, rhs=rhs, rhs_scale=kappa, source="poiseuille_flow.py:199-209")
 
 
+def outflow_stress(pointset: PointSet, k: int, normal, rhs, norm_vel: float, norm_pre: float, ni: float,
+                   in_tape: bool = False) -> ResidualForm:
+    """Coronary ``neu_loss(edge, k, rhs)``: ni * grad(norm_vel*N_k) . n - norm_pre*N_2 * n[k] - rhs with the script's
+    un-normalised normals n = (2, 1) on OUT1 and (1, 0) on OUT2 (coronary_flow_steady.py:197-211).  There the model
+    is called AFTER the tape closed (:205-209), so ``gradient`` returns zeros and only the pressure part survives --
+    ``in_tape=False`` restates that (for n[k] = 0 the residual is the constant -rhs: the flat BCN_v_OUT2 log of
+    Test_Case_#123); ``in_tape=True`` is the intended traction condition."""
+    coef = {(2, ch_val()): -norm_pre * float(normal[k])}
+    if in_tape:
+        for j in (0, 1):
+            if normal[j] != 0:
+                coef[(k, ch_d(j))] = ni * norm_vel * float(normal[j])
+    return ResidualForm(pointset, coef, rhs=rhs, rhs_scale=1.0, source="coronary_flow_steady.py:197-211")
+
+
 def poisson_pde(pointset: PointSet, forcing) -> ResidualForm:
     """``PDE``: -laplacian(u) - f (poisson.py:58-63, poisson_misto.py:62-67)."""
     dim = pointset.dim

@@ -5,6 +5,10 @@
 Writes, next to this script:
   weights_<case>.npz   trained float64 weights of the saved runs (Weights.h5 via the product's h5lite)
   history_<case>.json  head + tail of every History_Loss.json (term names, weights, log values)
+  test_options.json    every Test_Options.txt recap, verbatim
+  coronary_geometry.npz  Coronary_Flow inputs: mesh nodes (coroParam.msh via the product's gmsh reader), labelled
+                       boundary points (DataGeneration/data/Coronary/bpoints.npy) and the u/v/p arrays of sol_pinn.h5
+                       (same node order) as the stand-in for the absent FEM solution
 The GPU box has no /root/reference; tests read only these fixtures.
 """
 import glob
@@ -71,6 +75,23 @@ def main(ref):
             opts[os.path.basename(os.path.dirname(p))] = fh.read()
     with open(os.path.join(HERE, "simulation_options.json"), "w") as fh:
         json.dump(opts, fh, indent=1)
+    recaps = {}
+    for p in sorted(glob.glob(os.path.join(ref, "Examples", "*", "Test_Case_*", "Test_Options.txt"))):
+        with open(p) as fh:
+            recaps[os.path.basename(os.path.dirname(os.path.dirname(p)))] = fh.read()
+    with open(os.path.join(HERE, "test_options.json"), "w") as fh:
+        json.dump(recaps, fh, indent=1)
+    # Coronary_Flow geometry and fields
+    from pinns_fluid_dynamics_b200.h5lite import H5File
+    from pinns_fluid_dynamics_b200.problems import read_gmsh_nodes
+    cor = os.path.join(ref, "Examples", "Coronary_Flow")
+    nodes = read_gmsh_nodes(os.path.join(cor, "coroParam.msh"))[:, :2]
+    bpts = np.load(os.path.join(ref, "DataGeneration", "data", "Coronary", "bpoints.npy"))
+    sol = H5File(os.path.join(cor, "sol_pinn.h5"))
+    np.savez_compressed(os.path.join(HERE, "coronary_geometry.npz"), nodes=nodes.astype(np.float32),
+                        bpoints_xy=bpts[:, :2].astype(np.float32), bpoints_label=bpts[:, 3].astype(np.int8),
+                        u=sol["u_pinn"].astype(np.float32), v=sol["v_pinn"].astype(np.float32),
+                        p=sol["p_pinn"].astype(np.float32))
 
 
 if __name__ == "__main__":

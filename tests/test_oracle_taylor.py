@@ -1,6 +1,8 @@
 """Taylor-mode jets + hand-written reverse sweep (oracle/taylor.py, the algorithm the kernels
 implement) == nested reverse-mode autodiff (oracle/reference_step.py, the reference's formulation),
 in float64, for every in-scope script."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -9,7 +11,10 @@ from oracle import reference_step, taylor
 from pinns_fluid_dynamics_b200 import loss_tables, problems
 from pinns_fluid_dynamics_b200.engine import assemble_losses, compile_problem
 
+CORONARY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "coronary_geometry.npz")
+
 CASES = {
+    "coronary_flow": dict(geometry=CORONARY, PDE=200, BC=800, Vel=50, Pres=0, Test=40, noise_bnd=0.01, noise_fit=0.01),
     "poisson": dict(),
     "poisson_misto": dict(),
     "poiseuille_flow": dict(PDE=200, BC=30, Vel=10, Pres=0, Test=40),
@@ -57,6 +62,26 @@ def test_in_tape_divergence_variant(name):
     names = [l.name for l in losses]
     i = names.index("PDE_MASS")
     assert vals[i] > 0 and abs(vals[i] - tr2[i]) <= 1e-11 * vals[i]
+
+
+def test_coronary_outflow_terms():
+    """coronary_flow_steady.py:201-215 calls the model after the tape closed: only the pressure part of the outflow
+    condition survives and BCN_v_OUT2 (n = (1, 0), k = 1) is the constant mean(rhs^2) with no gradient -- the flat
+    BCN_v_OUT2 log of Test_Case_#123.  faithful=False restores the traction term."""
+    ref, cp, theta, losses = _both("coronary_flow")
+    vals, _, _ = ref.loss_and_grad()
+    names = [l.name for l in losses]
+    data = problems.BUILDERS["coronary_flow"](seed=4, **CASES["coronary_flow"])
+    i = names.index("BCN_v_OUT2")
+    assert abs(vals[i] - np.mean(data.bnd_val[1]["OUT2"] ** 2)) <= 1e-12 * vals[i]
+    ref2, cp2, theta2, losses2 = _both("coronary_flow", faithful=False, in_tape_neumann=True)
+    vals2, total2, grad2 = ref2.loss_and_grad()
+    out = taylor.loss_and_grad(cp2, theta2)
+    tot, tr, _ = assemble_losses(cp2, out[cp2.n_params:])
+    assert vals2[i] != vals[i]
+    assert np.allclose(vals2, tr, rtol=1e-11, atol=1e-300)
+    g = grad2.numpy()
+    assert np.linalg.norm(g - out[:cp2.n_params]) <= 1e-11 * np.linalg.norm(g)
 
 
 def test_wide_deep_network():

@@ -1,6 +1,8 @@
 """GPU parity: CUDA loss step (through the facade and the C ABI) vs the float64 oracles on identical
 weights and points.  Tolerances are the north-star's: 1e-5 relative on loss values, 1e-4 relative L2
 on the parameter gradient."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -14,7 +16,10 @@ pytestmark = pytest.mark.gpu
 LOSS_RTOL = 1e-5
 GRAD_RTOL = 1e-4
 
+CORONARY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "coronary_geometry.npz")
+
 SMALL = {
+    "coronary_flow": dict(geometry=CORONARY, PDE=3000, BC=800, Vel=50, Pres=0, Test=1000, noise_bnd=0.01, noise_fit=0.01),
     "poisson": dict(),
     "poisson_misto": dict(),
     "poiseuille_flow": dict(PDE=1000, BC=100, Vel=10, Pres=0, Test=100),
@@ -72,7 +77,7 @@ def test_step_matches_reference_restatement(name, bias_std):
         assert _term_close(v, rv)
 
 
-@pytest.mark.parametrize("name", ["colliding_flow", "poiseuille_flow", "cavity_steady"])
+@pytest.mark.parametrize("name", ["colliding_flow", "poiseuille_flow", "cavity_steady", "coronary_flow"])
 def test_corrected_residuals_match_taylor_oracle(name):
     """faithful=False (in-tape divergence, -laplacian) vs the Taylor-mode oracle."""
     from oracle import taylor

@@ -1,10 +1,12 @@
 """ORACLE -- TEST INFRASTRUCTURE ONLY.  Never import this from the product package.
 
 Reference-faithful CPU restatement (torch float64, nested reverse-mode autodiff) of the loss tables
-of the five in-scope example scripts.  One ``model(x)`` forward PER LOSS TERM and one
+of the in-scope example scripts (five BASELINE configs + Coronary_Flow).  One ``model(x)`` forward PER LOSS TERM and one
 ``gradient(tape, ., x)`` sweep per call in the script -- including the duplicated sweeps -- so that
 this is also a fair stand-in for timing the reference's step on the CPU (bench.py cpu_baseline,
-kind "port").  PARITY UNPINNED for numerical values, see oracle/nisaba_like.py.
+kind "port").  PARITY UNPINNED at the bit level (TensorFlow / nisaba cannot run here), see oracle/nisaba_like.py;
+what the reference's saved artefacts pin numerically (trained-weight replays, sol_pinn.h5) is in tests/test_oracle_pins.py
+and tests/test_coronary.py.
 
 Each builder takes the ``ProblemData`` arrays (plain numpy) and the Keras-ordered weights and
 returns ``OptimizationProblem(variables, losses, losses_test)`` exactly as the script's last lines do.

@@ -38,6 +38,12 @@
  * which covers every closure of the five in-scope scripts (DESIGN.md section 3 lists the
  * coefficient sets).  The term's loss value is  sum_n r_n^2 / (normalization * n_global)  and the
  * total loss is  sum_t weight_t * value_t  (cavity_steady.py:212-231, nisaba semantics).
+ *
+ * A term of kind PINN_TERM_ABS_MEAN restates  ns.Loss('PRESS_0', lambda: tf.abs(tf.reduce_mean(model(x)[:,2])))
+ * (Examples/Colliding_Flow/colliding_flow_pressmean.py:176-179,196): its value is  |sum_n r_n| / (normalization *
+ * n_global),  its output slot carries the raw  sum_n r_n,  and its gradient is  sign(sum_n r_n) * weight /
+ * (normalization * n_global) * sum_n d r_n / d theta.  The sign is taken from a forward pre-pass over the term's point
+ * set inside pinn_loss_and_grad, so such a set must live entirely on ONE rank (the host side keeps it on rank 0).
  */
 #ifndef PINNSTEP_H
 #define PINNSTEP_H
@@ -49,12 +55,17 @@
 extern "C" {
 #endif
 
-#define PINN_VERSION 100 /* 0.1.0 */
+#define PINN_VERSION 101 /* 0.1.1: pinn_term_desc.kind, pinn_adam_step_dev */
 
 #define PINN_MAX_OUT 4   /* network outputs (u, v, p) padded to 4 */
 #define PINN_MAX_CH 6    /* value, d/dt, d/dx, d/dy, d2/dx2, d2/dy2 */
 #define PINN_MAX_DIM 3
 #define PINN_MAX_TERMS_PER_SET 8
+
+enum pinn_term_kind {
+  PINN_TERM_MEAN_SQUARES = 0, /* ns.LossMeanSquares */
+  PINN_TERM_ABS_MEAN = 1      /* ns.Loss over |mean(residual)| (colliding_flow_pressmean.py:196) */
+};
 
 enum pinn_status {
   PINN_OK = 0,
@@ -88,6 +99,7 @@ typedef struct pinn_term_desc {
   int64_t n_global;                      /* number of roots of this term over ALL ranks */
   int32_t train;                         /* 1: contributes to the total loss and gradient;
                                             0: test loss (forward only, pinn_loss) */
+  int32_t kind;                          /* PINN_TERM_MEAN_SQUARES (0) | PINN_TERM_ABS_MEAN (1) */
 } pinn_term_desc;
 
 /* One point set = one category of the scripts (PDE / one boundary edge / IC / Vel / Pres / Test). */

@@ -136,6 +136,21 @@ class LossMeanSquares:
         return torch.mean(torch.square(r)) / self.normalization
 
 
+class Loss:
+    """ns.Loss(name, eval_loss, normalization=1.0, weight=1.0, non_negative=False): a scalar loss,
+    value = eval_loss() / normalization [inferred by analogy with LossMeanSquares; the only call site,
+    colliding_flow_pressmean.py:196, passes normalization=1e0]."""
+
+    def __init__(self, name: str, eval_loss: Callable[[], torch.Tensor], normalization: float = 1.0, weight: float = 1.0,
+                 non_negative: bool = False):
+        self.name, self.eval_loss = name, eval_loss
+        self.weight, self.normalization = float(weight), float(normalization)
+        self.non_negative, self.display_sqrt = bool(non_negative), False
+
+    def __call__(self) -> torch.Tensor:
+        return self.eval_loss() / self.normalization
+
+
 class OptimizationProblem:
     """ns.OptimizationProblem(variables, losses, losses_test): total = sum_t weight_t * loss_t()."""
 

@@ -19,7 +19,7 @@ from typing import Dict, List, Sequence
 import numpy as np
 import torch
 
-from .nisaba_like import (DTYPE, GradientTape, KerasMLP, LossMeanSquares, OptimizationProblem,
+from .nisaba_like import (DTYPE, GradientTape, KerasMLP, Loss, LossMeanSquares, OptimizationProblem,
                           divergence_vector, gradient_scalar, laplacian_scalar)
 
 
@@ -276,6 +276,62 @@ def poiseuille_flow(data, variables, in_tape_divergence: bool = False) -> Optimi
 
 
 # --------------------------------------------------------------------------------------------
+# Colliding_Flow, pressure-mean variant  (Examples/Colliding_Flow/colliding_flow_pressmean.py)
+# --------------------------------------------------------------------------------------------
+
+def colliding_flow_pressmean(data, variables) -> OptimizationProblem:
+    model = KerasMLP(variables)
+    dim = 2
+    vel_max, p_max = data.norm_vel, data.norm_pre
+    x_PDE, x_col, x_BCD = _t(data.x_pde), _t(data.x_vel), _t(data.extra["x_BCD"])
+    x_test, x_pres = _t(data.x_test), _t(data.x_pres)
+    rhs = {k: _t(data.extra[k]) for k in ("bcd_u", "bcd_v", "col_u", "col_v", "col_p")}
+    sol_test = [_t(v) for v in data.sol_test]
+
+    def PDE_MASS(x):  # colliding_flow_pressmean.py:140-145
+        x = _watch(x)
+        with GradientTape(persistent=True) as tape:
+            tape.watch(x)
+            u_vect = model(x)[:, 0:2] * vel_max
+            div = divergence_vector(tape, u_vect, x, dim)
+        return div
+
+    def PDE_MOM(x, k):  # :147-159 (zero forcing)
+        x = _watch(x)
+        with GradientTape(persistent=True) as tape:
+            tape.watch(x)
+            u_vect = model(x)
+            p = u_vect[:, 2] * p_max
+            u_eq = u_vect[:, k] * vel_max
+            dp = gradient_scalar(tape, p, x)[:, k]
+            lapl_eq = laplacian_scalar(tape, u_eq, x, dim)
+        return - (lapl_eq) + dp
+
+    def BC_D(x, k, target):  # :163-166 and exact_value :170-173; target = (g_bc(x) + noise) / norm
+        return model(x)[:, k] - target
+
+    def PRESS_0(x):  # :176-179
+        uk = model(x)[:, 2]
+        return torch.abs(torch.mean(uk))
+
+    LMS = LossMeanSquares
+    losses = [LMS('PDE_MASS', lambda: PDE_MASS(x_PDE), normalization=1e4, weight=1e0),
+              LMS('PDE_MOMU', lambda: PDE_MOM(x_PDE, 0), normalization=1e4, weight=1e-2),
+              LMS('PDE_MOMV', lambda: PDE_MOM(x_PDE, 1), normalization=1e4, weight=1e-2),
+              LMS('BCD_u', lambda: BC_D(x_BCD, 0, rhs["bcd_u"]), weight=1e0),
+              LMS('BCD_v', lambda: BC_D(x_BCD, 1, rhs["bcd_v"]), weight=1e0)]
+    if data.consts["collocation"]:
+        losses += [LMS('COL_u', lambda: BC_D(x_col, 0, rhs["col_u"])), LMS('COL_v', lambda: BC_D(x_col, 1, rhs["col_v"]))]
+    if data.consts["press_mode"] == "Collocation":
+        losses += [LMS('COL_p', lambda: BC_D(x_pres, 2, rhs["col_p"]))]
+    if data.consts["press_mode"] == "Mean":
+        losses += [Loss('PRESS_0', lambda: PRESS_0(x_pres), normalization=1e0, weight=1e-2, non_negative=True)]
+    loss_test = [LMS('u_fit', lambda: BC_D(x_test, 0, sol_test[0])), LMS('v_fit', lambda: BC_D(x_test, 1, sol_test[1])),
+                 LMS('p_fit', lambda: BC_D(x_test, 2, sol_test[2]))]
+    return OptimizationProblem(model.variables, losses, loss_test)
+
+
+# --------------------------------------------------------------------------------------------
 # Coronary_Flow  (Examples/Coronary_Flow/coronary_flow_steady.py)
 # --------------------------------------------------------------------------------------------
 
@@ -416,6 +472,7 @@ BUILDERS = {
     "poisson": poisson,
     "poisson_misto": poisson,
     "coronary_flow": coronary_flow,
+    "colliding_flow_pressmean": colliding_flow_pressmean,
 }
 
 

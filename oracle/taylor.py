@@ -179,6 +179,13 @@ def loss_and_grad(cp, theta: np.ndarray, with_grad: bool = True, include_test: b
             rhs = t.form.rhs_array()
             rhs = None if rhs is None else rhs[cs.start:cs.stop].astype(np.float64)
             r = residual(t, J, d, rhs)
+            if t.abs_mean:     # ns.Loss over |mean(roots)|: slot = sum r, adjoint = sign(sum r) w / (nu N)
+                total_r = float(np.sum(r))
+                out[cp.n_params + t.out_index] += total_r
+                if t.train and with_grad:
+                    sgn = -1.0 if total_r < 0 else 1.0
+                    Jbar += residual_adjoint(t, J, np.full_like(r, sgn * t.weight / (t.normalization * t.n_global)), d)
+                continue
             out[cp.n_params + t.out_index] += float(np.sum(r * r))
             if t.train and with_grad:
                 scale = 2.0 * t.weight / (t.normalization * t.n_global)

@@ -39,6 +39,7 @@ class TermDesc(C.Structure):
         ("normalization", C.c_double),
         ("n_global", C.c_int64),
         ("train", C.c_int32),
+        ("kind", C.c_int32),
     ]
 
 

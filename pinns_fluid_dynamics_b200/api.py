@@ -139,13 +139,21 @@ class LossMeanSquares:
 
 
 class Loss:
-    """Generic scalar loss (``ns.Loss('PRESS_0', ...)`` of the out-of-scope pressmean variant).  Only
-    mean-square terms are on the fused path; a generic scalar closure is rejected loudly."""
+    """``ns.Loss(name, eval_loss, normalization, weight, non_negative)`` -- a scalar loss, value = eval_loss() /
+    normalization.  The reference's only use is ``ns.Loss('PRESS_0', lambda: PRESS_0(x_pres), normalization=1e0,
+    weight=1e-2, non_negative=True)`` with PRESS_0 = |mean(model(x)[:, 2])| (colliding_flow_pressmean.py:176-179,196);
+    that scalar is served on the fused path as the ``abs_mean`` reduction of a residual form
+    (``residuals.mean_value``).  Any other scalar closure is rejected loudly."""
 
     def __init__(self, name, eval_loss, weight=1.0, normalization=1.0, non_negative=False):
-        raise NotImplementedError(
-            "ns.Loss with an arbitrary scalar closure is outside the fused loss-step path "
-            "(only used by colliding_flow_pressmean.py:196, SURVEY.md row 3b); use LossMeanSquares")
+        form = eval_loss() if callable(eval_loss) and not isinstance(eval_loss, ResidualForm) else eval_loss
+        if not isinstance(form, ResidualForm) or form.reduction != "abs_mean":
+            raise NotImplementedError(
+                "ns.Loss serves |mean(residual)| forms (residuals.mean_value, colliding_flow_pressmean.py:196); "
+                "an arbitrary scalar closure cannot be fused into the kernel")
+        self.name, self.form = name, form
+        self.weight, self.normalization = float(weight), float(normalization)
+        self.non_negative, self.display_sqrt = bool(non_negative), False
 
 
 # ------------------------------------------------------------------------------------------------

@@ -21,6 +21,9 @@ struct TermDev {
   const float* rhs;     // [n_local] or nullptr
   int out_index;        // slot in the [T] tail of a workspace row
   int train;
+  int kind;             // 0: sum r^2, adjoint scale*r;  1 (|mean|): sum r, adjoint scale*(*sign)
+  int pad_;
+  const float* sign;    // kind 1: +-1 written by the pre-pass of pinn_loss_and_grad
 };
 
 // One point set (a "segment" of a launch): chunks [chunk_begin, chunk_begin + n_chunks).

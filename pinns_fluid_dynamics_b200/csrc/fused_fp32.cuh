@@ -555,11 +555,16 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
       if (rhs != nullptr) r = fma2(bc2(-__ldg(&T->rhs_scale)), make_float2(__ldg(rhs + i0), __ldg(rhs + i1)), r);
       r.x = valid0 ? r.x : 0.f;
       r.y = valid1 ? r.y : 0.f;
-      float sq = (lc == 0) ? fmaf(r.x, r.x, r.y * r.y) : 0.f;
+      const bool abs_mean = __ldg(&T->kind) != 0;     // |mean r| term: slot carries sum r, adjoint is +-scale
+      float sq = (lc == 0) ? (abs_mean ? r.x + r.y : fmaf(r.x, r.x, r.y * r.y)) : 0.f;
       sq = reduce_warp(sq);
       if (lane == 0) ssq[T->out_index] += sq;
       if constexpr (TRAIN) {
-        const float2 rb = mul2(bc2(__ldg(&T->scale)), r);
+        float2 rb = mul2(bc2(__ldg(&T->scale)), r);
+        if (abs_mean) {
+          const float sg = __ldg(&T->scale) * __ldg(T->sign);
+          rb = make_float2(valid0 ? sg : 0.f, valid1 ? sg : 0.f);
+        }
 #pragma unroll
         for (int o = 0; o < O; ++o)
 #pragma unroll

@@ -60,6 +60,10 @@ struct pinn_plan {
   std::vector<pinn_pointset_desc> sets;
   std::vector<int> term_base;            // first output slot of each set
   LaunchTable train[3], eval[3];         // by derivative order
+  LaunchTable prepass[3];                // sets that carry a |mean| training term (forward pre-pass for its sign)
+  bool has_abs_mean = false;
+  float* signs = nullptr;                // [T] +-1 per term slot (only |mean| slots are read)
+  float* prepass_out = nullptr;          // [P + T] scratch of the pre-pass
   float* ws = nullptr;                   // [rows_max][P + T]
   int rows_max = 0;
   size_t ws_bytes = 0;
@@ -106,6 +110,7 @@ static bool pick_kernel(const pinn_mlp_desc& m, int order, bool train, FusedKern
   if (m.in_dim == 2 && m.width == 32 && m.out_dim == 3) return pick_order<2, 32, 3, 3>(order, train, k);
   if (m.in_dim == 3 && m.width == 32 && m.out_dim == 3) return pick_order<3, 32, 3, 3>(order, train, k);
   if (m.in_dim == 2 && m.width == 20 && m.out_dim == 1) return pick_order<2, 20, 3, 1>(order, train, k);
+  if (m.in_dim == 2 && m.width == 20 && m.out_dim == 3) return pick_order<2, 20, 3, 3>(order, train, k);   // pressmean variant
   return false;
 }
 
@@ -114,18 +119,26 @@ static int64_t param_count(const pinn_mlp_desc& m) {
   return d * H + H + (L - 1) * (H * H + H) + H * O + O;
 }
 
-static int build_table(pinn_plan* p, int order, bool train_only, LaunchTable* out) {
+// mode 0: every term (pinn_loss); 1: training terms; 2: only the sets with a |mean| training term (sign pre-pass)
+static int build_table(pinn_plan* p, int order, int mode, LaunchTable* out) {
+  const bool train_only = mode != 0;
   std::vector<SegDev> segs;
   int chunk = 0;
   for (size_t s = 0; s < p->sets.size(); ++s) {
     const pinn_pointset_desc& ps = p->sets[s];
     if (ps.deriv_order != order || ps.n_local <= 0) continue;
+    if (mode == 2) {
+      bool any = false;
+      for (int t = 0; t < ps.n_terms; ++t) any = any || (ps.terms[t].train && ps.terms[t].kind == PINN_TERM_ABS_MEAN);
+      if (!any) continue;
+    }
     SegDev sd;
     memset(&sd, 0, sizeof(sd));
     int nt = 0;
     for (int t = 0; t < ps.n_terms; ++t) {
       const pinn_term_desc& td = ps.terms[t];
       if (train_only && !td.train) continue;
+      if (mode == 2 && td.kind != PINN_TERM_ABS_MEAN) continue;
       TermDev& d = sd.terms[nt++];
       memcpy(d.coef, td.coef, sizeof(d.coef));
       d.conv = td.conv;
@@ -134,8 +147,11 @@ static int build_table(pinn_plan* p, int order, bool train_only, LaunchTable* ou
       d.rhs = td.rhs_dev;
       d.train = td.train;
       d.out_index = p->term_base[s] + t;
+      d.kind = td.kind;
+      d.sign = p->signs ? p->signs + d.out_index : nullptr;
       const double denom = td.normalization * (double)td.n_global;
-      d.scale = (td.train && denom != 0.0) ? (float)(2.0 * td.weight / denom) : 0.f;
+      // d/dtheta of w/(nu N) sum r^2 is (2w/(nu N)) sum r dr; of w/(nu N) |sum r| it is (sign w/(nu N)) sum dr
+      d.scale = (td.train && denom != 0.0) ? (float)((td.kind == PINN_TERM_ABS_MEAN ? 1.0 : 2.0) * td.weight / denom) : 0.f;
     }
     if (nt == 0) continue;
     sd.pts = ps.points_dev;
@@ -465,7 +481,7 @@ extern "C" int pinn_plan_create(const pinn_mlp_desc* mlp, const pinn_pointset_de
   const bool use_layered = !use_fused && !use_tc && layered_supported(*mlp);
   if (!use_fused && !use_layered && !use_tc)
     return fail(PINN_E_INVALID,
-                "no engine for MLP d=%d H=%d L=%d O=%d (fused_fp32: 2-20x3-1, 2-32x3-3, 3-32x3-3; layered_tf32x3: "
+                "no engine for MLP d=%d H=%d L=%d O=%d (fused_fp32: 2-20x3-1, 2-20x3-3, 2-32x3-3, 3-32x3-3; layered_tf32x3: "
                 "d in {2,3}, H = 128, L >= 2, O = 3; layered_fp32: d in {2,3}, H in {64,128}, L >= 2, O = 3)", mlp->in_dim, mlp->width, mlp->n_hidden, mlp->out_dim);
   CUDA_TRY(cudaSetDevice(device));
   cudaDeviceProp prop;
@@ -494,9 +510,34 @@ extern "C" int pinn_plan_create(const pinn_mlp_desc* mlp, const pinn_pointset_de
     return fail(PINN_E_INVALID, "%d loss terms exceed the limit of %d", T, kMaxLaunchTerms);
   }
   p->T = T;
+  for (int s = 0; s < n_sets; ++s)
+    for (int t = 0; t < sets[s].n_terms; ++t) {
+      const int kind = sets[s].terms[t].kind;
+      if (kind != PINN_TERM_MEAN_SQUARES && kind != PINN_TERM_ABS_MEAN) {
+        delete p;
+        return fail(PINN_E_INVALID, "set %d term %d: unknown term kind %d", s, t, kind);
+      }
+      if (kind == PINN_TERM_ABS_MEAN) {
+        if (!use_fused) {
+          delete p;
+          return fail(PINN_E_INVALID, "|mean| terms (PINN_TERM_ABS_MEAN) are served by the fused_fp32 engine only");
+        }
+        p->has_abs_mean = p->has_abs_mean || sets[s].terms[t].train;
+      }
+    }
+  if (p->has_abs_mean) {
+    std::vector<float> ones((size_t)T, 1.f);
+    if (cudaMalloc(&p->signs, sizeof(float) * (size_t)T) != cudaSuccess ||
+        cudaMalloc(&p->prepass_out, sizeof(float) * (size_t)(p->P + T)) != cudaSuccess) {
+      pinn_plan_destroy(p);
+      return fail(PINN_E_ALLOC, "sign buffers");
+    }
+    CUDA_TRY(cudaMemcpy(p->signs, ones.data(), sizeof(float) * (size_t)T, cudaMemcpyHostToDevice));
+  }
   for (int o = 0; o < 3; ++o) {
-    int rc = build_table(p, o, true, &p->train[o]);
-    if (rc == PINN_OK) rc = build_table(p, o, false, &p->eval[o]);
+    int rc = build_table(p, o, 1, &p->train[o]);
+    if (rc == PINN_OK) rc = build_table(p, o, 0, &p->eval[o]);
+    if (rc == PINN_OK && p->has_abs_mean) rc = build_table(p, o, 2, &p->prepass[o]);
     if (rc != PINN_OK) {
       pinn_plan_destroy(p);
       return rc;
@@ -557,7 +598,10 @@ extern "C" int pinn_plan_destroy(pinn_plan* p) {
     if (p->eval[o].segs_dev) cudaFree(p->eval[o].segs_dev);
     if (p->train[o].tiles_dev) cudaFree(p->train[o].tiles_dev);
     if (p->eval[o].tiles_dev) cudaFree(p->eval[o].tiles_dev);
+    if (p->prepass[o].segs_dev) cudaFree(p->prepass[o].segs_dev);
   }
+  if (p->signs) cudaFree(p->signs);
+  if (p->prepass_out) cudaFree(p->prepass_out);
   if (p->ws) cudaFree(p->ws);
   if (p->act) cudaFree(p->act);
   if (p->wt) cudaFree(p->wt);
@@ -607,8 +651,10 @@ extern "C" int pinn_plan_set_rhs(pinn_plan* p, int32_t set_index, int32_t term_i
   const int o = ps.deriv_order;
   if (p->train[o].segs_dev) { cudaFree(p->train[o].segs_dev); p->train[o].segs_dev = nullptr; }
   if (p->eval[o].segs_dev) { cudaFree(p->eval[o].segs_dev); p->eval[o].segs_dev = nullptr; }
-  int rc = build_table(p, o, true, &p->train[o]);
-  if (rc == PINN_OK) rc = build_table(p, o, false, &p->eval[o]);
+  if (p->prepass[o].segs_dev) { cudaFree(p->prepass[o].segs_dev); p->prepass[o].segs_dev = nullptr; }
+  int rc = build_table(p, o, 1, &p->train[o]);
+  if (rc == PINN_OK) rc = build_table(p, o, 0, &p->eval[o]);
+  if (rc == PINN_OK && p->has_abs_mean) rc = build_table(p, o, 2, &p->prepass[o]);
   if (rc == PINN_OK && p->tc) {
     rc = tc_build_tiles(&p->train[o], p->mlp.in_dim);
     if (rc == PINN_OK) rc = tc_build_tiles(&p->eval[o], p->mlp.in_dim);
@@ -616,27 +662,33 @@ extern "C" int pinn_plan_set_rhs(pinn_plan* p, int32_t set_index, int32_t term_i
   return rc;
 }
 
-static int run(pinn_plan* p, const float* params, float* out, cudaStream_t st, bool train) {
-  if (!p || !params || !out) return fail(PINN_E_INVALID, "null argument");
-  if (p->tc) return run_tc(p, params, out, st, train);
-  if (p->layered) return run_layered(p, params, out, st, train);
+// sign[t] = +-1 from the pre-pass sums (slots of other terms are never read)
+__global__ void sign_kernel(const float* __restrict__ sums, float* __restrict__ sign, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) sign[i] = sums[i] < 0.f ? -1.f : 1.f;
+}
+
+// One pass of the fused engine over `tables` (train: gradient + training sums into out[0, P+T); otherwise the term
+// sums only, into out[P, P+T)).
+static int fused_pass(pinn_plan* p, const LaunchTable* tables, const float* params, float* out, cudaStream_t st, bool train,
+                      bool timed, int* launches_out) {
   const int stride = (int)(p->P + p->T);
   int rows = 0, launches = 0;
   const int aligned = ((uintptr_t)params & 15u) == 0;
   // big derivative order first: the collocation kernel dominates
   for (int o = 2; o >= 0; --o) {
-    const LaunchTable& lt = train ? p->train[o] : p->eval[o];
+    const LaunchTable& lt = tables[o];
     if (lt.n_segs == 0) continue;
     FusedKernel k;
     if (!pick_kernel(p->mlp, o, train, &k)) return fail(PINN_E_INVALID, "no kernel");
     int grid = (lt.total_chunks + k.nw - 1) / k.nw;
     if (grid > p->num_sms) grid = p->num_sms;
     if (rows + grid > p->rows_max) return fail(PINN_E_STATE, "workspace rows exhausted");
-    if (p->timing) CUDA_TRY(cudaEventRecord(p->ev0[o], st));
+    if (timed) CUDA_TRY(cudaEventRecord(p->ev0[o], st));
     k.fn<<<grid, k.nw * 32, k.smem_bytes, st>>>(params, lt.segs_dev, lt.n_segs, lt.total_chunks,
                                                 p->ws + (size_t)rows * stride, stride, p->T, aligned);
     CUDA_TRY(cudaGetLastError());
-    if (p->timing) {
+    if (timed) {
       CUDA_TRY(cudaEventRecord(p->ev1[o], st));
       p->ev_valid[o] = true;
     }
@@ -652,6 +704,25 @@ static int run(pinn_plan* p, const float* params, float* out, cudaStream_t st, b
     CUDA_TRY(cudaGetLastError());
     ++launches;
   }
+  *launches_out += launches;
+  return PINN_OK;
+}
+
+static int run(pinn_plan* p, const float* params, float* out, cudaStream_t st, bool train) {
+  if (!p || !params || !out) return fail(PINN_E_INVALID, "null argument");
+  if (p->tc) return run_tc(p, params, out, st, train);
+  if (p->layered) return run_layered(p, params, out, st, train);
+  int launches = 0;
+  if (train && p->has_abs_mean) {
+    // forward pre-pass over the sets with a |mean| term: sum r -> sign (colliding_flow_pressmean.py:176-179)
+    int rc = fused_pass(p, p->prepass, params, p->prepass_out, st, false, false, &launches);
+    if (rc != PINN_OK) return rc;
+    sign_kernel<<<(p->T + 127) / 128, 128, 0, st>>>(p->prepass_out + p->P, p->signs, p->T);
+    CUDA_TRY(cudaGetLastError());
+    ++launches;
+  }
+  int rc = fused_pass(p, train ? p->train : p->eval, params, out, st, train, p->timing, &launches);
+  if (rc != PINN_OK) return rc;
   p->last_launches = launches;
   return PINN_OK;
 }

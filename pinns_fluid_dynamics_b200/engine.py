@@ -34,6 +34,11 @@ class CompiledTerm:
     n_global: int
     out_index: int = -1            # position in the [T] tail of the output vector (-1: identically zero)
 
+    @property
+    def abs_mean(self) -> bool:
+        """|mean r| reduction (ns.Loss): the output slot carries sum r instead of sum r^2"""
+        return self.form.reduction == "abs_mean"
+
 
 @dataclass
 class CompiledSet:
@@ -121,6 +126,10 @@ def compile_problem(var_shapes, losses, losses_test=(), rank: int = 0, world: in
     for ps in order:
         group = by_set[ps.uid]
         start, stop = shard_bounds(ps.n, rank, world)
+        if any(t.abs_mean for t in group):
+            # the sign of a |mean| term comes from a forward pre-pass over its whole point set (include/pinnstep.h):
+            # such a set is not sharded, rank 0 owns it
+            start, stop = (0, ps.n) if rank == 0 else (0, 0)
         for i in range(0, len(group), MAX_TERMS_PER_SET):
             chunk = group[i:i + MAX_TERMS_PER_SET]
             cs = CompiledSet(ps, start, stop, max(t.form.deriv_order() for t in chunk), chunk)
@@ -134,7 +143,8 @@ def compile_problem(var_shapes, losses, losses_test=(), rank: int = 0, world: in
 
 def assemble_losses(cp: CompiledProblem, sumsq: np.ndarray) -> Tuple[float, List[float], List[float]]:
     """(total, train values, test values) from the GLOBAL sums of squares.
-    value_t = sum r^2 / (N_t * normalization_t); total = sum_train weight_t * value_t
+    value_t = sum r^2 / (N_t * normalization_t) (|sum r| / (N_t * normalization_t) for an ns.Loss |mean| term);
+    total = sum_train weight_t * value_t
     (nisaba semantics evidenced by History_Loss.json).  An empty point set gives
     NaN, like the reference's mean over an empty tensor (quirk Q3)."""
     train_vals, test_vals = [], []
@@ -144,6 +154,8 @@ def assemble_losses(cp: CompiledProblem, sumsq: np.ndarray) -> Tuple[float, List
             v = 0.0
         elif t.n_global == 0:
             v = float("nan")
+        elif t.abs_mean:      # ns.Loss over |mean(roots)|: the slot carries sum r
+            v = abs(float(sumsq[t.out_index])) / (t.n_global * t.normalization)
         else:
             v = float(sumsq[t.out_index]) / (t.n_global * t.normalization)
         if t.train:
@@ -209,6 +221,7 @@ class CudaPlan:
                     td.rhs_dev = None
                 td.weight, td.normalization = t.weight, t.normalization
                 td.n_global, td.train = t.n_global, 1 if t.train else 0
+                td.kind = 1 if t.abs_mean else 0
         d, H, L, O = cp.mlp
         mlp = _capi.MlpDesc(d, H, L, O)
         handle = C.c_void_p()

@@ -13,6 +13,7 @@ from __future__ import annotations
 from typing import List, Tuple
 
 from . import residuals as R
+from .api import Loss
 from .api import LossMeanSquares as LMS
 from .problems import ProblemData
 from .residuals import PointSet
@@ -158,6 +159,27 @@ def coronary_flow(data: ProblemData, faithful: bool = True):
     return losses, test
 
 
+def colliding_flow_pressmean(data: ProblemData, faithful: bool = True):
+    """colliding_flow_pressmean.py:137-214"""
+    vel_max, p_max = data.norm_vel, data.norm_pre
+    pde, bcd = PointSet(data.x_pde, "PDE"), PointSet(data.extra["x_BCD"], "BCD")
+    col, pres, test = PointSet(data.x_vel, "col"), PointSet(data.x_pres, "pres"), PointSet(data.x_test, "Test")
+    losses = [LMS("PDE_MASS", lambda: R.mass(pde, scale=vel_max), normalization=1e4, weight=1e0),
+              LMS("PDE_MOMU", lambda: R.stokes_momentum(pde, 0, vel_max, p_max), normalization=1e4, weight=1e-2),
+              LMS("PDE_MOMV", lambda: R.stokes_momentum(pde, 1, vel_max, p_max), normalization=1e4, weight=1e-2),
+              LMS("BCD_u", lambda: R.dirichlet(bcd, 0, data.extra["bcd_u"]), weight=1e0),
+              LMS("BCD_v", lambda: R.dirichlet(bcd, 1, data.extra["bcd_v"]), weight=1e0)]
+    if data.consts["collocation"]:
+        losses += [LMS("COL_u", lambda: R.dirichlet(col, 0, data.extra["col_u"]), weight=1e0),
+                   LMS("COL_v", lambda: R.dirichlet(col, 1, data.extra["col_v"]), weight=1e0)]
+    if data.consts["press_mode"] == "Collocation":
+        losses += [LMS("COL_p", lambda: R.dirichlet(pres, 2, data.extra["col_p"]), weight=1e0)]
+    if data.consts["press_mode"] == "Mean":
+        losses += [Loss("PRESS_0", lambda: R.mean_value(pres, 2), normalization=1e0, weight=1e-2, non_negative=True)]
+    loss_test = [LMS(f"{c}_fit", lambda i=i: R.dirichlet(test, i, data.sol_test[i])) for i, c in enumerate(("u", "v", "p"))]
+    return losses, loss_test
+
+
 def poisson(data: ProblemData, faithful: bool = True):
     """poisson.py:58-69 / poisson_misto.py:62-88"""
     pde = PointSet(data.x_pde, "PDE")
@@ -181,6 +203,7 @@ TABLES = {
     "colliding_flow": colliding_flow,
     "poiseuille_flow": poiseuille_flow,
     "coronary_flow": coronary_flow,
+    "colliding_flow_pressmean": colliding_flow_pressmean,
     "poisson": poisson,
     "poisson_misto": poisson,
 }

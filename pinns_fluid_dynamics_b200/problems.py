@@ -433,6 +433,43 @@ def poisson(mixed: bool = True, seed: int = 1, num_pde: int = 200, num_bc: int =
     return d
 
 
+def colliding_flow_pressmean(seed: int = 1, num_pde: int = 1000, num_bc: int = 100, num_col: int = 0, num_test: int = 1000,
+                             num_pres: int = 100, press_mode: str = "Mean", collocation: bool = False,
+                             use_noise: bool = False) -> ProblemData:
+    """Examples/Colliding_Flow/colliding_flow_pressmean.py:35-97,127-133: Stokes flow on (-1, 1)^2 with a 2-20x3-3
+    network, all point sets uniform random, normalisation by the maxima of |u|, |v|, |p| on the boundary points,
+    pressure fixed by ``press_mode``: "Mean" (ns.Loss over |mean p|), "Collocation" (fit p on x_pres) or "None"."""
+    if press_mode not in ("Mean", "Collocation", "None"):
+        raise ValueError("press_mode must be 'Mean', 'Collocation' or 'None'")
+    rng = np.random.default_rng(seed)
+    o = SimulationOptions(epochs=5000)
+    o.n_pts.update({"PDE": num_pde, "BC": num_bc, "Vel": num_col, "Pres": num_pres, "Test": num_test})
+    d = ProblemData("colliding_flow_pressmean", 2, [20, 20, 20], 3, o)
+    a, b = -1.0, 1.0
+    p_exact = lambda x: 60 * x[:, 0] ** 2 * x[:, 1] - 20 * x[:, 1] ** 3
+    u_exact = lambda x: 20 * x[:, 0] * x[:, 1] ** 3
+    v_exact = lambda x: 5 * x[:, 0] ** 4 - 5 * x[:, 1] ** 4
+    uni = lambda n, lo, hi: np.asarray(lo) + rng.random((n, 2)) * (np.asarray(hi, dtype=np.float64) - np.asarray(lo))
+    d.x_pde = uni(num_pde, [a, a], [b, b])
+    d.x_vel = uni(num_col, [a, a], [b, b])                           # x_col
+    edges = [uni(num_bc, [a, a], [a, b]), uni(num_bc, [b, a], [b, b]), uni(num_bc, [a, a], [b, a]), uni(num_bc, [a, b], [b, b])]
+    d.x_test = uni(num_test, [a, a], [b, b])
+    d.x_pres = uni(num_pres, [a, a], [b, b])
+    d = _round_all(d)
+    x_bcd = _f32(np.concatenate(edges, axis=0))                      # x0, x1, y0, y1 (:72-78)
+    vel_max = max(np.max(np.abs(u_exact(x_bcd))), np.max(np.abs(v_exact(x_bcd))))
+    p_max = np.max(np.abs(p_exact(x_bcd)))
+    d.consts = {"norm_vel": float(vel_max), "norm_pre": float(p_max), "press_mode": press_mode,
+                "collocation": bool(collocation)}
+    noise = (lambda: 1e-1 * rng.standard_normal(x_bcd.shape[0])) if use_noise else (lambda: 0.0)   # :127-133
+    d.extra = {"x_BCD": x_bcd,
+               "bcd_u": _f32((u_exact(x_bcd) + noise()) / vel_max), "bcd_v": _f32((v_exact(x_bcd) + noise()) / vel_max),
+               "col_u": _f32(u_exact(d.x_vel) / vel_max), "col_v": _f32(v_exact(d.x_vel) / vel_max),
+               "col_p": _f32(p_exact(d.x_pres) / p_max)}
+    d.sol_test = [_f32(u_exact(d.x_test) / vel_max), _f32(v_exact(d.x_test) / vel_max), _f32(p_exact(d.x_test) / p_max)]
+    return d
+
+
 BUILDERS: Dict[str, Callable[..., ProblemData]] = {
     "poisson": lambda **kw: poisson(mixed=False, **kw),
     "poisson_misto": lambda **kw: poisson(mixed=True, **kw),
@@ -441,6 +478,7 @@ BUILDERS: Dict[str, Callable[..., ProblemData]] = {
     "cavity_steady": cavity_steady,
     "cavity_unsteady": cavity_unsteady,
     "coronary_flow": coronary_flow,
+    "colliding_flow_pressmean": colliding_flow_pressmean,
 }
 
 # BASELINE.json configs: name -> builder kwargs

@@ -78,6 +78,7 @@ class ResidualForm:
     rhs: Optional[np.ndarray] = None
     rhs_scale: float = 1.0
     identically_zero: bool = False      # quirk Q1: logs 0.0, contributes no gradient
+    reduction: str = "mean_squares"     # "mean_squares": mean(r^2) (ns.LossMeanSquares); "abs_mean": |mean(r)| (ns.Loss)
     source: str = ""                    # reference closure this form restates (file:line)
 
     def deriv_order(self) -> int:
@@ -121,13 +122,14 @@ def dirichlet(pointset: PointSet, component: int, rhs=None) -> ResidualForm:
                         source="cavity_steady.py:192-194")
 
 
-def mass(pointset: PointSet, in_tape: bool = True) -> ResidualForm:
+def mass(pointset: PointSet, in_tape: bool = True, scale: float = 1.0) -> ResidualForm:
     """``PDE_MASS``: d_x N_0 + d_y N_1 on the normalised outputs (cavity_steady.py:159-166,
     cavity_unsteady.py:169-176).  ``in_tape=False`` restates Colliding_Flow / Poiseuille_Flow, where
     ``divergence(tape, u_vect, x, dim)`` runs after the tape closed (colliding_flow.py:160-165,
-    poiseuille_flow.py:173-178) and the term is identically zero (quirk Q1)."""
+    poiseuille_flow.py:173-178) and the term is identically zero (quirk Q1).  ``scale`` = vel_max restates the pressmean
+    variant's in-tape divergence of ``model(x)[:, 0:2] * vel_max`` (colliding_flow_pressmean.py:140-145)."""
     sx, sy = spatial_cols(pointset.dim)
-    return ResidualForm(pointset, {(0, ch_d(sx)): 1.0, (1, ch_d(sy)): 1.0},
+    return ResidualForm(pointset, {(0, ch_d(sx)): float(scale), (1, ch_d(sy)): float(scale)},
                         identically_zero=not in_tape, source="cavity_steady.py:159-166")
 
 
@@ -180,6 +182,22 @@ def outflow_stress(pointset: PointSet, k: int, normal, rhs, norm_vel: float, nor
             if normal[j] != 0:
                 coef[(k, ch_d(j))] = ni * norm_vel * float(normal[j])
     return ResidualForm(pointset, coef, rhs=rhs, rhs_scale=1.0, source="coronary_flow_steady.py:197-211")
+
+
+def stokes_momentum(pointset: PointSet, k: int, vel_max: float, p_max: float, forcing=None) -> ResidualForm:
+    """Pressmean variant ``PDE_MOM(x, k, force)``: -laplacian(vel_max*N_k) + d_k (p_max*N_2) - force(x)
+    (colliding_flow_pressmean.py:147-159; no convective term, no normalisation constant)."""
+    dim = pointset.dim
+    return ResidualForm(pointset, {(k, ch_dd(dim, 0)): -float(vel_max), (k, ch_dd(dim, 1)): -float(vel_max),
+                                   (2, ch_d(k)): float(p_max)}, rhs=forcing, rhs_scale=1.0,
+                        source="colliding_flow_pressmean.py:147-159")
+
+
+def mean_value(pointset: PointSet, component: int) -> ResidualForm:
+    """``PRESS_0(x)``: |mean(model(x)[:, component])| -- the scalar handed to ``ns.Loss``
+    (colliding_flow_pressmean.py:176-179,196).  The roots are N_component(x_n); the reduction is |mean|."""
+    return ResidualForm(pointset, {(component, ch_val()): 1.0}, reduction="abs_mean",
+                        source="colliding_flow_pressmean.py:176-179")
 
 
 def poisson_pde(pointset: PointSet, forcing) -> ResidualForm:

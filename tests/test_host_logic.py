@@ -74,6 +74,12 @@ def test_facade_rejects_closures_and_foreign_variables():
         ns.LossMeanSquares("x", lambda: torch.zeros(3))
     with pytest.raises(NotImplementedError):
         ns.Loss("PRESS_0", lambda: 0.0)
+    from pinns_fluid_dynamics_b200 import residuals as R
+    ps = R.PointSet(np.zeros((4, 2)))
+    with pytest.raises(NotImplementedError):       # ns.Loss takes the |mean| reduction only
+        ns.Loss("PRESS_0", lambda: R.dirichlet(ps, 2))
+    l = ns.Loss("PRESS_0", lambda: R.mean_value(ps, 2), normalization=1e0, weight=1e-2, non_negative=True)
+    assert (l.weight, l.normalization, l.non_negative, l.form.reduction) == (1e-2, 1.0, True, "abs_mean")
     loose = [v.clone() for v in model.variables]
     with pytest.raises(ValueError):
         ns.OptimizationProblem(loose, losses, ltest, engine_factory=TaylorEngine)

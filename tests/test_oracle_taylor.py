@@ -15,6 +15,7 @@ CORONARY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c
 
 CASES = {
     "coronary_flow": dict(geometry=CORONARY, PDE=200, BC=800, Vel=50, Pres=0, Test=40, noise_bnd=0.01, noise_fit=0.01),
+    "colliding_flow_pressmean": dict(num_pde=200, num_bc=30, num_test=40, num_pres=25),
     "poisson": dict(),
     "poisson_misto": dict(),
     "poiseuille_flow": dict(PDE=200, BC=30, Vel=10, Pres=0, Test=40),

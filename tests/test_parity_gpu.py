@@ -20,6 +20,7 @@ CORONARY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c
 
 SMALL = {
     "coronary_flow": dict(geometry=CORONARY, PDE=3000, BC=800, Vel=50, Pres=0, Test=1000, noise_bnd=0.01, noise_fit=0.01),
+    "colliding_flow_pressmean": dict(),
     "poisson": dict(),
     "poisson_misto": dict(),
     "poiseuille_flow": dict(PDE=1000, BC=100, Vel=10, Pres=0, Test=100),
@@ -385,3 +386,30 @@ def test_graph_replayed_training_steps_equal_eager_steps(monkeypatch):
     assert used_g and not used_e and t_g == t_e == 12
     assert torch.equal(x_g, x_e)
     assert torch.equal(s_g, s_e)
+
+
+@pytest.mark.parametrize("shift", [-0.7, 0.7])
+def test_abs_mean_term_takes_the_sign_of_the_mean(shift):
+    """ns.Loss('PRESS_0', |mean p|) (colliding_flow_pressmean.py:176-179,196): the sign of the mean comes from the forward
+    pre-pass inside pinn_loss_and_grad; both signs are forced through the output bias of p."""
+    from oracle import reference_step
+    data = problems.colliding_flow_pressmean(seed=2, num_pde=500, num_bc=50, num_test=100, num_pres=100)
+    var = reference_step.glorot_uniform_variables(data.dim, data.hidden, data.out_dim, seed=5, bias_std=0.1)
+    var[-1][2] = float(np.float32(shift))
+    model = ns.TanhMLP(data.dim, data.hidden, data.out_dim, device="cuda")
+    model.set_weights([v.numpy() for v in var])
+    losses, loss_test = loss_tables.build_loss_table(data)
+    pb = ns.OptimizationProblem(model.variables, losses, loss_test)
+    total, values, grad = pb.evaluate()
+    ref = reference_step.build(data, var)
+    ref_values, ref_total, ref_grad = ref.loss_and_grad()
+    names = [l.name for l in pb.losses]
+    i = names.index("PRESS_0")
+    assert names == [l.name for l in ref.losses]
+    assert ref_values[i] > 0.3 and _rel(values[i], ref_values[i]) < LOSS_RTOL
+    assert _rel(total, ref_total) < LOSS_RTOL
+    g, rg = grad.double().cpu().numpy(), ref_grad.numpy()
+    assert np.linalg.norm(g - rg) / np.linalg.norm(rg) < GRAD_RTOL
+    # d/d b_out[2] of w |mean p| is w sign(mean): the last gradient entry carries the sign
+    assert np.sign(g[-1]) == np.sign(rg[-1]) == np.sign(shift)
+    assert pb.plan.last_launch_count() >= 5      # pre-pass (kernel, finalize, sign) + main pass

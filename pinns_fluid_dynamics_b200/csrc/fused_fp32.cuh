@@ -27,6 +27,10 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef PINN_FUSED_MMA_WGRAD
+#define PINN_FUSED_MMA_WGRAD 1
+#endif
+
 namespace pinn {
 
 template <int D_, int H_, int L_, int O_, int ORDER_>
@@ -38,6 +42,9 @@ struct FusedCfg {
   static constexpr int RS = C * kChunk + 4;         // floats per neuron row of a jet buffer
   static constexpr int NBUF = L - 1;                // jet buffers: layers 2..L
   static constexpr int SX = D - 2, SY = D - 1;      // spatial input columns
+  // H = 32: the weight-gradient GEMM of the hidden layers runs on the warp-level tensor path (mma.sync m16n8k8, 3xTF32
+  // split) concurrently with the FFMA2 GEMMs of the other warps on the FMA pipe
+  static constexpr bool MMA_WGRAD = (H == 32) && (PINN_FUSED_MMA_WGRAD != 0);
   static_assert(H % 4 == 0, "width must be a multiple of 4");
   static_assert(L >= 3, "fused kernel needs >= 3 hidden layers (scratch aliasing)");
   // CTA-shared weights (floats)
@@ -316,6 +323,72 @@ __device__ __forceinline__ void warp_wgrad(const float* __restrict__ A, const fl
   }
 }
 
+// ---- the same weight-gradient GEMM on the warp-level tensor path (H = 32) ---------------------------------------
+// D[k][j] += sum_{c,p} A[k][c][p] * Z[j][c][p] as mma.sync.m16n8k8 (tf32 in, fp32 accumulate): M = k (2 tiles of 16),
+// N = j (4 tiles of 8), K = the C*16 contiguous (channel, point) entries of a jet row (2C steps of 8).  FP32 accuracy
+// comes from the 3-pass split x = hi + lo (hi = x rounded to tf32, lo = x - hi, which the tensor core truncates):
+// lo*hi + hi*lo + hi*hi.  The tensor core's FP32 accumulation truncates, so a chunk accumulates into fresh registers
+// (30-36 MMAs) and is then added to the running totals with FADD.
+// Fragment loads are bank-conflict free with RS = 16C+4: A/B element (row g, col t) sits at g*RS + t, RS mod 32 = 4 | 20.
+__device__ __forceinline__ void tf32_hi_lo(float x, unsigned& hi, unsigned& lo) {
+  hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_m16n8k8_tf32(float (&d)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// gK[m][n][.] : lane (g = lane>>2, t = lane&3) holds D[16m+g][8n+2t], [..][8n+2t+1], D[16m+g+8][8n+2t], [..][8n+2t+1]
+template <class Cfg>
+__device__ __forceinline__ void warp_wgrad_mma(const float* __restrict__ A, const float* __restrict__ Z,
+                                               float (&gK)[2][4][4], int g, int t) {
+  constexpr int C = Cfg::C, RS = Cfg::RS;
+  static_assert(Cfg::H == 32, "mma weight-gradient path is written for H = 32");
+  float d[2][4][4];
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) d[m][n][i] = 0.f;
+  const float* ap = A + g * RS + t;
+  const float* zp = Z + g * RS + t;
+#pragma unroll 2
+  for (int s = 0; s < 2 * C; ++s) {
+    unsigned ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      const float* q = ap + 16 * m * RS + 8 * s;
+      tf32_hi_lo(q[0], ah[m][0], al[m][0]);
+      tf32_hi_lo(q[8 * RS], ah[m][1], al[m][1]);
+      tf32_hi_lo(q[4], ah[m][2], al[m][2]);
+      tf32_hi_lo(q[8 * RS + 4], ah[m][3], al[m][3]);
+    }
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      const float* q = zp + 8 * n * RS + 8 * s;
+      tf32_hi_lo(q[0], bh[n][0], bl[n][0]);
+      tf32_hi_lo(q[4], bh[n][1], bl[n][1]);
+    }
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        mma_m16n8k8_tf32(d[m][n], al[m], bh[n]);
+        mma_m16n8k8_tf32(d[m][n], ah[m], bl[n]);
+        mma_m16n8k8_tf32(d[m][n], ah[m], bh[n]);
+      }
+  }
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) gK[m][n][i] += d[m][n][i];
+}
+
 __device__ __forceinline__ float reduce_over_lr(float v) {   // sum over the 8 row-lanes (same lc)
   v += __shfl_xor_sync(0xffffffffu, v, 4);
   v += __shfl_xor_sync(0xffffffffu, v, 8);
@@ -411,15 +484,19 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
   __syncwarp();
 
   float gK[NBUF][TI][TC];
-  float gb[NBUF][TC];
+  float gb[NBUF][TC];           // MMA_WGRAD: per-lane partial over the lane's own points, summed over lr at the end
+  float gKm[NBUF][2][4][4];     // MMA_WGRAD: weight-gradient totals in mma.sync accumulator layout
 #pragma unroll
-  for (int l = 0; l < NBUF; ++l)
+  for (int l = 0; l < NBUF; ++l) {
 #pragma unroll
     for (int jj = 0; jj < TC; ++jj) {
       gb[l][jj] = 0.f;
 #pragma unroll
       for (int ii = 0; ii < TI; ++ii) gK[l][ii][jj] = 0.f;
     }
+#pragma unroll
+    for (int q = 0; q < 32; ++q) gKm[l][q >> 4][(q >> 2) & 3][q & 3] = 0.f;
+  }
 
   for (int chunk = blockIdx.x * NW + warp; chunk < total_chunks; chunk += gridDim.x * NW) {
     int si = 0;
@@ -622,6 +699,7 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
             if (lr == 0) sg[Cfg::G_KO + j * 4 + o] += v;
           }
           tanh_jet2_bwd<Cfg, false>(aj, zdummy, ab, zb);
+          if constexpr (Cfg::MMA_WGRAD) gb[L - 2][jj] += zb[0].x + zb[0].y;      // bias gradient of layer L
 #pragma unroll
           for (int c = 0; c < C; ++c) *reinterpret_cast<float2*>(bufL + j * RS + c * kChunk + 2 * lr) = zb[c];
         }
@@ -639,7 +717,8 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
           write_a1_jets<Cfg>(Aprev, a1buf, sK1, lr, lc);
           __syncwarp();
         }
-        warp_wgrad<Cfg>(Aprev, Zl, gK[l - 2], gb[l - 2], lr, lc);
+        if constexpr (Cfg::MMA_WGRAD) warp_wgrad_mma<Cfg>(Aprev, Zl, gKm[l - 2], lr, lc);
+        else warp_wgrad<Cfg>(Aprev, Zl, gK[l - 2], gb[l - 2], lr, lc);
         float2 acc[C][TC];
 #pragma unroll
         for (int c = 0; c < C; ++c)
@@ -660,6 +739,7 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
               ab[c] = acc[c][jj];
             }
             tanh_jet2_bwd<Cfg, false>(aj, zdummy, ab, zb);
+            if constexpr (Cfg::MMA_WGRAD) gb[(l > 2) ? l - 3 : 0][jj] += zb[0].x + zb[0].y;   // bias gradient of layer l-1
 #pragma unroll
             for (int c = 0; c < C; ++c) *reinterpret_cast<float2*>(Aprev + j * RS + c * kChunk + 2 * lr) = zb[c];
           }
@@ -701,17 +781,32 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
     // dump the register accumulators into the (now idle) jet buffer of the warp, natural layout
     float* scr = buf;
 #pragma unroll
-    for (int l = 0; l < NBUF; ++l)
+    for (int l = 0; l < NBUF; ++l) {
+      if constexpr (Cfg::MMA_WGRAD) {
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+          for (int n = 0; n < 4; ++n)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              scr[l * H * H + (16 * m + lr + 8 * (i >> 1)) * H + 8 * n + 2 * lc + (i & 1)] = gKm[l][m][n][i];
+      }
 #pragma unroll
       for (int jj = 0; jj < TC; ++jj) {
         const int j = lc + 4 * jj;
+        if constexpr (Cfg::MMA_WGRAD) {
+          const float v = reduce_over_lr(gb[l][jj]);
+          if (lr == 0) scr[NBUF * H * H + l * H + j] = v;
+        } else {
 #pragma unroll
-        for (int ii = 0; ii < TI; ++ii) {
-          const int i = lr + 8 * ii;
-          if (i < H) scr[l * H * H + i * H + j] = gK[l][ii][jj];
+          for (int ii = 0; ii < TI; ++ii) {
+            const int i = lr + 8 * ii;
+            if (i < H) scr[l * H * H + i * H + j] = gK[l][ii][jj];
+          }
+          if (lr == 0) scr[NBUF * H * H + l * H + j] = gb[l][jj];
         }
-        if (lr == 0) scr[NBUF * H * H + l * H + j] = gb[l][jj];
       }
+    }
     __syncthreads();
     for (int idx = tid; idx < P; idx += nthr) {
       int off;   // offset inside a warp's private area

@@ -30,6 +30,9 @@
 #ifndef PINN_FUSED_MMA_WGRAD
 #define PINN_FUSED_MMA_WGRAD 1
 #endif
+#ifndef PINN_FUSED_MMA_GEMM
+#define PINN_FUSED_MMA_GEMM 1
+#endif
 
 namespace pinn {
 
@@ -45,11 +48,15 @@ struct FusedCfg {
   // H = 32: the weight-gradient GEMM of the hidden layers runs on the warp-level tensor path (mma.sync m16n8k8, 3xTF32
   // split) concurrently with the FFMA2 GEMMs of the other warps on the FMA pipe
   static constexpr bool MMA_WGRAD = (H == 32) && (PINN_FUSED_MMA_WGRAD != 0);
+  // ... and so do the forward / input-adjoint GEMMs (PINN_FUSED_MMA_GEMM): the lane's neurons become {8n + 2lc + e}
+  // (the mma.sync accumulator columns) instead of {lc + 4jj}; its points stay {2lr, 2lr+1}
+  static constexpr bool MMA = MMA_WGRAD && (PINN_FUSED_MMA_GEMM != 0);
+  static constexpr int WS = 36;                     // row stride of the hi / lo weight images (conflict-free B fragments)
   static_assert(H % 4 == 0, "width must be a multiple of 4");
   static_assert(L >= 3, "fused kernel needs >= 3 hidden layers (scratch aliasing)");
   // CTA-shared weights (floats)
-  static constexpr int W_K = (L - 1) * H * H;
-  static constexpr int W_KT = (L - 1) * H * H;
+  static constexpr int W_K = MMA ? (L - 1) * H * WS : (L - 1) * H * H;    // MMA: tf32 hi image of K_l, [k][WS]
+  static constexpr int W_KT = MMA ? (L - 1) * H * WS : (L - 1) * H * H;   // MMA: lo image
   static constexpr int W_K1 = D * H;
   static constexpr int W_B = L * H;
   static constexpr int W_KO = H * 4;
@@ -389,6 +396,52 @@ __device__ __forceinline__ void warp_wgrad_mma(const float* __restrict__ A, cons
       for (int i = 0; i < 4; ++i) gK[m][n][i] += d[m][n][i];
 }
 
+// Forward / input-adjoint GEMM of one hidden layer on the tensor path.  Per channel c an m16 tile of the warp's 16 points
+// (fragment rows g, g+8 <-> points 2g, 2g+1, so a lane keeps the two points it owns everywhere else), N = 4 tiles of 8
+// neurons, K = 4 steps of 8 with fragment columns (t, t+4) <-> k = 8ks + 2t, 8ks + 2t + 1 (conflict-free LDS.64 of the jet rows).
+//   TR = false:  d[c][n] += sum_k in[k][c][p] * K[k][8n + ..]        (forward,  B[k][j] = K[k][j])
+//   TR = true :  d[c][n] += sum_j in[j][c][p] * K[8n + ..][j]        (adjoint,  B[j][k] = K[k][j])
+// Wh / Wl: tf32 hi / lo images of K_l, row stride WS.  d[c][n][.]: (p=2g, col 2t), (2g, 2t+1), (2g+1, 2t), (2g+1, 2t+1).
+template <class Cfg, bool TR>
+__device__ __forceinline__ void warp_gemm_mma(const float* __restrict__ in, const float* __restrict__ Wh,
+                                              const float* __restrict__ Wl, float (&d)[Cfg::C][4][4], int g, int t) {
+  constexpr int C = Cfg::C, RS = Cfg::RS, WS = Cfg::WS;
+  const float* arow = in + 2 * g + 2 * t * RS;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    unsigned bh[4][2], bl[4][2];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      if constexpr (!TR) {
+        const int o = (8 * ks + 2 * t) * WS + 8 * n + g;
+        bh[n][0] = __float_as_uint(Wh[o]); bh[n][1] = __float_as_uint(Wh[o + WS]);
+        bl[n][0] = __float_as_uint(Wl[o]); bl[n][1] = __float_as_uint(Wl[o + WS]);
+      } else {
+        const int o = (8 * n + g) * WS + 8 * ks + 2 * t;
+        const float2 h = *reinterpret_cast<const float2*>(Wh + o), l = *reinterpret_cast<const float2*>(Wl + o);
+        bh[n][0] = __float_as_uint(h.x); bh[n][1] = __float_as_uint(h.y);
+        bl[n][0] = __float_as_uint(l.x); bl[n][1] = __float_as_uint(l.y);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float2 v0 = *reinterpret_cast<const float2*>(arow + 8 * ks * RS + c * kChunk);
+      const float2 v1 = *reinterpret_cast<const float2*>(arow + (8 * ks + 1) * RS + c * kChunk);
+      unsigned ah[4], al[4];
+      tf32_hi_lo(v0.x, ah[0], al[0]);
+      tf32_hi_lo(v0.y, ah[1], al[1]);
+      tf32_hi_lo(v1.x, ah[2], al[2]);
+      tf32_hi_lo(v1.y, ah[3], al[3]);
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        mma_m16n8k8_tf32(d[c][n], al, bh[n]);
+        mma_m16n8k8_tf32(d[c][n], ah, bl[n]);
+        mma_m16n8k8_tf32(d[c][n], ah, bh[n]);
+      }
+    }
+  }
+}
+
 __device__ __forceinline__ float reduce_over_lr(float v) {   // sum over the 8 row-lanes (same lc)
   v += __shfl_xor_sync(0xffffffffu, v, 4);
   v += __shfl_xor_sync(0xffffffffu, v, 8);
@@ -401,6 +454,12 @@ __device__ __forceinline__ float reduce_warp(float v) {
   return v;
 }
 
+// the jj-th neuron of lane group lc: FFMA path lc + 4jj; tensor path the accumulator columns 8n + 2lc + e (jj = 2n + e)
+template <class Cfg>
+__device__ __forceinline__ constexpr int neuron_of(int jj, int lc) {
+  return Cfg::MMA ? 8 * (jj >> 1) + 2 * lc + (jj & 1) : lc + 4 * jj;
+}
+
 // materialise the layer-1 a-jets of this lane's (2 points x TC neurons) from tanh(z1) in a1buf
 template <class Cfg>
 __device__ __forceinline__ void write_a1_jets(float* __restrict__ dst, const float* __restrict__ a1buf,
@@ -408,7 +467,7 @@ __device__ __forceinline__ void write_a1_jets(float* __restrict__ dst, const flo
   constexpr int C = Cfg::C, TC = Cfg::TC, D = Cfg::D, H = Cfg::H, RS = Cfg::RS;
 #pragma unroll
   for (int jj = 0; jj < TC; ++jj) {
-    const int j = lc + 4 * jj;
+    const int j = neuron_of<Cfg>(jj, lc);
     const float2 a0 = *reinterpret_cast<const float2*>(a1buf + j * kChunk + 2 * lr);
     float2 zd[D], a[C];
 #pragma unroll
@@ -456,12 +515,23 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
     for (int i = (int)(bulk_bytes / 4) + tid; i < P; i += nthr) raw[i] = __ldg(params + i);
     if (bulk_bytes) mbar_wait(bar, 0);
     __syncthreads();
-    for (int idx = tid; idx < Cfg::W_K; idx += nthr) {
-      const int l = idx / (H * H), k = (idx / H) % H, col = idx % H;
-      const int g = col / TC, t = col % TC;           // lane group / slot
-      const int j = g + 4 * t;
-      sK[idx] = raw[Cfg::offK(l + 2) + k * H + j];    // sK[l][k][g][t]  = K_l[k][g+4t]
-      sKT[idx] = raw[Cfg::offK(l + 2) + j * H + k];   // sKT[l][k][g][t] = K_l[g+4t][k]
+    if constexpr (Cfg::MMA) {
+      for (int idx = tid; idx < (L - 1) * H * H; idx += nthr) {     // tf32 hi / lo images of K_l, row stride WS
+        const int l = idx / (H * H), k = (idx / H) % H, j = idx % H;
+        const float w = raw[Cfg::offK(l + 2) + k * H + j];
+        unsigned hi, lo;
+        tf32_hi_lo(w, hi, lo);
+        sK[(l * H + k) * Cfg::WS + j] = __uint_as_float(hi);
+        sKT[(l * H + k) * Cfg::WS + j] = __uint_as_float(lo);
+      }
+    } else {
+      for (int idx = tid; idx < Cfg::W_K; idx += nthr) {
+        const int l = idx / (H * H), k = (idx / H) % H, col = idx % H;
+        const int g = col / TC, t = col % TC;           // lane group / slot
+        const int j = g + 4 * t;
+        sK[idx] = raw[Cfg::offK(l + 2) + k * H + j];    // sK[l][k][g][t]  = K_l[k][g+4t]
+        sKT[idx] = raw[Cfg::offK(l + 2) + j * H + k];   // sKT[l][k][g][t] = K_l[g+4t][k]
+      }
     }
     for (int idx = tid; idx < D * H; idx += nthr) sK1[idx] = raw[idx];
     for (int idx = tid; idx < L * H; idx += nthr) {
@@ -532,7 +602,7 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
     float* const bufL = buf + (NBUF - 1) * H * RS;
 #pragma unroll
     for (int jj = 0; jj < TC; ++jj) {
-      const int j = lc + 4 * jj;
+      const int j = neuron_of<Cfg>(jj, lc);
       float2 z = bc2(sB[j]);
 #pragma unroll
       for (int i = 0; i < D; ++i) z = fma2(make_float2(x0[i], x1[i]), bc2(sK1[i * H + j]), z);
@@ -552,18 +622,33 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
       const float* in = (l == 2) ? bufL : buf + (l - 3) * H * RS;
       float* out = buf + (l - 2) * H * RS;
       float2 acc[C][TC];
+      if constexpr (Cfg::MMA) {
+        float d[C][4][4];
 #pragma unroll
-      for (int jj = 0; jj < TC; ++jj) {
-        const float b = sB[(l - 1) * H + lc + 4 * jj];
-        acc[0][jj] = make_float2(b, b);
+        for (int c = 0; c < C; ++c)
 #pragma unroll
-        for (int c = 1; c < C; ++c) acc[c][jj] = make_float2(0.f, 0.f);
+          for (int n = 0; n < 4; ++n)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) d[c][n][i] = (c == 0) ? sB[(l - 1) * H + 8 * n + 2 * lc + (i & 1)] : 0.f;
+        warp_gemm_mma<Cfg, false>(in, sK + (l - 2) * H * Cfg::WS, sKT + (l - 2) * H * Cfg::WS, d, lr, lc);
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+#pragma unroll
+          for (int jj = 0; jj < TC; ++jj) acc[c][jj] = make_float2(d[c][jj >> 1][jj & 1], d[c][jj >> 1][2 + (jj & 1)]);
+      } else {
+#pragma unroll
+        for (int jj = 0; jj < TC; ++jj) {
+          const float b = sB[(l - 1) * H + lc + 4 * jj];
+          acc[0][jj] = make_float2(b, b);
+#pragma unroll
+          for (int c = 1; c < C; ++c) acc[c][jj] = make_float2(0.f, 0.f);
+        }
+        warp_gemm<Cfg>(in, sK + (l - 2) * H * H, acc, lr, lc);
       }
-      warp_gemm<Cfg>(in, sK + (l - 2) * H * H, acc, lr, lc);
       __syncwarp();   // all lanes finished reading `in` (it may alias `out`)
 #pragma unroll
       for (int jj = 0; jj < TC; ++jj) {
-        const int j = lc + 4 * jj;
+        const int j = neuron_of<Cfg>(jj, lc);
         float2 zd[D], a[C];
         float2 zxx = bc2(0.f), zyy = bc2(0.f);
 #pragma unroll
@@ -673,7 +758,7 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
         }
 #pragma unroll
         for (int jj = 0; jj < TC; ++jj) {
-          const int j = lc + 4 * jj;
+          const int j = neuron_of<Cfg>(jj, lc);
           float2 aj[C], ab[C], zb[C], zdummy[D];
 #pragma unroll
           for (int i = 0; i < D; ++i) zdummy[i] = bc2(0.f);
@@ -720,16 +805,31 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
         if constexpr (Cfg::MMA_WGRAD) warp_wgrad_mma<Cfg>(Aprev, Zl, gKm[l - 2], lr, lc);
         else warp_wgrad<Cfg>(Aprev, Zl, gK[l - 2], gb[l - 2], lr, lc);
         float2 acc[C][TC];
+        if constexpr (Cfg::MMA) {
+          float d[C][4][4];
 #pragma unroll
-        for (int c = 0; c < C; ++c)
+          for (int c = 0; c < C; ++c)
 #pragma unroll
-          for (int jj = 0; jj < TC; ++jj) acc[c][jj] = make_float2(0.f, 0.f);
-        warp_gemm<Cfg>(Zl, sKT + (l - 2) * H * H, acc, lr, lc);
+            for (int n = 0; n < 4; ++n)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) d[c][n][i] = 0.f;
+          warp_gemm_mma<Cfg, true>(Zl, sK + (l - 2) * H * Cfg::WS, sKT + (l - 2) * H * Cfg::WS, d, lr, lc);
+#pragma unroll
+          for (int c = 0; c < C; ++c)
+#pragma unroll
+            for (int jj = 0; jj < TC; ++jj) acc[c][jj] = make_float2(d[c][jj >> 1][jj & 1], d[c][jj >> 1][2 + (jj & 1)]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < C; ++c)
+#pragma unroll
+            for (int jj = 0; jj < TC; ++jj) acc[c][jj] = make_float2(0.f, 0.f);
+          warp_gemm<Cfg>(Zl, sKT + (l - 2) * H * H, acc, lr, lc);
+        }
         __syncwarp();
         if (l > 2) {
 #pragma unroll
           for (int jj = 0; jj < TC; ++jj) {
-            const int j = lc + 4 * jj;
+            const int j = neuron_of<Cfg>(jj, lc);
             float2 aj[C], ab[C], zb[C], zdummy[D];
 #pragma unroll
             for (int i = 0; i < D; ++i) zdummy[i] = bc2(0.f);
@@ -748,7 +848,7 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
           // layer 1: z-bar stays in registers; K1 / b1 gradients via shuffle reduction
 #pragma unroll
           for (int jj = 0; jj < TC; ++jj) {
-            const int j = lc + 4 * jj;
+            const int j = neuron_of<Cfg>(jj, lc);
             float2 aj[C], ab[C], zb[C], zd[D];
             aj[0] = *reinterpret_cast<const float2*>(a1buf + j * kChunk + 2 * lr);
 #pragma unroll
@@ -793,7 +893,7 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
       }
 #pragma unroll
       for (int jj = 0; jj < TC; ++jj) {
-        const int j = lc + 4 * jj;
+        const int j = neuron_of<Cfg>(jj, lc);
         if constexpr (Cfg::MMA_WGRAD) {
           const float v = reduce_over_lr(gb[l][jj]);
           if (lr == 0) scr[NBUF * H * H + l * H + j] = v;

@@ -26,12 +26,16 @@
 //     writes ONE row of the workspace; a finalize kernel sums the rows (no atomics anywhere).
 #pragma once
 #include "common.cuh"
+#include "umma.cuh"
 
 #ifndef PINN_FUSED_MMA_WGRAD
 #define PINN_FUSED_MMA_WGRAD 1
 #endif
 #ifndef PINN_FUSED_MMA_GEMM
 #define PINN_FUSED_MMA_GEMM 1
+#endif
+#ifndef PINN_FUSED_TMEM_TOTALS
+#define PINN_FUSED_TMEM_TOTALS 1
 #endif
 
 namespace pinn {
@@ -52,6 +56,10 @@ struct FusedCfg {
   // (the mma.sync accumulator columns) instead of {lc + 4jj}; its points stay {2lr, 2lr+1}
   static constexpr bool MMA = MMA_WGRAD && (PINN_FUSED_MMA_GEMM != 0);
   static constexpr int WS = 36;                     // row stride of the hi / lo weight images (conflict-free B fragments)
+  // the running weight-gradient totals (64 registers per lane) live in tensor memory: one 32-column block per warp and
+  // layer, read-modify-written once per chunk with tcgen05.ld / tcgen05.st -- the registers go to the tanh-jet phases
+  static constexpr bool TMEM_TOTALS = MMA_WGRAD && (PINN_FUSED_TMEM_TOTALS != 0);
+  static constexpr int TMEM_COLS = 128;             // 2 warps per lane quadrant x (L-1 = 2) layers x 32 columns
   static_assert(H % 4 == 0, "width must be a multiple of 4");
   static_assert(L >= 3, "fused kernel needs >= 3 hidden layers (scratch aliasing)");
   // CTA-shared weights (floats)
@@ -342,15 +350,41 @@ __device__ __forceinline__ void tf32_hi_lo(float x, unsigned& hi, unsigned& lo) 
   lo = __float_as_uint(x - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma_m16n8k8_tf32(float (&d)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// tensor memory as accumulator storage: thread i of a warp owns lane (32*(warp%4) + i), columns [col, col+32)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]),
+        "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]), "=f"(v[17]), "=f"(v[18]),
+        "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]),
+        "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n\t"
+      "tcgen05.wait::st.sync.aligned;"
+      :: "r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]),
+        "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]), "f"(v[16]), "f"(v[17]), "f"(v[18]),
+        "f"(v[19]), "f"(v[20]), "f"(v[21]), "f"(v[22]), "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]),
+        "f"(v[28]), "f"(v[29]), "f"(v[30]), "f"(v[31])
+      : "memory");
 }
 
 // gK[m][n][.] : lane (g = lane>>2, t = lane&3) holds D[16m+g][8n+2t], [..][8n+2t+1], D[16m+g+8][8n+2t], [..][8n+2t+1]
 template <class Cfg>
 __device__ __forceinline__ void warp_wgrad_mma(const float* __restrict__ A, const float* __restrict__ Z,
-                                               float (&gK)[2][4][4], int g, int t) {
+                                               float (&gK)[2][4][4], uint32_t tmem_totals, int g, int t) {
   constexpr int C = Cfg::C, RS = Cfg::RS;
   static_assert(Cfg::H == 32, "mma weight-gradient path is written for H = 32");
   float d[2][4][4];
@@ -379,21 +413,34 @@ __device__ __forceinline__ void warp_wgrad_mma(const float* __restrict__ A, cons
       tf32_hi_lo(q[0], bh[n][0], bl[n][0]);
       tf32_hi_lo(q[4], bh[n][1], bl[n][1]);
     }
+    // pass-major: the 8 accumulators are independent, the three passes of one accumulator are 8 MMAs apart
 #pragma unroll
     for (int m = 0; m < 2; ++m)
 #pragma unroll
-      for (int n = 0; n < 4; ++n) {
-        mma_m16n8k8_tf32(d[m][n], al[m], bh[n]);
-        mma_m16n8k8_tf32(d[m][n], ah[m], bl[n]);
-        mma_m16n8k8_tf32(d[m][n], ah[m], bh[n]);
-      }
+      for (int n = 0; n < 4; ++n) mma_m16n8k8_tf32(d[m][n], al[m], bh[n]);
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int n = 0; n < 4; ++n) mma_m16n8k8_tf32(d[m][n], ah[m], bl[n]);
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int n = 0; n < 4; ++n) mma_m16n8k8_tf32(d[m][n], ah[m], bh[n]);
   }
+  if constexpr (Cfg::TMEM_TOTALS) {
+    float tot[32];
+    tmem_ld32(tmem_totals, tot);
 #pragma unroll
-  for (int m = 0; m < 2; ++m)
+    for (int q = 0; q < 32; ++q) tot[q] += d[q >> 4][(q >> 2) & 3][q & 3];
+    tmem_st32(tmem_totals, tot);
+  } else {
 #pragma unroll
-    for (int n = 0; n < 4; ++n)
+    for (int m = 0; m < 2; ++m)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) gK[m][n][i] += d[m][n][i];
+      for (int n = 0; n < 4; ++n)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) gK[m][n][i] += d[m][n][i];
+  }
 }
 
 // Forward / input-adjoint GEMM of one hidden layer on the tensor path.  Per channel c an m16 tile of the warp's 16 points
@@ -433,11 +480,11 @@ __device__ __forceinline__ void warp_gemm_mma(const float* __restrict__ in, cons
       tf32_hi_lo(v1.x, ah[2], al[2]);
       tf32_hi_lo(v1.y, ah[3], al[3]);
 #pragma unroll
-      for (int n = 0; n < 4; ++n) {
-        mma_m16n8k8_tf32(d[c][n], al, bh[n]);
-        mma_m16n8k8_tf32(d[c][n], ah, bl[n]);
-        mma_m16n8k8_tf32(d[c][n], ah, bh[n]);
-      }
+      for (int n = 0; n < 4; ++n) mma_m16n8k8_tf32(d[c][n], al, bh[n]);
+#pragma unroll
+      for (int n = 0; n < 4; ++n) mma_m16n8k8_tf32(d[c][n], ah, bl[n]);
+#pragma unroll
+      for (int n = 0; n < 4; ++n) mma_m16n8k8_tf32(d[c][n], ah, bh[n]);
     }
   }
 }
@@ -544,6 +591,24 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
     }
     if (tid < 4) sBo[tid] = (tid < O) ? raw[Cfg::OFF_BO + tid] : 0.f;
     __syncthreads();
+  }
+
+  // tensor memory for the running weight-gradient totals (TRAIN): warp w owns lanes 32*(w%4).., columns 64*(w/4)..+64
+  uint32_t tmem_base = 0, tmem_w = 0;
+  if constexpr (TRAIN && Cfg::TMEM_TOTALS) {
+    static_assert(NW <= 8 && NBUF == 2, "tensor-memory layout of the totals assumes <= 8 warps and 2 hidden-hidden layers");
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 1);
+    if (warp == 0) umma::tmem_alloc<Cfg::TMEM_COLS>(tslot);
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    umma::fence_after_thread_sync();
+    tmem_base = *tslot;
+    tmem_w = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + 64u * (uint32_t)(warp >> 2);
+    float zero[32];
+#pragma unroll
+    for (int q = 0; q < 32; ++q) zero[q] = 0.f;
+    tmem_st32(tmem_w, zero);
+    tmem_st32(tmem_w + 32u, zero);
   }
 
   float* buf = warp_base + warp * Cfg::PW_TOTAL;
@@ -802,7 +867,7 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
           write_a1_jets<Cfg>(Aprev, a1buf, sK1, lr, lc);
           __syncwarp();
         }
-        if constexpr (Cfg::MMA_WGRAD) warp_wgrad_mma<Cfg>(Aprev, Zl, gKm[l - 2], lr, lc);
+        if constexpr (Cfg::MMA_WGRAD) warp_wgrad_mma<Cfg>(Aprev, Zl, gKm[l - 2], tmem_w + 32u * (uint32_t)(l - 2), lr, lc);
         else warp_wgrad<Cfg>(Aprev, Zl, gK[l - 2], gb[l - 2], lr, lc);
         float2 acc[C][TC];
         if constexpr (Cfg::MMA) {
@@ -882,6 +947,12 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
     float* scr = buf;
 #pragma unroll
     for (int l = 0; l < NBUF; ++l) {
+      if constexpr (Cfg::TMEM_TOTALS) {
+        float tot[32];
+        tmem_ld32(tmem_w + 32u * (uint32_t)l, tot);
+#pragma unroll
+        for (int q = 0; q < 32; ++q) gKm[l][q >> 4][(q >> 2) & 3][q & 3] = tot[q];
+      }
       if constexpr (Cfg::MMA_WGRAD) {
 #pragma unroll
         for (int m = 0; m < 2; ++m)
@@ -931,6 +1002,11 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
 #pragma unroll
     for (int w = 0; w < NW; ++w) s += warp_base[w * Cfg::PW_TOTAL + Cfg::PW_BUF + Cfg::PW_A1 + Cfg::PW_G + t];
     row[ws_stride - n_terms_total + t] = s;
+  }
+  if constexpr (TRAIN && Cfg::TMEM_TOTALS) {
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 

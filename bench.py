@@ -226,6 +226,7 @@ def run_ours(args):
     flop_launch = n_local_pde * flops_per_point(d, H, L, O, C)
     achieved = flop_launch / (k_ms * 1e-3) * 1e-12
     traffic = None
+    extra = {}
     if plan.engine == "layered_tf32x3":
         # hidden-layer contractions on tcgen05 kind::tf32, 3 MMA passes per algorithmic product (hi/lo split)
         bound, peak, peak_src = "tensor", 368.4, "fallback"
@@ -241,6 +242,34 @@ def run_ours(args):
             pass
         try:
             with open(os.path.join(ROOT, "profiles", "ncu_traffic_tc_r01.json")) as fh:
+                traffic = json.load(fh)["dram_bytes_per_point"] * n_local_pde
+        except Exception:
+            pass
+    elif plan.engine == "fused_tf32x3":
+        # hidden-layer GEMMs (97 % of the algorithmic flops) on the warp-level tensor path, 3 mma.sync passes per product;
+        # `peak` is the chip's tensor roofline for 3xTF32 (tcgen05 rate / 3); the path the kernel actually uses
+        # (mma.sync.m16n8k8, tools/mma_sync_probe.cu) tops out lower -- both fractions are reported
+        bound, peak, peak_src = "tensor", 368.4, "fallback"
+        kernel_name = "fused_step_kernel<D,H,L,O,ORDER=2,TRAIN> (mma.sync m16n8k8 tf32 x3 GEMMs, FFMA2 tanh-jet math)"
+        extra = {}
+        try:
+            with open(os.path.join(ROOT, "profiles", "tf32_peak_r01.json")) as fh:
+                pk = json.load(fh)
+            peak = pk["tf32_mma_tflops_n256"] / pk["passes_per_product"]
+            peak_src = ("profiles/tf32_peak_r01.json: measured tcgen05 kind::tf32 MMA rate (tools/tc_probe.cu) / 3 passes; "
+                        "MEASURED_PEAKS.json holds no TF32 figure")
+            with open(os.path.join(ROOT, "profiles", "mma_sync_peak_r01.json")) as fh:
+                wk = json.load(fh)
+            with open(os.path.join(ROOT, "profiles", "fp32_peak_r01.json")) as fh:
+                fk = json.load(fh)
+            extra = {"warp_level_path_peak": wk["tf32_m16n8k8_tflops"] / 3.0,
+                     "frac_of_warp_level_path": achieved / (wk["tf32_m16n8k8_tflops"] / 3.0),
+                     "fp32_fma_peak": max(fk["ffma_chain_tflops"], fk["ffma2_chain_tflops"]),
+                     "vs_fp32_fma_peak": achieved / max(fk["ffma_chain_tflops"], fk["ffma2_chain_tflops"])}
+        except Exception:
+            pass
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")) as fh:
                 traffic = json.load(fh)["dram_bytes_per_point"] * n_local_pde
         except Exception:
             pass
@@ -295,7 +324,8 @@ def run_ours(args):
         line = {
             "metric": "collocation_points_per_second_per_training_step", "value": value, "unit": "pts/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (3xtf32 tensor-core products, fp32 accumulate)" if plan.engine.endswith("tf32x3") else "f32", "data": "synthetic",
             "config": {"workload": f"{args.config}: {per_gpu} uniform collocation points per GPU ({n_global_pde} total), "
                                    f"{data.options.n_pts['BC']}x4 boundary, {data.options.n_pts['Vel']} velocity + "
                                    f"{data.options.n_pts['Pres']} pressure fitting points, tanh MLP "
@@ -309,7 +339,7 @@ def run_ours(args):
                          "traffic": traffic, "kernel": kernel_name, "kernel_ms": k_ms,
                          "flop_per_point": flops_per_point(d, H, L, O, C), "points_per_launch": n_local_pde,
                          "peak_source": peak_src,
-                         "hbm_GBps": (n_local_pde * 4 * d) / (k_ms * 1e-3) * 1e-9},
+                         "hbm_GBps": (n_local_pde * 4 * d) / (k_ms * 1e-3) * 1e-9, **extra},
             "cpu_baseline": cpu,
             "clocks": sampler.summary(),
         }

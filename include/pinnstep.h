@@ -126,7 +126,7 @@ int pinn_plan_destroy(pinn_plan* plan);
 int64_t pinn_plan_param_count(const pinn_plan* plan);
 int32_t pinn_plan_term_count(const pinn_plan* plan);
 size_t pinn_plan_workspace_bytes(const pinn_plan* plan);
-/* Name of the engine chosen for the plan's networks: "fused_fp32" | "layered_fp32" | "layered_tf32x3". */
+/* Name of the engine chosen for the plan's networks: "fused_fp32" | "fused_tf32x3" | "layered_fp32" | "layered_tf32x3". */
 const char* pinn_plan_engine(const pinn_plan* plan);
 /* Kernel launches enqueued by the last pinn_loss_and_grad / pinn_loss call. */
 int32_t pinn_plan_last_launch_count(const pinn_plan* plan);

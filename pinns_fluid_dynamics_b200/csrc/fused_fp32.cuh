@@ -34,6 +34,9 @@
 #ifndef PINN_FUSED_MMA_GEMM
 #define PINN_FUSED_MMA_GEMM 1
 #endif
+#ifndef PINN_FUSED_SPLIT_TRUNC
+#define PINN_FUSED_SPLIT_TRUNC 0
+#endif
 #ifndef PINN_FUSED_TMEM_TOTALS
 #define PINN_FUSED_TMEM_TOTALS 1
 #endif
@@ -346,8 +349,13 @@ __device__ __forceinline__ void warp_wgrad(const float* __restrict__ A, const fl
 // (30-36 MMAs) and is then added to the running totals with FADD.
 // Fragment loads are bank-conflict free with RS = 16C+4: A/B element (row g, col t) sits at g*RS + t, RS mod 32 = 4 | 20.
 __device__ __forceinline__ void tf32_hi_lo(float x, unsigned& hi, unsigned& lo) {
+#if PINN_FUSED_SPLIT_TRUNC
+  hi = __float_as_uint(x);                               // the tensor core reads the top 19 bits
+  lo = __float_as_uint(x - __uint_as_float(hi & 0xFFFFE000u));
+#else
   hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
   lo = __float_as_uint(x - __uint_as_float(hi));
+#endif
 }
 __device__ __forceinline__ void mma_m16n8k8_tf32(float (&d)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
   asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"

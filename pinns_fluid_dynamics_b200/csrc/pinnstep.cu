@@ -520,7 +520,7 @@ extern "C" int pinn_plan_create(const pinn_mlp_desc* mlp, const pinn_pointset_de
       if (kind == PINN_TERM_ABS_MEAN) {
         if (!use_fused) {
           delete p;
-          return fail(PINN_E_INVALID, "|mean| terms (PINN_TERM_ABS_MEAN) are served by the fused_fp32 engine only");
+          return fail(PINN_E_INVALID, "|mean| terms (PINN_TERM_ABS_MEAN) are served by the fused engines only");
         }
         p->has_abs_mean = p->has_abs_mean || sets[s].terms[t].train;
       }
@@ -569,6 +569,8 @@ extern "C" int pinn_plan_create(const pinn_mlp_desc* mlp, const pinn_pointset_de
     *out = p;
     return PINN_OK;
   }
+  // H = 32: hidden-layer GEMMs on the warp-level tensor path (3xTF32), see fused_fp32.cuh
+  if (mlp->width == 32 && pinn::FusedCfg<2, 32, 3, 3, 2>::MMA) p->engine = "fused_tf32x3";
   p->rows_max = 3 * p->num_sms;
   p->ws_bytes = (size_t)p->rows_max * (size_t)(p->P + p->T) * sizeof(float);
   if (cudaMalloc(&p->ws, p->ws_bytes) != cudaSuccess) {

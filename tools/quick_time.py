@@ -24,14 +24,14 @@ for _ in range(3):
     pb.plan.loss_and_grad(pb.flat)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-K = 20 if pb.plan.engine == 'fused_fp32' else 3
+K = 20 if pb.plan.engine.startswith('fused') else 3
 e0.record()
 for _ in range(K):
     pb.plan.loss_and_grad(pb.flat)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / K
 kms = C.c_float()
-if pb.plan.engine == "fused_fp32":
+if pb.plan.engine.startswith("fused"):
     lib.pinn_plan_kernel_time_ms(pb.plan.handle, 2, C.byref(kms))
 else:
     kms.value = ms

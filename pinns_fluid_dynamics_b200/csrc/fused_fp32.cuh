@@ -34,6 +34,9 @@
 #ifndef PINN_FUSED_MMA_GEMM
 #define PINN_FUSED_MMA_GEMM 1
 #endif
+#ifndef PINN_FUSED_SPLIT_CVT
+#define PINN_FUSED_SPLIT_CVT 0
+#endif
 #ifndef PINN_FUSED_SPLIT_TRUNC
 #define PINN_FUSED_SPLIT_TRUNC 0
 #endif
@@ -352,6 +355,9 @@ __device__ __forceinline__ void tf32_hi_lo(float x, unsigned& hi, unsigned& lo) 
 #if PINN_FUSED_SPLIT_TRUNC
   hi = __float_as_uint(x);                               // the tensor core reads the top 19 bits
   lo = __float_as_uint(x - __uint_as_float(hi & 0xFFFFE000u));
+#elif PINN_FUSED_SPLIT_CVT
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  lo = __float_as_uint(x - __uint_as_float(hi));
 #else
   hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
   lo = __float_as_uint(x - __uint_as_float(hi));

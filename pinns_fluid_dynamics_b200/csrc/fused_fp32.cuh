@@ -34,6 +34,15 @@
 #ifndef PINN_FUSED_MMA_GEMM
 #define PINN_FUSED_MMA_GEMM 1
 #endif
+#ifndef PINN_FUSED_LO_RNA
+#define PINN_FUSED_LO_RNA 1
+#endif
+#ifndef PINN_FUSED_KSTEP_DRAIN
+#define PINN_FUSED_KSTEP_DRAIN 1
+#endif
+#ifndef PINN_FUSED_MAX_WARPS
+#define PINN_FUSED_MAX_WARPS 8       // experiments: fewer warps per CTA (latency vs contention)
+#endif
 #ifndef PINN_FUSED_SPLIT_CVT
 #define PINN_FUSED_SPLIT_CVT 0
 #endif
@@ -65,7 +74,8 @@ struct FusedCfg {
   // the running weight-gradient totals (64 registers per lane) live in tensor memory: one 32-column block per warp and
   // layer, read-modify-written once per chunk with tcgen05.ld / tcgen05.st -- the registers go to the tanh-jet phases
   static constexpr bool TMEM_TOTALS = MMA_WGRAD && (PINN_FUSED_TMEM_TOTALS != 0);
-  static constexpr int TMEM_COLS = 128;             // 2 warps per lane quadrant x (L-1 = 2) layers x 32 columns
+  static constexpr int TMEM_COLS = 256;             // 2 warps per lane quadrant x 128: (L-1 = 2) layers x 32 columns of weight-
+                                                    // gradient totals at +0, 2 x 8 columns of bias-gradient partials at +64
   static_assert(H % 4 == 0, "width must be a multiple of 4");
   static_assert(L >= 3, "fused kernel needs >= 3 hidden layers (scratch aliasing)");
   // CTA-shared weights (floats)
@@ -87,7 +97,7 @@ struct FusedCfg {
   static constexpr int PW_TOTAL = PW_BUF + PW_A1 + PW_G + PW_SQ;
   static constexpr int kSmemMax = 232448;           // 227 KB opt-in limit per CTA on sm_100
   static constexpr int NW_FIT = (kSmemMax - W_TOTAL * 4) / (PW_TOTAL * 4);
-  static constexpr int NW = NW_FIT > 8 ? 8 : NW_FIT;
+  static constexpr int NW = NW_FIT > PINN_FUSED_MAX_WARPS ? PINN_FUSED_MAX_WARPS : NW_FIT;
   static_assert(NW >= 2, "configuration does not fit shared memory");
   static constexpr int SMEM_BYTES = (W_TOTAL + NW * PW_TOTAL) * 4;
   static constexpr int P = D * H + H + (L - 1) * (H * H + H) + H * O + O;
@@ -361,6 +371,9 @@ __device__ __forceinline__ void tf32_hi_lo(float x, unsigned& hi, unsigned& lo) 
 #else
   hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
   lo = __float_as_uint(x - __uint_as_float(hi));
+#if PINN_FUSED_LO_RNA
+  lo += 0x1000u;      // the tensor core truncates the low 13 bits: adding half an ulp first makes that a round-to-nearest
+#endif                // (without it every product is biased towards zero by ~2^-24, which adds up over the layers)
 #endif
 }
 __device__ __forceinline__ void mma_m16n8k8_tf32(float (&d)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
@@ -393,6 +406,23 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) 
         "f"(v[19]), "f"(v[20]), "f"(v[21]), "f"(v[22]), "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]),
         "f"(v[28]), "f"(v[29]), "f"(v[30]), "f"(v[31])
       : "memory");
+}
+
+__device__ __forceinline__ void tmem_add8(uint32_t taddr, const float (&v)[8]) {      // [taddr .. +8) += v
+  float t[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\t"
+               "tcgen05.wait::ld.sync.aligned;"
+               : "=f"(t[0]), "=f"(t[1]), "=f"(t[2]), "=f"(t[3]), "=f"(t[4]), "=f"(t[5]), "=f"(t[6]), "=f"(t[7]) : "r"(taddr) : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t[i] += v[i];
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n\t"
+               "tcgen05.wait::st.sync.aligned;"
+               :: "r"(taddr), "f"(t[0]), "f"(t[1]), "f"(t[2]), "f"(t[3]), "f"(t[4]), "f"(t[5]), "f"(t[6]), "f"(t[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&t)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\t"
+               "tcgen05.wait::ld.sync.aligned;"
+               : "=f"(t[0]), "=f"(t[1]), "=f"(t[2]), "=f"(t[3]), "=f"(t[4]), "=f"(t[5]), "=f"(t[6]), "=f"(t[7]) : "r"(taddr) : "memory");
 }
 
 // gK[m][n][.] : lane (g = lane>>2, t = lane&3) holds D[16m+g][8n+2t], [..][8n+2t+1], D[16m+g+8][8n+2t], [..][8n+2t+1]
@@ -493,12 +523,33 @@ __device__ __forceinline__ void warp_gemm_mma(const float* __restrict__ in, cons
       tf32_hi_lo(v0.y, ah[1], al[1]);
       tf32_hi_lo(v1.x, ah[2], al[2]);
       tf32_hi_lo(v1.y, ah[3], al[3]);
+#if PINN_FUSED_KSTEP_DRAIN
+      // the tensor core truncates when it adds into its accumulator: the three passes of ONE k-step go into a fresh
+      // accumulator (small lo-terms first, so only the final hi*hi addition sees a full-magnitude sum) and the k-steps
+      // are joined in FP32 with round-to-nearest FADDs on the otherwise idle FMA pipe
+      float tacc[4][4];
+#pragma unroll
+      for (int n = 0; n < 4; ++n)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tacc[n][i] = 0.f;
+#pragma unroll
+      for (int n = 0; n < 4; ++n) mma_m16n8k8_tf32(tacc[n], al, bh[n]);
+#pragma unroll
+      for (int n = 0; n < 4; ++n) mma_m16n8k8_tf32(tacc[n], ah, bl[n]);
+#pragma unroll
+      for (int n = 0; n < 4; ++n) mma_m16n8k8_tf32(tacc[n], ah, bh[n]);
+#pragma unroll
+      for (int n = 0; n < 4; ++n)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[c][n][i] += tacc[n][i];
+#else
 #pragma unroll
       for (int n = 0; n < 4; ++n) mma_m16n8k8_tf32(d[c][n], al, bh[n]);
 #pragma unroll
       for (int n = 0; n < 4; ++n) mma_m16n8k8_tf32(d[c][n], ah, bl[n]);
 #pragma unroll
       for (int n = 0; n < 4; ++n) mma_m16n8k8_tf32(d[c][n], ah, bh[n]);
+#endif
     }
   }
 }
@@ -610,19 +661,20 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
   // tensor memory for the running weight-gradient totals (TRAIN): warp w owns lanes 32*(w%4).., columns 64*(w/4)..+64
   uint32_t tmem_base = 0, tmem_w = 0;
   if constexpr (TRAIN && Cfg::TMEM_TOTALS) {
-    static_assert(NW <= 8 && NBUF == 2, "tensor-memory layout of the totals assumes <= 8 warps and 2 hidden-hidden layers");
+    static_assert(NW <= 8 && NBUF == 2 && TC == 8, "tensor-memory layout of the totals assumes <= 8 warps and 2 hidden-hidden layers");
     uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 1);
     if (warp == 0) umma::tmem_alloc<Cfg::TMEM_COLS>(tslot);
     umma::fence_before_thread_sync();
     __syncthreads();
     umma::fence_after_thread_sync();
     tmem_base = *tslot;
-    tmem_w = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + 64u * (uint32_t)(warp >> 2);
+    tmem_w = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + 128u * (uint32_t)(warp >> 2);
     float zero[32];
 #pragma unroll
     for (int q = 0; q < 32; ++q) zero[q] = 0.f;
     tmem_st32(tmem_w, zero);
     tmem_st32(tmem_w + 32u, zero);
+    tmem_st32(tmem_w + 64u, zero);       // bias-gradient partials (16 of these 32 columns are used)
   }
 
   float* buf = warp_base + warp * Cfg::PW_TOTAL;
@@ -829,6 +881,7 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
     if constexpr (TRAIN) {
       // ---- output layer backward + tanh-jet backward of layer L (in place in B(L)) ------------
       {
+        float gbl[8];   // this chunk's bias-gradient partials of the lane's neurons (lane's own two points)
         // b_out gradient: sum over the warp's points of Jb[0][o] (identical in the 4 neuron-lanes)
 #pragma unroll
         for (int o = 0; o < O; ++o) {
@@ -863,9 +916,15 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
             if (lr == 0) sg[Cfg::G_KO + j * 4 + o] += v;
           }
           tanh_jet2_bwd<Cfg, false>(aj, zdummy, ab, zb);
-          if constexpr (Cfg::MMA_WGRAD) gb[L - 2][jj] += zb[0].x + zb[0].y;      // bias gradient of layer L
+          if constexpr (Cfg::MMA_WGRAD) gbl[jj] = zb[0].x + zb[0].y;            // bias gradient of layer L
 #pragma unroll
           for (int c = 0; c < C; ++c) *reinterpret_cast<float2*>(bufL + j * RS + c * kChunk + 2 * lr) = zb[c];
+        }
+        if constexpr (Cfg::TMEM_TOTALS) {
+          tmem_add8(tmem_w + 64u + 8u * (uint32_t)(L - 2), gbl);
+        } else if constexpr (Cfg::MMA_WGRAD) {
+#pragma unroll
+          for (int jj = 0; jj < TC; ++jj) gb[L - 2][jj] += gbl[jj];
         }
         __syncwarp();
       }
@@ -906,6 +965,7 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
         }
         __syncwarp();
         if (l > 2) {
+          float gbl[8];
 #pragma unroll
           for (int jj = 0; jj < TC; ++jj) {
             const int j = neuron_of<Cfg>(jj, lc);
@@ -918,9 +978,15 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
               ab[c] = acc[c][jj];
             }
             tanh_jet2_bwd<Cfg, false>(aj, zdummy, ab, zb);
-            if constexpr (Cfg::MMA_WGRAD) gb[(l > 2) ? l - 3 : 0][jj] += zb[0].x + zb[0].y;   // bias gradient of layer l-1
+            if constexpr (Cfg::MMA_WGRAD) gbl[jj] = zb[0].x + zb[0].y;                       // bias gradient of layer l-1
 #pragma unroll
             for (int c = 0; c < C; ++c) *reinterpret_cast<float2*>(Aprev + j * RS + c * kChunk + 2 * lr) = zb[c];
+          }
+          if constexpr (Cfg::TMEM_TOTALS) {
+            tmem_add8(tmem_w + 64u + 8u * (uint32_t)((l > 2) ? l - 3 : 0), gbl);
+          } else if constexpr (Cfg::MMA_WGRAD) {
+#pragma unroll
+            for (int jj = 0; jj < TC; ++jj) gb[(l > 2) ? l - 3 : 0][jj] += gbl[jj];
           }
           __syncwarp();
         } else {
@@ -961,7 +1027,9 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
     float* scr = buf;
 #pragma unroll
     for (int l = 0; l < NBUF; ++l) {
+      float gbt[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       if constexpr (Cfg::TMEM_TOTALS) {
+        tmem_ld8(tmem_w + 64u + 8u * (uint32_t)l, gbt);
         float tot[32];
         tmem_ld32(tmem_w + 32u * (uint32_t)l, tot);
 #pragma unroll
@@ -980,7 +1048,7 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
       for (int jj = 0; jj < TC; ++jj) {
         const int j = neuron_of<Cfg>(jj, lc);
         if constexpr (Cfg::MMA_WGRAD) {
-          const float v = reduce_over_lr(gb[l][jj]);
+          const float v = reduce_over_lr(Cfg::TMEM_TOTALS ? gbt[jj & 7] : gb[l][jj]);
           if (lr == 0) scr[NBUF * H * H + l * H + j] = v;
         } else {
 #pragma unroll

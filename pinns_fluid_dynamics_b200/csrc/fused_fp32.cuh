@@ -699,7 +699,9 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
     for (int q = 0; q < 32; ++q) gKm[l][q >> 4][(q >> 2) & 3][q & 3] = 0.f;
   }
 
-  for (int chunk = blockIdx.x * NW + warp; chunk < total_chunks; chunk += gridDim.x * NW) {
+  // chunk c goes to CTA c % grid first, then to its warps: a launch with fewer chunks than warps spreads them over the
+  // SMs (one warp per scheduler runs a chunk ~30 % faster than two sharing the tensor pipe)
+  for (int chunk = warp * gridDim.x + blockIdx.x; chunk < total_chunks; chunk += gridDim.x * NW) {
     int si = 0;
     while (si + 1 < n_segs && chunk >= __ldg(&segs[si + 1].chunk_begin)) ++si;
     const SegDev* __restrict__ seg = segs + si;

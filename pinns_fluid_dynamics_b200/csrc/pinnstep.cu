@@ -683,8 +683,7 @@ static int fused_pass(pinn_plan* p, const LaunchTable* tables, const float* para
     if (lt.n_segs == 0) continue;
     FusedKernel k;
     if (!pick_kernel(p->mlp, o, train, &k)) return fail(PINN_E_INVALID, "no kernel");
-    int grid = (lt.total_chunks + k.nw - 1) / k.nw;
-    if (grid > p->num_sms) grid = p->num_sms;
+    int grid = lt.total_chunks < p->num_sms ? lt.total_chunks : p->num_sms;    // chunks are dealt to CTAs first, then to warps
     if (rows + grid > p->rows_max) return fail(PINN_E_STATE, "workspace rows exhausted");
     if (timed) CUDA_TRY(cudaEventRecord(p->ev0[o], st));
     k.fn<<<grid, k.nw * 32, k.smem_bytes, st>>>(params, lt.segs_dev, lt.n_segs, lt.total_chunks,
@@ -805,8 +804,7 @@ extern "C" int pinn_forward(const pinn_mlp_desc* mlp, const float* params_dev, c
   SegDev* sd_dev = nullptr;
   CUDA_TRY(cudaMallocAsync(&sd_dev, sizeof(SegDev), st));
   CUDA_TRY(cudaMemcpyAsync(sd_dev, &sd, sizeof(SegDev), cudaMemcpyHostToDevice, st));
-  int grid = (sd.n_chunks + k.nw - 1) / k.nw;
-  if (grid > num_sms) grid = num_sms;
+  int grid = sd.n_chunks < num_sms ? sd.n_chunks : num_sms;
   const int aligned = ((uintptr_t)params_dev & 15u) == 0;
   k.fn<<<grid, k.nw * 32, k.smem_bytes, st>>>(params_dev, sd_dev, 1, sd.n_chunks, nullptr, 0, 0, aligned);
   CUDA_TRY(cudaGetLastError());

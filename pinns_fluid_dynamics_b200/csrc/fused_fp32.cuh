@@ -745,12 +745,10 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
     __syncwarp();
 
     // ---- hidden layers 2..L (+ output layer folded into the epilogue of layer L) --------------
+    // (the layer loop is unrolled so that the output-jet accumulators J only exist in the epilogue of layer L: kept
+    //  live as zeros through a rolled loop they cost 2*C*O registers in every GEMM)
     float2 J[C][O];
 #pragma unroll
-    for (int c = 0; c < C; ++c)
-#pragma unroll
-      for (int o = 0; o < O; ++o) J[c][o] = make_float2(0.f, 0.f);
-#pragma unroll 1
     for (int l = 2; l <= L; ++l) {
       const float* in = (l == 2) ? bufL : buf + (l - 3) * H * RS;
       float* out = buf + (l - 2) * H * RS;
@@ -779,6 +777,12 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
         warp_gemm<Cfg>(in, sK + (l - 2) * H * H, acc, lr, lc);
       }
       __syncwarp();   // all lanes finished reading `in` (it may alias `out`)
+      if (l == L) {
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+#pragma unroll
+          for (int o = 0; o < O; ++o) J[c][o] = make_float2(0.f, 0.f);
+      }
 #pragma unroll
       for (int jj = 0; jj < TC; ++jj) {
         const int j = neuron_of<Cfg>(jj, lc);

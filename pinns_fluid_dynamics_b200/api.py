@@ -181,6 +181,7 @@ class OptimizationProblem:
                                                          self.losses, self.losses_test, self.rank, self.world)
         self.plan = (engine_factory or CudaPlan)(self.compiled)
         self._graph, self._graph_opt, self._graph_sumsq, self._eager_steps = None, None, None, 0
+        self._h_theta = self._h_out = self._perm_np = None      # pinned staging of evaluate_host
         self.iteration = 0
         self.history = {
             "log": {"iter": [], "round": [], "iter_round": [], "loss_global": []},
@@ -258,6 +259,31 @@ class OptimizationProblem:
         grad, sumsq = self.loss_and_grad_device()
         total, train_vals, _ = assemble_losses(self.compiled, sumsq.detach().double().cpu().numpy())
         return total, train_vals, grad
+
+    def evaluate_host(self, theta: np.ndarray):
+        """(total, float64 gradient) at host parameters ``theta`` -- the objective SciPy-style drivers call thousands of
+        times.  One pinned H2D copy of the parameters, one loss step, ONE pinned D2H copy of the [P+T] result
+        (``evaluate`` issues several small kernels and two synchronising reads)."""
+        P = self.compiled.n_params
+        if not (self.flat.is_cuda and isinstance(self.plan, CudaPlan)):
+            self.flat.copy_(torch.as_tensor(theta, dtype=torch.float32))
+            total, _, grad = self.evaluate()
+            return float(total), grad.detach().double().cpu().numpy()
+        if self._h_theta is None:
+            self._h_theta = torch.empty(P, dtype=torch.float32, pin_memory=True)
+            self._h_out = torch.empty(self.plan.out.numel(), dtype=torch.float32, pin_memory=True)
+            self._perm_np = np.asarray(self.plan._perm, dtype=np.int64)
+        self._h_theta.numpy()[:] = theta
+        self.flat.copy_(self._h_theta, non_blocking=True)
+        out = self._reduce(self.plan.loss_and_grad(self.flat))
+        self._h_out.copy_(out, non_blocking=True)
+        torch.cuda.current_stream(self.flat.device).synchronize()
+        o = self._h_out.numpy()
+        sums = np.zeros(max(1, self.compiled.n_out_terms))
+        if self.plan.n_kernel_terms:
+            sums[self._perm_np] = o[P:P + self.plan.n_kernel_terms]
+        total, _, _ = assemble_losses(self.compiled, sums)
+        return float(total), o[:P].astype(np.float64)
 
     def evaluate_all(self):
         """Forward-only values of train and test terms (log points)."""
@@ -356,9 +382,7 @@ def minimize(pb: OptimizationProblem, backend: str, optimizer, num_epochs: int) 
         pb.log_state()
 
         def fun(theta: np.ndarray):
-            pb.flat.copy_(torch.as_tensor(theta, dtype=torch.float32))
-            total, _, grad = pb.evaluate()
-            return float(total), grad.detach().double().cpu().numpy()
+            return pb.evaluate_host(theta)
 
         def cb(_theta):
             pb.step_done()

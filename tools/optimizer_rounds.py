@@ -18,14 +18,14 @@ torch.cuda.synchronize(); t1 = time.perf_counter()
 print(f"Adam round: {(t1 - t0) / 100 * 1e3:.3f} ms per epoch ({n} collocation points), loss {pb.evaluate()[0]:.4e}")
 ns.minimize(pb, "scipy", "BFGS", num_epochs=2)      # warm-up: cuBLAS handle, float64 kernels
 evals = [0]
-orig = pb.evaluate
-def counted():
+orig = pb.evaluate_host
+def counted(theta):
     evals[0] += 1
-    return orig()
-pb.evaluate = counted
+    return orig(theta)
+pb.evaluate_host = counted
 t0 = time.perf_counter()
 ns.minimize(pb, "scipy", "BFGS", num_epochs=30)
 t1 = time.perf_counter()
-pb.evaluate = orig
+pb.evaluate_host = orig
 print(f"BFGS round ({os.environ.get("PINN_BFGS", "device")} algebra): {(t1 - t0) / 30 * 1e3:.3f} ms per iteration, {evals[0] / 30:.2f} loss/gradient evaluations per iteration, "
       f"loss {pb.evaluate()[0]:.4e}")

@@ -55,7 +55,9 @@
 
 namespace pinn {
 
-template <int D_, int H_, int L_, int O_, int ORDER_>
+// TENSOR_: hidden-layer GEMMs on the warp-level tensor path (H = 32 only); false keeps the FP32 FFMA2 GEMMs (the
+// engine of H = 20, and of H = 32 under PINN_ENGINE=fused_fp32: the cross-check of the tensor path)
+template <int D_, int H_, int L_, int O_, int ORDER_, bool TENSOR_ = true>
 struct FusedCfg {
   static constexpr int D = D_, H = H_, L = L_, O = O_, ORDER = ORDER_;
   static constexpr int C = n_channels(D, ORDER);
@@ -66,7 +68,7 @@ struct FusedCfg {
   static constexpr int SX = D - 2, SY = D - 1;      // spatial input columns
   // H = 32: the weight-gradient GEMM of the hidden layers runs on the warp-level tensor path (mma.sync m16n8k8, 3xTF32
   // split) concurrently with the FFMA2 GEMMs of the other warps on the FMA pipe
-  static constexpr bool MMA_WGRAD = (H == 32) && (PINN_FUSED_MMA_WGRAD != 0);
+  static constexpr bool MMA_WGRAD = (H == 32) && TENSOR_ && (PINN_FUSED_MMA_WGRAD != 0);
   // ... and so do the forward / input-adjoint GEMMs (PINN_FUSED_MMA_GEMM): the lane's neurons become {8n + 2lc + e}
   // (the mma.sync accumulator columns) instead of {lc + 4jj}; its points stay {2lr, 2lr+1}
   static constexpr bool MMA = MMA_WGRAD && (PINN_FUSED_MMA_GEMM != 0);
@@ -590,11 +592,11 @@ __device__ __forceinline__ void write_a1_jets(float* __restrict__ dst, const flo
   }
 }
 
-template <int D, int H, int L, int O, int ORDER, bool TRAIN>
-__global__ void __launch_bounds__(FusedCfg<D, H, L, O, ORDER>::NW * 32, 1)
+template <int D, int H, int L, int O, int ORDER, bool TRAIN, bool TENSOR>
+__global__ void __launch_bounds__(FusedCfg<D, H, L, O, ORDER, TENSOR>::NW * 32, 1)
 fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ segs, int n_segs, int total_chunks,
                   float* __restrict__ ws, int ws_stride, int n_terms_total, int params_aligned) {
-  using Cfg = FusedCfg<D, H, L, O, ORDER>;
+  using Cfg = FusedCfg<D, H, L, O, ORDER, TENSOR>;
   constexpr int C = Cfg::C, TC = Cfg::TC, TI = Cfg::TI, RS = Cfg::RS, NBUF = Cfg::NBUF, NW = Cfg::NW;
   constexpr int SX = Cfg::SX, SY = Cfg::SY, P = Cfg::P;
   extern __shared__ __align__(16) float smem[];

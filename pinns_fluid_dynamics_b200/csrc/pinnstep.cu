@@ -62,6 +62,7 @@ struct pinn_plan {
   LaunchTable train[3], eval[3];         // by derivative order
   LaunchTable prepass[3];                // sets that carry a |mean| training term (forward pre-pass for its sign)
   bool has_abs_mean = false;
+  int fused_tensor = 0;                  // fused engines: 1 = hidden-layer GEMMs on the tensor path (fixed at plan creation)
   float* signs = nullptr;                // [T] +-1 per term slot (only |mean| slots are read)
   float* prepass_out = nullptr;          // [P + T] scratch of the pre-pass
   float* ws = nullptr;                   // [rows_max][P + T]
@@ -89,28 +90,38 @@ struct FusedKernel {
   int nw;
 };
 
-template <int D, int H, int L, int O, int ORDER, bool TRAIN>
+template <int D, int H, int L, int O, int ORDER, bool TRAIN, bool TENSOR>
 static FusedKernel make_kernel() {
-  using Cfg = FusedCfg<D, H, L, O, ORDER>;
-  return FusedKernel{(fused_fn)fused_step_kernel<D, H, L, O, ORDER, TRAIN>, Cfg::SMEM_BYTES, Cfg::NW};
+  using Cfg = FusedCfg<D, H, L, O, ORDER, TENSOR>;
+  return FusedKernel{(fused_fn)fused_step_kernel<D, H, L, O, ORDER, TRAIN, TENSOR>, Cfg::SMEM_BYTES, Cfg::NW};
 }
 
-template <int D, int H, int L, int O>
+template <int D, int H, int L, int O, bool TENSOR>
 static bool pick_order(int order, bool train, FusedKernel* k) {
   switch (order) {
-    case 0: *k = train ? make_kernel<D, H, L, O, 0, true>() : make_kernel<D, H, L, O, 0, false>(); return true;
-    case 1: *k = train ? make_kernel<D, H, L, O, 1, true>() : make_kernel<D, H, L, O, 1, false>(); return true;
-    case 2: *k = train ? make_kernel<D, H, L, O, 2, true>() : make_kernel<D, H, L, O, 2, false>(); return true;
+    case 0: *k = train ? make_kernel<D, H, L, O, 0, true, TENSOR>() : make_kernel<D, H, L, O, 0, false, TENSOR>(); return true;
+    case 1: *k = train ? make_kernel<D, H, L, O, 1, true, TENSOR>() : make_kernel<D, H, L, O, 1, false, TENSOR>(); return true;
+    case 2: *k = train ? make_kernel<D, H, L, O, 2, true, TENSOR>() : make_kernel<D, H, L, O, 2, false, TENSOR>(); return true;
   }
   return false;
 }
 
-static bool pick_kernel(const pinn_mlp_desc& m, int order, bool train, FusedKernel* k) {
+// H = 32 runs its hidden-layer GEMMs on the tensor path unless PINN_ENGINE=fused_fp32 asks for the FP32 FFMA2 build of
+// the same kernel (cross-check of the tensor path, and the tighter-accuracy option: DESIGN.md section 6)
+static bool fused_tensor_path(const pinn_mlp_desc& m) {
+  const char* force = getenv("PINN_ENGINE");
+  return m.width == 32 && pinn::FusedCfg<2, 32, 3, 3, 2, true>::MMA && !(force && strcmp(force, "fused_fp32") == 0);
+}
+
+static bool pick_kernel(const pinn_mlp_desc& m, int order, bool train, FusedKernel* k, int tensor = -1) {
   if (m.n_hidden != 3) return false;
-  if (m.in_dim == 2 && m.width == 32 && m.out_dim == 3) return pick_order<2, 32, 3, 3>(order, train, k);
-  if (m.in_dim == 3 && m.width == 32 && m.out_dim == 3) return pick_order<3, 32, 3, 3>(order, train, k);
-  if (m.in_dim == 2 && m.width == 20 && m.out_dim == 1) return pick_order<2, 20, 3, 1>(order, train, k);
-  if (m.in_dim == 2 && m.width == 20 && m.out_dim == 3) return pick_order<2, 20, 3, 3>(order, train, k);   // pressmean variant
+  const bool tp = tensor < 0 ? fused_tensor_path(m) : tensor != 0;
+  if (m.in_dim == 2 && m.width == 32 && m.out_dim == 3)
+    return tp ? pick_order<2, 32, 3, 3, true>(order, train, k) : pick_order<2, 32, 3, 3, false>(order, train, k);
+  if (m.in_dim == 3 && m.width == 32 && m.out_dim == 3)
+    return tp ? pick_order<3, 32, 3, 3, true>(order, train, k) : pick_order<3, 32, 3, 3, false>(order, train, k);
+  if (m.in_dim == 2 && m.width == 20 && m.out_dim == 1) return pick_order<2, 20, 3, 1, false>(order, train, k);
+  if (m.in_dim == 2 && m.width == 20 && m.out_dim == 3) return pick_order<2, 20, 3, 3, false>(order, train, k);   // pressmean variant
   return false;
 }
 
@@ -570,7 +581,8 @@ extern "C" int pinn_plan_create(const pinn_mlp_desc* mlp, const pinn_pointset_de
     return PINN_OK;
   }
   // H = 32: hidden-layer GEMMs on the warp-level tensor path (3xTF32), see fused_fp32.cuh
-  if (mlp->width == 32 && pinn::FusedCfg<2, 32, 3, 3, 2>::MMA) p->engine = "fused_tf32x3";
+  p->fused_tensor = fused_tensor_path(*mlp) ? 1 : 0;
+  if (p->fused_tensor) p->engine = "fused_tf32x3";
   p->rows_max = 3 * p->num_sms;
   p->ws_bytes = (size_t)p->rows_max * (size_t)(p->P + p->T) * sizeof(float);
   if (cudaMalloc(&p->ws, p->ws_bytes) != cudaSuccess) {
@@ -581,7 +593,7 @@ extern "C" int pinn_plan_create(const pinn_mlp_desc* mlp, const pinn_pointset_de
   for (int o = 0; o < 3; ++o)
     for (int tr = 0; tr < 2; ++tr) {
       FusedKernel k;
-      pick_kernel(p->mlp, o, tr != 0, &k);
+      pick_kernel(p->mlp, o, tr != 0, &k, p->fused_tensor);
       cudaError_t e = cudaFuncSetAttribute((const void*)k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, k.smem_bytes);
       if (e != cudaSuccess) {
         pinn_plan_destroy(p);
@@ -682,7 +694,7 @@ static int fused_pass(pinn_plan* p, const LaunchTable* tables, const float* para
     const LaunchTable& lt = tables[o];
     if (lt.n_segs == 0) continue;
     FusedKernel k;
-    if (!pick_kernel(p->mlp, o, train, &k)) return fail(PINN_E_INVALID, "no kernel");
+    if (!pick_kernel(p->mlp, o, train, &k, p->fused_tensor)) return fail(PINN_E_INVALID, "no kernel");
     int grid = lt.total_chunks < p->num_sms ? lt.total_chunks : p->num_sms;    // chunks are dealt to CTAs first, then to warps
     if (rows + grid > p->rows_max) return fail(PINN_E_STATE, "workspace rows exhausted");
     if (timed) CUDA_TRY(cudaEventRecord(p->ev0[o], st));

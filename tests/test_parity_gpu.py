@@ -413,3 +413,20 @@ def test_abs_mean_term_takes_the_sign_of_the_mean(shift):
     # d/d b_out[2] of w |mean p| is w sign(mean): the last gradient entry carries the sign
     assert np.sign(g[-1]) == np.sign(rg[-1]) == np.sign(shift)
     assert pb.plan.last_launch_count() >= 5      # pre-pass (kernel, finalize, sign) + main pass
+
+
+def test_tensor_path_fused_engine_agrees_with_fp32_fused_engine(monkeypatch):
+    """H = 32: the mma.sync 3xTF32 GEMMs (fused_tf32x3) against the FP32 FFMA2 GEMMs of the same kernel
+    (PINN_ENGINE=fused_fp32), two independent implementations of every hidden-layer contraction."""
+    data, var, model, pb1 = _setup("cavity_unsteady", SMALL["cavity_unsteady"])
+    assert pb1.plan.engine == "fused_tf32x3"
+    t1, v1, g1 = pb1.evaluate()
+    monkeypatch.setenv("PINN_ENGINE", "fused_fp32")
+    losses, loss_test = loss_tables.build_loss_table(data)
+    pb2 = ns.OptimizationProblem(model.variables, losses, loss_test)
+    assert pb2.plan.engine == "fused_fp32"
+    t2, v2, g2 = pb2.evaluate()
+    assert _rel(t1, t2) < LOSS_RTOL
+    for a, b in zip(v1, v2):
+        assert _term_close(a, b)
+    assert float((g1 - g2).norm() / g2.norm()) < GRAD_RTOL

@@ -521,6 +521,20 @@ extern "C" int pinn_plan_create(const pinn_mlp_desc* mlp, const pinn_pointset_de
     return fail(PINN_E_INVALID, "%d loss terms exceed the limit of %d", T, kMaxLaunchTerms);
   }
   p->T = T;
+  if (use_fused) {
+    // Small lower-order sets (boundary edges, fit points: 0.4 % of the chunks of the BASELINE configs) ride in the launch of
+    // the highest derivative order instead of getting kernels of their own: their residual coefficients on the extra
+    // channels are zero, the value channel is computed by the same instruction sequence, and the step loses a launch
+    // and its tail.  Only when they are at most 1/16 of that launch.
+    long long chunks[3] = {0, 0, 0};
+    for (const pinn_pointset_desc& ps : p->sets)
+      if (ps.n_local > 0 && ps.n_terms > 0) chunks[ps.deriv_order] += (ps.n_local + kChunk - 1) / kChunk;
+    int top = chunks[2] ? 2 : (chunks[1] ? 1 : 0);
+    long long lower = 0;
+    for (int o = 0; o < top; ++o) lower += chunks[o];
+    if (top > 0 && lower > 0 && lower * 16 <= chunks[top] && !(getenv("PINN_NO_PROMOTE") && atoi(getenv("PINN_NO_PROMOTE"))))
+      for (pinn_pointset_desc& ps : p->sets) ps.deriv_order = top;
+  }
   for (int s = 0; s < n_sets; ++s)
     for (int t = 0; t < sets[s].n_terms; ++t) {
       const int kind = sets[s].terms[t].kind;

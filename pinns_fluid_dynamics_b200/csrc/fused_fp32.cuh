@@ -1101,20 +1101,33 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
 }
 
 // rows -> out: out[i] = sum_r ws[r][i] for i in [i_begin, stride)
-__global__ void finalize_rows_kernel(const float* __restrict__ ws, int rows, int stride, int i_begin,
-                                     float* __restrict__ out) {
-  const int i = i_begin + blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= stride) return;
+// A CTA owns 32 columns; its 32 warps take the rows r = warp, warp + 32, ... (one coalesced 128-byte read per row and
+// warp, four independent partial sums), then the 32 per-warp partials of a column are added in a fixed order: the result
+// does not depend on scheduling (bit-reproducible) and the ~150-450 rows are read with 1024-way parallelism per CTA.
+__global__ void __launch_bounds__(1024)
+finalize_rows_kernel(const float* __restrict__ ws, int rows, int stride, int i_begin, float* __restrict__ out) {
+  __shared__ float part[32][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = i_begin + blockIdx.x * 32 + lane;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int r = 0;
-  for (; r + 3 < rows; r += 4) {
-    s0 += ws[(size_t)r * stride + i];
-    s1 += ws[(size_t)(r + 1) * stride + i];
-    s2 += ws[(size_t)(r + 2) * stride + i];
-    s3 += ws[(size_t)(r + 3) * stride + i];
+  if (i < stride) {
+    int r = warp;
+    for (; r + 96 < rows; r += 128) {
+      s0 += ws[(size_t)r * stride + i];
+      s1 += ws[(size_t)(r + 32) * stride + i];
+      s2 += ws[(size_t)(r + 64) * stride + i];
+      s3 += ws[(size_t)(r + 96) * stride + i];
+    }
+    for (; r < rows; r += 32) s0 += ws[(size_t)r * stride + i];
   }
-  for (; r < rows; ++r) s0 += ws[(size_t)r * stride + i];
-  out[i] = (s0 + s1) + (s2 + s3);
+  part[warp][lane] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (warp == 0 && i < stride) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 32; ++w) s += part[w][lane];
+    out[i] = s;
+  }
 }
 
 }  // namespace pinn

@@ -727,7 +727,7 @@ static int fused_pass(pinn_plan* p, const LaunchTable* tables, const float* para
   if (rows == 0) {
     CUDA_TRY(cudaMemsetAsync(out + i_begin, 0, sizeof(float) * count, st));
   } else if (count > 0) {
-    finalize_rows_kernel<<<(count + 127) / 128, 128, 0, st>>>(p->ws, rows, stride, i_begin, out);
+    finalize_rows_kernel<<<(count + 31) / 32, 1024, 0, st>>>(p->ws, rows, stride, i_begin, out);
     CUDA_TRY(cudaGetLastError());
     ++launches;
   }

@@ -28,29 +28,32 @@
 #include "common.cuh"
 #include "umma.cuh"
 
+// Build-time switches of the H = 32 tensor path.  The defaults are the shipped kernel; the others are the variants measured
+// in DESIGN.md section 6 (accuracy / speed table) and are kept so those measurements can be repeated
+// (nvcc -D..., load the result with PINN_LIBPINNSTEP=/path/to/lib.so).
 #ifndef PINN_FUSED_MMA_WGRAD
-#define PINN_FUSED_MMA_WGRAD 1
+#define PINN_FUSED_MMA_WGRAD 1     // weight-gradient GEMM on mma.sync (0: the whole kernel stays FP32, like PINN_ENGINE=fused_fp32)
 #endif
 #ifndef PINN_FUSED_MMA_GEMM
-#define PINN_FUSED_MMA_GEMM 1
+#define PINN_FUSED_MMA_GEMM 1      // forward / input-adjoint GEMMs on mma.sync as well
 #endif
 #ifndef PINN_FUSED_LO_RNA
-#define PINN_FUSED_LO_RNA 1
+#define PINN_FUSED_LO_RNA 1        // round (not truncate) the lo part of an activation: +0x1000 before the hardware cut
 #endif
 #ifndef PINN_FUSED_KSTEP_DRAIN
-#define PINN_FUSED_KSTEP_DRAIN 1
-#endif
-#ifndef PINN_FUSED_MAX_WARPS
-#define PINN_FUSED_MAX_WARPS 8       // experiments: fewer warps per CTA (latency vs contention)
-#endif
-#ifndef PINN_FUSED_SPLIT_CVT
-#define PINN_FUSED_SPLIT_CVT 0
-#endif
-#ifndef PINN_FUSED_SPLIT_TRUNC
-#define PINN_FUSED_SPLIT_TRUNC 0
+#define PINN_FUSED_KSTEP_DRAIN 1   // join the 4 k-steps of a forward / adjoint accumulator with FP32 FADDs (0: in the tensor core)
 #endif
 #ifndef PINN_FUSED_TMEM_TOTALS
-#define PINN_FUSED_TMEM_TOTALS 1
+#define PINN_FUSED_TMEM_TOTALS 1   // running weight- and bias-gradient totals in tensor memory instead of 80 registers
+#endif
+#ifndef PINN_FUSED_MAX_WARPS
+#define PINN_FUSED_MAX_WARPS 8     // 4: one warp per scheduler (33 k instead of 47 k cycles per chunk and warp: latency vs contention)
+#endif
+#ifndef PINN_FUSED_SPLIT_CVT
+#define PINN_FUSED_SPLIT_CVT 0     // hi by cvt.rna.tf32.f32 (4 SASS instructions on sm_100a: 5 % slower)
+#endif
+#ifndef PINN_FUSED_SPLIT_TRUNC
+#define PINN_FUSED_SPLIT_TRUNC 0   // raw operand as hi (the hardware truncates): 1 % faster, worst loss term 9e-6 -- rejected
 #endif
 
 namespace pinn {

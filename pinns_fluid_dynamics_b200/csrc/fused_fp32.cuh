@@ -1,6 +1,5 @@
-// Fused FP32 loss-step kernel for narrow tanh MLPs (H <= 32): Taylor-mode jets forward, residuals,
-// weighted mean-square terms and the hand-written reverse sweep to parameter gradients, all in ONE
-// kernel with every activation kept on chip.
+// Fused loss-step kernel for narrow tanh MLPs (H <= 32): Taylor-mode jets forward, residuals, weighted mean-square
+// terms and the hand-written reverse sweep to parameter gradients, all in ONE kernel with every activation kept on chip.
 //
 // Replaces (reference, per epoch): 3 x model(x) + 14 inner tape.gradient sweeps + nisaba's outer
 // tape.gradient over the collocation set (cavity_steady.py:159-188,212-214,242) and the per-term
@@ -8,22 +7,29 @@
 //
 // Work decomposition
 //   * a WARP owns a chunk of 16 points from layer 1 to the parameter-gradient contribution; warps
-//     never synchronise with each other inside the main loop (only __syncwarp).
-//   * lane = (lr, lc): lr = lane>>2 owns points {2lr, 2lr+1} of the chunk, lc = lane&3 owns the
-//     neurons {lc + 4*jj}.  A hidden layer is a register-tiled FP32 GEMM
-//     [C*16 rows] x [H] x [H]: per k-step a lane loads its two points' C channel values (C LDS.64)
-//     and TC weights (LDS.128, pre-permuted so they are contiguous per lane) and issues 2*C*TC FFMA.
-//   * jets live in shared memory as J[neuron k][channel c][point p] (row stride RS = 16C+4 floats,
-//     RS/4 odd so the weight-gradient GEMM's LDS.128 are bank-conflict free).
+//     never synchronise with each other inside the main loop (only __syncwarp).  Chunks are dealt to CTAs first, then
+//     to their warps.
+//   * lane = (lr, lc): lr = lane>>2 owns points {2lr, 2lr+1} of the chunk (the two halves of every float2 in the
+//     tanh-jet math), lc = lane&3 owns 8 neurons.
+//   * jets live in shared memory as J[neuron k][channel c][point p] (row stride RS = 16C+4 floats: the fragment / LDS.128
+//     patterns of all three GEMMs are bank-conflict free).
+//   * hidden-layer GEMMs, two instantiations of the same kernel:
+//       TENSOR (H = 32, engine "fused_tf32x3"): mma.sync.m16n8k8 tf32 with the 3-pass hi/lo split -- forward
+//         [16C rows] x 32 x 32, input adjoint, weight gradient 32 x 32 over K = 16C; the lane's neurons are the
+//         accumulator columns {8n + 2lc + e}; see warp_gemm_mma / warp_wgrad_mma.
+//       FP32 (H = 20, and H = 32 under PINN_ENGINE=fused_fp32, engine "fused_fp32"): register-tiled FFMA2, neurons
+//         {lc + 4jj}; per k-step a lane loads its two points' C channel values (C LDS.64) and TC weights (LDS.128,
+//         pre-permuted so they are contiguous per lane) and issues C*TC FFMA2.
 //   * the whole parameter vector is staged into shared memory once per CTA by one TMA bulk copy
-//     (cp.async.bulk + mbarrier), then permuted/transposed copies are built for the GEMMs.
+//     (cp.async.bulk + mbarrier), then the GEMM images are built (tf32 hi / lo images, or permuted / transposed copies).
 //   * reverse sweep: z-bar overwrites the a-jets in place; the pre-activation jets are recovered
 //     from the stored a-jets (z_x = a_x / s, ...), so only the a-jets of layers 2..L and tanh(z1)
 //     are stored: (L-1)*C*H + H floats per point.
-//   * weight gradients of the H x H layers accumulate in registers across ALL chunks of a warp
-//     (4 x TC per lane per layer); small gradients (K1, b1, K_out, b_out) go through a warp shuffle
-//     reduction into per-warp shared-memory accumulators.  At the end the CTA sums its warps and
-//     writes ONE row of the workspace; a finalize kernel sums the rows (no atomics anywhere).
+//   * weight gradients of the H x H layers accumulate per warp across ALL its chunks (32 values per lane and layer: in
+//     tensor memory via tcgen05.ld/st for the TENSOR instantiation, in registers otherwise); small gradients (K1, b1,
+//     K_out, b_out) go through a warp shuffle reduction into per-warp shared-memory accumulators.  At the end the CTA
+//     sums its warps and writes ONE row of the workspace; a finalize kernel sums the rows in a fixed order (no atomics
+//     anywhere: bit-reproducible).
 #pragma once
 #include "common.cuh"
 #include "umma.cuh"

@@ -9,7 +9,7 @@ constexpr int kChunk = 16;          // points per warp-chunk (8 row-lanes x 2 po
 constexpr int kMaxTerms = 8;        // PINN_MAX_TERMS_PER_SET
 constexpr int kMaxOut = 4;          // PINN_MAX_OUT
 constexpr int kMaxCh = 6;           // PINN_MAX_CH
-constexpr int kMaxLaunchTerms = 64; // per-warp sum r^2 slots in shared memory
+constexpr int kMaxLaunchTerms = 32; // per-warp sum r^2 slots in shared memory (the scripts' tables have at most 20 terms)
 
 // One loss term as the kernels see it (host fills `scale` = 2*weight/(normalization*n_global)).
 struct TermDev {

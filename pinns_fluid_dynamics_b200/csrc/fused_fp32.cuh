@@ -52,6 +52,12 @@
 #ifndef PINN_FUSED_TMEM_TOTALS
 #define PINN_FUSED_TMEM_TOTALS 1   // running weight- and bias-gradient totals in tensor memory instead of 80 registers
 #endif
+#ifndef PINN_FUSED_BWD_BF16
+#define PINN_FUSED_BWD_BF16 1      // input-adjoint GEMM: the same bf16 correction passes (needs 10 KB of bf16 weight images)
+#endif
+#ifndef PINN_FUSED_WGRAD_BF16
+#define PINN_FUSED_WGRAD_BF16 1    // weight gradient: correction passes lo*hi, hi*lo as bf16 m16n8k16 over pairs of k-steps
+#endif
 #ifndef PINN_FUSED_MAX_WARPS
 #define PINN_FUSED_MAX_WARPS 8     // 4: one warp per scheduler (33 k instead of 47 k cycles per chunk and warp: latency vs contention)
 #endif
@@ -82,6 +88,11 @@ struct FusedCfg {
   // (the mma.sync accumulator columns) instead of {lc + 4jj}; its points stay {2lr, 2lr+1}
   static constexpr bool MMA = MMA_WGRAD && (PINN_FUSED_MMA_GEMM != 0);
   static constexpr int WS = 36;                     // row stride of the hi / lo weight images (conflict-free B fragments)
+  // input-adjoint GEMM (gradients only: tolerance 1e-4): correction passes lo*hi, hi*lo as bf16 m16n8k16 over pairs of
+  // k-steps; needs bf16 images of K_l and of its lo part, rows of WSB 32-bit words (two bf16 each, conflict-free)
+  static constexpr bool BWD_BF16 = MMA && (PINN_FUSED_BWD_BF16 != 0);
+  static constexpr int WSB = 20;
+  static constexpr int W_BF = BWD_BF16 ? 2 * (L - 1) * H * WSB : 0;
   // the running weight-gradient totals (64 registers per lane) live in tensor memory: one 32-column block per warp and
   // layer, read-modify-written once per chunk with tcgen05.ld / tcgen05.st -- the registers go to the tanh-jet phases
   static constexpr bool TMEM_TOTALS = MMA_WGRAD && (PINN_FUSED_TMEM_TOTALS != 0);
@@ -96,7 +107,7 @@ struct FusedCfg {
   static constexpr int W_B = L * H;
   static constexpr int W_KO = H * 4;
   static constexpr int W_BO = 4;
-  static constexpr int W_TOTAL = W_K + W_KT + W_K1 + W_B + W_KO + W_BO + 4 /* mbarrier */;
+  static constexpr int W_TOTAL = W_K + W_KT + W_K1 + W_B + W_KO + W_BO + 4 /* mbarrier */ + W_BF;
   // per-warp (floats)
   static constexpr int PW_JETS = NBUF * H * RS;
   static constexpr int PW_SCR = NBUF * (H * H + H);   // end-of-kernel reduction scratch (aliases the jets)
@@ -437,6 +448,17 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&t)[8]) {
 }
 
 // gK[m][n][.] : lane (g = lane>>2, t = lane&3) holds D[16m+g][8n+2t], [..][8n+2t+1], D[16m+g+8][8n+2t], [..][8n+2t+1]
+__device__ __forceinline__ void mma_m16n8k16_bf16(float (&d)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ unsigned pack_bf16(float lo16, float hi16) {      // two bf16 (round to nearest) in one register
+  unsigned r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi16), "f"(lo16));
+  return r;
+}
+
 template <class Cfg>
 __device__ __forceinline__ void warp_wgrad_mma(const float* __restrict__ A, const float* __restrict__ Z,
                                                float (&gK)[2][4][4], uint32_t tmem_totals, int g, int t) {
@@ -451,6 +473,65 @@ __device__ __forceinline__ void warp_wgrad_mma(const float* __restrict__ A, cons
       for (int i = 0; i < 4; ++i) d[m][n][i] = 0.f;
   const float* ap = A + g * RS + t;
   const float* zp = Z + g * RS + t;
+#if PINN_FUSED_WGRAD_BF16
+  // The gradient tolerance (1e-4) is loose next to the loss tolerance, so the two correction passes lo*hi and hi*lo run
+  // as bf16 m16n8k16 MMAs over a PAIR of k-steps (their 2^-9 operand rounding sits on terms 2^-12 below the product:
+  // 5e-7 per product), the main pass hi*hi stays tf32: 32 instead of 48 MMAs per pair.  The bf16 instruction's K index
+  // (2t, 2t+1 | 2t+8, 2t+9) is mapped to the columns the lane already holds for tf32, (t, t+4) of either step.
+#pragma unroll 1
+  for (int s = 0; s < 2 * C; s += 2) {
+    unsigned ah[2][2][4], ahb[2][4], alb[2][4], bh[2][4][2], bhb[4][2], blb[4][2];
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      float x[2][4], lo[2][4];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float* q = ap + 16 * m * RS + 8 * (s + u);
+        x[u][0] = q[0]; x[u][1] = q[8 * RS]; x[u][2] = q[4]; x[u][3] = q[8 * RS + 4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          ah[u][m][i] = (__float_as_uint(x[u][i]) + 0x1000u) & 0xFFFFE000u;
+          lo[u][i] = x[u][i] - __uint_as_float(ah[u][m][i]);
+        }
+      }
+      // bf16 A fragment: {row g: (k0, k1) of step s | row g+8: same | row g: step s+1 | row g+8: step s+1}
+      ahb[m][0] = pack_bf16(x[0][0], x[0][2]); ahb[m][1] = pack_bf16(x[0][1], x[0][3]);
+      ahb[m][2] = pack_bf16(x[1][0], x[1][2]); ahb[m][3] = pack_bf16(x[1][1], x[1][3]);
+      alb[m][0] = pack_bf16(lo[0][0], lo[0][2]); alb[m][1] = pack_bf16(lo[0][1], lo[0][3]);
+      alb[m][2] = pack_bf16(lo[1][0], lo[1][2]); alb[m][3] = pack_bf16(lo[1][1], lo[1][3]);
+    }
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      float y[2][2], lo[2][2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float* q = zp + 8 * n * RS + 8 * (s + u);
+        y[u][0] = q[0]; y[u][1] = q[4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          bh[u][n][i] = (__float_as_uint(y[u][i]) + 0x1000u) & 0xFFFFE000u;
+          lo[u][i] = y[u][i] - __uint_as_float(bh[u][n][i]);
+        }
+      }
+      bhb[n][0] = pack_bf16(y[0][0], y[0][1]); bhb[n][1] = pack_bf16(y[1][0], y[1][1]);
+      blb[n][0] = pack_bf16(lo[0][0], lo[0][1]); blb[n][1] = pack_bf16(lo[1][0], lo[1][1]);
+    }
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int n = 0; n < 4; ++n) mma_m16n8k16_bf16(d[m][n], alb[m], bhb[n]);
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int n = 0; n < 4; ++n) mma_m16n8k16_bf16(d[m][n], ahb[m], blb[n]);
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int n = 0; n < 4; ++n) mma_m16n8k8_tf32(d[m][n], ah[u][m], bh[u][n]);
+  }
+#else
 #pragma unroll 2
   for (int s = 0; s < 2 * C; ++s) {
     unsigned ah[2][4], al[2][4], bh[4][2], bl[4][2];
@@ -482,6 +563,7 @@ __device__ __forceinline__ void warp_wgrad_mma(const float* __restrict__ A, cons
 #pragma unroll
       for (int n = 0; n < 4; ++n) mma_m16n8k8_tf32(d[m][n], ah[m], bh[n]);
   }
+#endif
   if constexpr (Cfg::TMEM_TOTALS) {
     float tot[32];
     tmem_ld32(tmem_totals, tot);
@@ -565,6 +647,69 @@ __device__ __forceinline__ void warp_gemm_mma(const float* __restrict__ in, cons
   }
 }
 
+// Input-adjoint GEMM with bf16 correction passes (BWD_BF16): d[c][n] += sum_j in[j][c][p] * K[8n + ..][j], the main pass
+// hi*hi as tf32 m16n8k8 per k-step, lo*hi and hi*lo as bf16 m16n8k16 over the PAIR of k-steps (same lane-to-column mapping
+// as the weight gradient: instruction K (2t, 2t+1 | 2t+8, 2t+9) <-> j = 8ks+2t, 8ks+2t+1 of either step).  One fresh
+// accumulator per pair (16 MMAs), joined by FP32 FADDs.  Wbh / Wbl: bf16 images of K_l and of its lo part.
+template <class Cfg>
+__device__ __forceinline__ void warp_gemm_bwd_bf16(const float* __restrict__ in, const float* __restrict__ Wh,
+                                                   const unsigned* __restrict__ Wbh, const unsigned* __restrict__ Wbl,
+                                                   float (&d)[Cfg::C][4][4], int g, int t) {
+  constexpr int C = Cfg::C, RS = Cfg::RS, WS = Cfg::WS, WSB = Cfg::WSB;
+  const float* arow = in + 2 * g + 2 * t * RS;
+#pragma unroll
+  for (int kp = 0; kp < 2; ++kp) {
+    unsigned bh[2][4][2], bhb[4][2], blb[4][2];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float2 h = *reinterpret_cast<const float2*>(Wh + (8 * n + g) * WS + 8 * (2 * kp + u) + 2 * t);
+        bh[u][n][0] = __float_as_uint(h.x); bh[u][n][1] = __float_as_uint(h.y);
+        bhb[n][u] = Wbh[(8 * n + g) * WSB + 4 * (2 * kp + u) + t];
+        blb[n][u] = Wbl[(8 * n + g) * WSB + 4 * (2 * kp + u) + t];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      unsigned ah[2][4], ahb[4], alb[4];
+      float x[2][4], lo[2][4];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float2 v0 = *reinterpret_cast<const float2*>(arow + 8 * (2 * kp + u) * RS + c * kChunk);
+        const float2 v1 = *reinterpret_cast<const float2*>(arow + (8 * (2 * kp + u) + 1) * RS + c * kChunk);
+        x[u][0] = v0.x; x[u][1] = v0.y; x[u][2] = v1.x; x[u][3] = v1.y;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          ah[u][i] = (__float_as_uint(x[u][i]) + 0x1000u) & 0xFFFFE000u;
+          lo[u][i] = x[u][i] - __uint_as_float(ah[u][i]);
+        }
+      }
+      ahb[0] = pack_bf16(x[0][0], x[0][2]); ahb[1] = pack_bf16(x[0][1], x[0][3]);
+      ahb[2] = pack_bf16(x[1][0], x[1][2]); ahb[3] = pack_bf16(x[1][1], x[1][3]);
+      alb[0] = pack_bf16(lo[0][0], lo[0][2]); alb[1] = pack_bf16(lo[0][1], lo[0][3]);
+      alb[2] = pack_bf16(lo[1][0], lo[1][2]); alb[3] = pack_bf16(lo[1][1], lo[1][3]);
+      float tacc[4][4];
+#pragma unroll
+      for (int n = 0; n < 4; ++n)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tacc[n][i] = 0.f;
+#pragma unroll
+      for (int n = 0; n < 4; ++n) mma_m16n8k16_bf16(tacc[n], alb, bhb[n]);
+#pragma unroll
+      for (int n = 0; n < 4; ++n) mma_m16n8k16_bf16(tacc[n], ahb, blb[n]);
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int n = 0; n < 4; ++n) mma_m16n8k8_tf32(tacc[n], ah[u], bh[u][n]);
+#pragma unroll
+      for (int n = 0; n < 4; ++n)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[c][n][i] += tacc[n][i];
+    }
+  }
+}
+
 __device__ __forceinline__ float reduce_over_lr(float v) {   // sum over the 8 row-lanes (same lc)
   v += __shfl_xor_sync(0xffffffffu, v, 4);
   v += __shfl_xor_sync(0xffffffffu, v, 8);
@@ -616,6 +761,7 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
   float* sKo = sB + Cfg::W_B;
   float* sBo = sKo + Cfg::W_KO;
   uint64_t* bar = reinterpret_cast<uint64_t*>(sBo + Cfg::W_BO);
+  unsigned* sWb = reinterpret_cast<unsigned*>(sBo + Cfg::W_BO + 4);     // bf16 images: [hi | lo][l][row][WSB]
   float* warp_base = smem + Cfg::W_TOTAL;
 
   const int tid = threadIdx.x, nthr = NW * 32;
@@ -646,6 +792,17 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
         tf32_hi_lo(w, hi, lo);
         sK[(l * H + k) * Cfg::WS + j] = __uint_as_float(hi);
         sKT[(l * H + k) * Cfg::WS + j] = __uint_as_float(lo);
+      }
+      if constexpr (Cfg::BWD_BF16) {
+        for (int idx = tid; idx < (L - 1) * H * (H / 2); idx += nthr) {     // word w of row r: (K[r][2w], K[r][2w+1]) as bf16
+          const int l = idx / (H * (H / 2)), r = (idx / (H / 2)) % H, w = idx % (H / 2);
+          const float w0 = raw[Cfg::offK(l + 2) + r * H + 2 * w], w1 = raw[Cfg::offK(l + 2) + r * H + 2 * w + 1];
+          unsigned h0, l0, h1, l1;
+          tf32_hi_lo(w0, h0, l0);
+          tf32_hi_lo(w1, h1, l1);
+          sWb[(l * H + r) * Cfg::WSB + w] = pack_bf16(w0, w1);
+          sWb[((L - 1) * H + l * H + r) * Cfg::WSB + w] = pack_bf16(w0 - __uint_as_float(h0), w1 - __uint_as_float(h1));
+        }
       }
     } else {
       for (int idx = tid; idx < Cfg::W_K; idx += nthr) {
@@ -968,7 +1125,11 @@ fused_step_kernel(const float* __restrict__ params, const SegDev* __restrict__ s
             for (int n = 0; n < 4; ++n)
 #pragma unroll
               for (int i = 0; i < 4; ++i) d[c][n][i] = 0.f;
-          warp_gemm_mma<Cfg, true>(Zl, sK + (l - 2) * H * Cfg::WS, sKT + (l - 2) * H * Cfg::WS, d, lr, lc);
+          if constexpr (Cfg::BWD_BF16)
+            warp_gemm_bwd_bf16<Cfg>(Zl, sK + (l - 2) * H * Cfg::WS, sWb + (l - 2) * H * Cfg::WSB,
+                                    sWb + ((L - 1) * H + (l - 2) * H) * Cfg::WSB, d, lr, lc);
+          else
+            warp_gemm_mma<Cfg, true>(Zl, sK + (l - 2) * H * Cfg::WS, sKT + (l - 2) * H * Cfg::WS, d, lr, lc);
 #pragma unroll
           for (int c = 0; c < C; ++c)
 #pragma unroll

@@ -250,7 +250,8 @@ def run_ours(args):
         # `peak` is the chip's tensor roofline for 3xTF32 (tcgen05 rate / 3); the path the kernel actually uses
         # (mma.sync.m16n8k8, tools/mma_sync_probe.cu) tops out lower -- both fractions are reported
         bound, peak, peak_src = "tensor", 368.4, "fallback"
-        kernel_name = "fused_step_kernel<D,H,L,O,ORDER=2,TRAIN> (mma.sync m16n8k8 tf32 x3 GEMMs, FFMA2 tanh-jet math)"
+        kernel_name = ("fused_step_kernel<D,H,L,O,ORDER=2,TRAIN> (mma.sync GEMMs: tf32 m16n8k8 x3 forward, tf32 + bf16 m16n8k16 "
+                       "correction passes in the gradient-only GEMMs; FFMA2 tanh-jet math)")
         extra = {}
         try:
             with open(os.path.join(ROOT, "profiles", "tf32_peak_r01.json")) as fh:

@@ -192,6 +192,12 @@ def run_ours(args):
     # ---- warm-up ---------------------------------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
         pb.training_step(opt)
+    # on one GPU the facade captures the step in a CUDA graph after three eager steps: that one-off capture (a host-side
+    # pause of several ms) belongs to the warm-up, whatever --warmup says
+    extra = 0
+    while getattr(pb, "_graph", None) is None and pb._graph_eligible(opt) and extra < 8:
+        pb.training_step(opt)
+        extra += 1
     launches_per_step = plan.last_launch_count() + 1   # + Adam kernel
     barrier()
 

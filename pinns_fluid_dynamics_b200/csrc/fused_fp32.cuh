@@ -16,7 +16,8 @@
 //   * hidden-layer GEMMs, two instantiations of the same kernel:
 //       TENSOR (H = 32, engine "fused_tf32x3"): mma.sync.m16n8k8 tf32 with the 3-pass hi/lo split -- forward
 //         [16C rows] x 32 x 32, input adjoint, weight gradient 32 x 32 over K = 16C; the lane's neurons are the
-//         accumulator columns {8n + 2lc + e}; see warp_gemm_mma / warp_wgrad_mma.
+//         accumulator columns {8n + 2lc + e}; the two gradient-only GEMMs run their correction passes as bf16
+//         m16n8k16; see warp_gemm_mma / warp_gemm_bwd_bf16 / warp_wgrad_mma.
 //       FP32 (H = 20, and H = 32 under PINN_ENGINE=fused_fp32, engine "fused_fp32"): register-tiled FFMA2, neurons
 //         {lc + 4jj}; per k-step a lane loads its two points' C channel values (C LDS.64) and TC weights (LDS.128,
 //         pre-permuted so they are contiguous per lane) and issues C*TC FFMA2.

@@ -137,3 +137,16 @@ def test_model_json_and_weights_export(tmp_path):
     assert torch.equal(m2.flat, model.flat)
     lim = np.sqrt(6.0 / (2 + 32))
     assert float(model.variables[0].abs().max()) <= lim and float(model.variables[1].abs().max()) == 0.0
+
+
+def test_host_objective_matches_evaluate():
+    """``evaluate_host`` (the objective SciPy-style drivers call) == ``evaluate`` at the same parameters; without CUDA it
+    takes the plain path through the injected engine."""
+    data, model, losses, ltest = _problem()
+    pb = ns.OptimizationProblem(model.variables, losses, ltest, engine_factory=TaylorEngine)
+    theta = pb.flat.detach().double().numpy().copy()
+    theta += 1e-3 * np.random.default_rng(0).standard_normal(theta.shape)
+    f, g = pb.evaluate_host(theta)
+    assert np.allclose(pb.flat.double().numpy(), theta.astype(np.float32).astype(np.float64))   # parameters were installed
+    total, _, grad = pb.evaluate()
+    assert f == total and np.array_equal(g, grad.double().numpy())

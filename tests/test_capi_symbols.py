@@ -43,3 +43,36 @@ def test_struct_layout_matches_header():
     assert C.sizeof(_capi.TermDesc) == 96 + 12 + 4 + 8 + 16 + 8 + 8
     assert C.sizeof(_capi.PointSetDesc) == 8 + 8 + 8 + 8 * C.sizeof(_capi.TermDesc)
     assert C.sizeof(_capi.MlpDesc) == 16
+
+
+def test_ctypes_structs_match_the_compiled_header(tmp_path):
+    """sizeof / offsetof of every ABI struct as gcc lays out include/pinnstep.h == the ctypes mirror in _capi.py."""
+    import ctypes as C
+    src = tmp_path / "layout.c"
+    src.write_text(r"""
+#include <stdio.h>
+#include <stddef.h>
+#include "pinnstep.h"
+int main(void) {
+  printf("term %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(pinn_term_desc), offsetof(pinn_term_desc, conv),
+         offsetof(pinn_term_desc, conv_k), offsetof(pinn_term_desc, rhs_scale), offsetof(pinn_term_desc, rhs_dev),
+         offsetof(pinn_term_desc, weight), offsetof(pinn_term_desc, normalization), offsetof(pinn_term_desc, n_global),
+         offsetof(pinn_term_desc, train), offsetof(pinn_term_desc, kind));
+  printf("set %zu %zu %zu %zu %zu\n", sizeof(pinn_pointset_desc), offsetof(pinn_pointset_desc, n_local),
+         offsetof(pinn_pointset_desc, n_terms), offsetof(pinn_pointset_desc, deriv_order), offsetof(pinn_pointset_desc, terms));
+  printf("mlp %zu\n", sizeof(pinn_mlp_desc));
+  printf("consts %d %d %d %d\n", PINN_MAX_OUT, PINN_MAX_CH, PINN_MAX_TERMS_PER_SET, PINN_VERSION);
+  return 0;
+}
+""")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    out = dict((l.split()[0], [int(v) for v in l.split()[1:]]) for l in
+               subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip().splitlines())
+    T, S = _capi.TermDesc, _capi.PointSetDesc
+    assert out["term"] == [C.sizeof(T)] + [getattr(T, f).offset for f in
+                                           ("conv", "conv_k", "rhs_scale", "rhs_dev", "weight", "normalization", "n_global", "train", "kind")]
+    assert out["set"] == [C.sizeof(S), S.n_local.offset, S.n_terms.offset, S.deriv_order.offset, S.terms.offset]
+    assert out["mlp"] == [C.sizeof(_capi.MlpDesc)]
+    lib = (_ensure_built(), _capi.load())[1]
+    assert out["consts"] == [_capi.MAX_OUT, _capi.MAX_CH, _capi.MAX_TERMS_PER_SET, lib.pinn_version()]

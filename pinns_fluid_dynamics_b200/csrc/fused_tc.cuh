@@ -1,0 +1,846 @@
+// Fused loss-step kernel for the 2-32x3-O tanh MLP with its hidden-layer GEMMs on tcgen05 (engine "fused_tcgen05").
+//
+// Same contract as fused_step_kernel (fused_fp32.cuh): Taylor-mode jets forward, residuals, weighted mean-square terms and the
+// hand-written reverse sweep to parameter gradients in ONE kernel, every activation on chip.  Replaces (reference, per epoch)
+// 3 x model(x) + 14 inner tape.gradient sweeps + nisaba's outer tape.gradient over the collocation set
+// (cavity_steady.py:159-188,212-214,242).
+//
+// Work decomposition (measurements behind every choice: profiles/tc_probes_r02.md)
+//   * a CTA (one per SM, persistent) works on a TILE of 128 points at a time.  TMEM lane = point: the 8 epilogue warps
+//     (2 per lane quadrant) own one point per thread and 16 of the 32 neurons each (warp w: points 32(w&3)..+31, neurons
+//     16(w>>2)..+15), so every channel of a (point, neuron) pair -- value, d/dx, d/dy, d2/dx2, d2/dy2 -- is in one thread and
+//     the tanh-jet math needs no cross-lane traffic.  Warp 8 issues the MMAs (whole warp in the loop, one lane by elect.sync:
+//     bare back-to-back UTCHMMA, 18 cycles each).
+//   * forward / input-adjoint GEMM of a hidden layer: per channel c an M = 128 (points) x N = 32 (neurons) x K = 32 tile,
+//     kind::tf32 with the 3-pass split x = hi + lo (lo*W_hi + hi*W_lo + hi*W_hi), FP32 accumulators in TENSOR MEMORY
+//     (columns 32c..), the activation operand ALSO in tensor memory (TS form: the epilogue threads write the hi / lo images of
+//     their own row with tcgen05.st -- no shared-memory operand traffic; from shared memory the same MMA costs 41 cycles
+//     instead of 18), weights as K-major hi / lo images in shared memory.  60 MMAs = 1075 cycles per layer and tile.
+//     The k-steps are issued as soon as the epilogue has produced the 8 neurons they contract over.
+//   * weight gradient K-bar_l = a_{l-1}^T z-bar_l (contraction over the 128 x C rows of the tile): kind::f16 (bf16) MMAs with
+//     BOTH operands MN-major straight from [row][neuron] images in shared memory, M = 64 = (hi | lo part) x 32 neurons,
+//     N = 32, K = 16 rows per instruction.  The a-jets and z-bars are kept in shared memory ONLY as these images: a bf16
+//     PAIR per value (b1 = bf16(x), b2 = bf16(x - b1): 16 mantissa bits), 4 bytes like the FP32 value they replace; the
+//     reverse sweep reads them back as b1 + b2 (they only feed gradients, tolerance 1e-4; the forward pass -- the loss
+//     values, tolerance 1e-5 -- never sees them: it goes registers -> tensor memory).  The accumulator (tensor memory,
+//     32 columns) is drained once per tile into FP32 totals in shared memory (the tensor core truncates when it adds).
+//   * small gradients (K1, b1, b_l, K_out, b_out): per-tile multi-value warp reductions into per-warp shared-memory
+//     accumulators; at the end the CTA writes ONE workspace row, finalize_rows_kernel sums the rows in a fixed order
+//     (no atomics anywhere: bit-reproducible).
+//
+// Tensor-memory map (512 columns, lane = point): D_c at 32c, A_c hi at 160 + 64c, lo at 160 + 64c + 32, W at 480.
+// Shared-memory map: TcCfg.
+#pragma once
+#include "fused_fp32.cuh"
+
+namespace pinn {
+namespace ftc {
+
+template <int D_, int O_>
+struct TcCfg {
+  static constexpr int D = D_, H = 32, L = 3, O = O_, ORDER = 2;
+  static constexpr int C = 3 + D;
+  static constexpr int SX = D - 2, SY = D - 1;
+  static constexpr int TP = 128;                    // points per tile
+  static constexpr int NEPI = 8;                    // epilogue warps
+  static constexpr int THREADS = 32 * (NEPI + 1);   // + the MMA warp
+  static_assert(D == 2, "tensor-memory budget: 32C + 64C + 32 columns <= 512 needs C = 5");
+  static constexpr uint32_t COL_D = 0, COL_A = 32 * C, COL_W = COL_A + 64 * C;
+  static_assert(COL_W + 32 <= 512, "tensor memory exhausted");
+  // shared memory (bytes)
+  static constexpr int IMG_BYTES = C * TP * 32 * 4;               // [row = (c, p)][neuron] bf16 pairs: 81920
+  static constexpr int OFF_X = 0, OFF_Y = IMG_BYTES;
+  static constexpr int OFF_A1 = 2 * IMG_BYTES;                    // tanh(z1): a1[j][p] fp32
+  static constexpr int OFF_W = OFF_A1 + 32 * TP * 4;              // weight images [(l-2)][fwd|bwd][hi|lo] of 4096 bytes
+  static constexpr int OFF_TOT = OFF_W + 8 * 4096;                // weight-gradient totals [2][32][32] fp32
+  static constexpr int OFF_SMALL = OFF_TOT + 2 * 32 * 32 * 4;     // K1 [D][32] | b [3][32] | K_out [32][4] | b_out [4]
+  static constexpr int S_K1 = 0, S_B = D * 32, S_KO = S_B + 3 * 32, S_BO = S_KO + 32 * 4, SMALL_FLOATS = S_BO + 4;
+  static constexpr int OFF_SG = OFF_SMALL + SMALL_FLOATS * 4;     // per epilogue warp: small-gradient accumulators of its 16 neurons
+  static constexpr int SG_K1 = 0, SG_B1 = D * 16, SG_B2 = SG_B1 + 16, SG_B3 = SG_B2 + 16, SG_KO = SG_B3 + 16, SG_BO = SG_KO + 64,
+                       SG_FLOATS = SG_BO + 4;
+  static constexpr int OFF_SSQ = OFF_SG + NEPI * SG_FLOATS * 4;   // per epilogue warp: sum r^2 per term slot
+  static constexpr int OFF_BAR = OFF_SSQ + NEPI * kMaxLaunchTerms * 4;
+  static constexpr int SMEM_BYTES = OFF_BAR + 16 * 8;
+  static_assert(SMEM_BYTES <= 232448, "shared memory exhausted");
+  static constexpr int P = D * H + H + (L - 1) * (H * H + H) + H * O + O;
+  static_assert(P * 4 <= IMG_BYTES, "parameter staging area");
+  __host__ __device__ static constexpr int offK(int l) { return D * H + H + (l - 2) * (H * H + H); }   // l = 2..L
+  static constexpr int OFF_KO = D * H + H + (L - 1) * (H * H + H);
+  static constexpr int OFF_BO = OFF_KO + H * O;
+};
+
+// barriers (uint64 slots at OFF_BAR)
+enum { B_AREADY = 0 /* ..3 */, B_DLOADED = 4, B_DFULL = 5, B_IMG = 6, B_WDONE = 7, B_STAGE = 8 };
+
+// ---- PTX helpers ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__host__ __device__ constexpr uint32_t idesc_bf16(int m, int n, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d),
+               "r"(a), "l"(b), "r"(idesc), "r"(acc)
+               : "memory");
+}
+__device__ __forceinline__ void mma_bf16_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d),
+               "l"(a), "l"(b), "r"(idesc), "r"(acc)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {   // thread i of the warp: lane (quadrant base + i), 16 columns
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]),
+        "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]), "f"(v[10]),
+      "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8u(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// x = hi + lo, hi rounded to tf32; the tensor core truncates the 13 low bits of lo: half an ulp added first makes that a rounding
+__device__ __forceinline__ void split_hi_lo(float x, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
+  lo = __float_as_uint(x - __uint_as_float(hi)) + 0x1000u;
+}
+// two neighbouring neurons as bf16 pairs: p1 = (bf16(x0) | bf16(x1) << 16), p2 the same of the remainders
+__device__ __forceinline__ void bf16_pair(float x0, float x1, uint32_t& p1, uint32_t& p2) {
+  p1 = pack_bf16(x0, x1);
+  p2 = pack_bf16(x0 - __uint_as_float(p1 << 16), x1 - __uint_as_float(p1 & 0xFFFF0000u));
+}
+__device__ __forceinline__ float2 bf16_unpair(uint32_t p1, uint32_t p2) {
+  return make_float2(__uint_as_float(p1 << 16) + __uint_as_float(p2 << 16),
+                     __uint_as_float(p1 & 0xFFFF0000u) + __uint_as_float(p2 & 0xFFFF0000u));
+}
+
+// sums of V per-lane values over the 32 lanes of a warp by halving exchanges: V = 8 m values v[m * n8 + t] (n8 = 0..7) end
+// up in the lanes with (lane & 3) == 0 as v[t], t < m, of n8 = lane >> 2   (V + ~2 shuffles instead of 5 V)
+template <int V, int S>
+__device__ __forceinline__ void xr_step(float* v, int lane) {
+  const bool up = (lane & S) != 0;
+#pragma unroll
+  for (int i = 0; i < V / 2; ++i) {
+    const float keep = up ? v[i + V / 2] : v[i];
+    const float send = up ? v[i] : v[i + V / 2];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, S);
+  }
+}
+template <int M>
+__device__ __forceinline__ void xreduce8(float (&v)[8 * M], int lane) {
+  xr_step<8 * M, 16>(v, lane);
+  xr_step<4 * M, 8>(v, lane);
+  xr_step<2 * M, 4>(v, lane);
+#pragma unroll
+  for (int i = 0; i < M; ++i) {
+    v[i] += __shfl_xor_sync(0xffffffffu, v[i], 2);
+    v[i] += __shfl_xor_sync(0xffffffffu, v[i], 1);
+  }
+}
+
+// hi / lo images of 8 neurons x C channels of this thread's row into tensor memory (operand of the next GEMM)
+template <int C>
+__device__ __forceinline__ void emit_operand(const float2 (&v)[C][4], uint32_t tm_a) {
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int pr = 0; pr < 4; ++pr) {
+      split_hi_lo(v[c][pr].x, hi[2 * pr], lo[2 * pr]);
+      split_hi_lo(v[c][pr].y, hi[2 * pr + 1], lo[2 * pr + 1]);
+    }
+    tmem_st8u(tm_a + 64u * c, hi);
+    tmem_st8u(tm_a + 64u * c + 32u, lo);
+  }
+}
+// bf16-pair images of the same values: rows (c, p), 8 neurons = 16 bytes per part
+template <int C>
+__device__ __forceinline__ void pack_images(const float2 (&v)[C][4], uint4 (&p1)[C], uint4 (&p2)[C]) {
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    bf16_pair(v[c][0].x, v[c][0].y, p1[c].x, p2[c].x);
+    bf16_pair(v[c][1].x, v[c][1].y, p1[c].y, p2[c].y);
+    bf16_pair(v[c][2].x, v[c][2].y, p1[c].z, p2[c].z);
+    bf16_pair(v[c][3].x, v[c][3].y, p1[c].w, p2[c].w);
+  }
+}
+template <int C>
+__device__ __forceinline__ void store_images(uint8_t* img_thr_g, const uint4 (&p1)[C], const uint4 (&p2)[C]) {
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    *reinterpret_cast<uint4*>(img_thr_g + c * 16384) = p1[c];
+    *reinterpret_cast<uint4*>(img_thr_g + c * 16384 + 128) = p2[c];
+  }
+}
+
+template <int D, int O, bool TRAIN>
+__global__ void __launch_bounds__(TcCfg<D, O>::THREADS, 1)
+fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ segs, int n_segs, int total_tiles,
+                float* __restrict__ ws, int ws_stride, int n_terms_total, int params_aligned) {
+  using Cfg = TcCfg<D, O>;
+  constexpr int C = Cfg::C, H = 32, P = Cfg::P, SX = Cfg::SX, SY = Cfg::SY;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* imgX = smem + Cfg::OFF_X;
+  uint8_t* imgY = smem + Cfg::OFF_Y;
+  float* a1buf = reinterpret_cast<float*>(smem + Cfg::OFF_A1);
+  float* wimg = reinterpret_cast<float*>(smem + Cfg::OFF_W);
+  float* tot = reinterpret_cast<float*>(smem + Cfg::OFF_TOT);
+  float* small = reinterpret_cast<float*>(smem + Cfg::OFF_SMALL);
+  float* sK1 = small + Cfg::S_K1;
+  float* sB = small + Cfg::S_B;
+  float* sKo = small + Cfg::S_KO;
+  float* sBo = small + Cfg::S_BO;
+  float* sg_all = reinterpret_cast<float*>(smem + Cfg::OFF_SG);
+  float* ssq_all = reinterpret_cast<float*>(smem + Cfg::OFF_SSQ);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 12);
+
+  const int tid = threadIdx.x, nthr = Cfg::THREADS;
+  const int lane = tid & 31, warp = tid >> 5;
+
+  // ---- stage the parameter vector (one TMA bulk copy + tail), build the operand images ------------------------------
+  {
+    float* raw = reinterpret_cast<float*>(imgX);
+    const uint32_t bulk_bytes = params_aligned ? ((uint32_t)(P * 4) & ~15u) : 0u;
+    if (tid == 0) {
+      mbar_init(&bar[B_AREADY + 0], 4);
+      mbar_init(&bar[B_AREADY + 1], 4);
+      mbar_init(&bar[B_AREADY + 2], 4);
+      mbar_init(&bar[B_AREADY + 3], 4);
+      mbar_init(&bar[B_DLOADED], Cfg::NEPI);
+      mbar_init(&bar[B_DFULL], 1);
+      mbar_init(&bar[B_IMG], Cfg::NEPI);
+      mbar_init(&bar[B_WDONE], 1);
+      mbar_init(&bar[B_STAGE], 1);
+      fence_barrier_init();
+    }
+    __syncthreads();
+    if (tid == 0 && bulk_bytes) {
+      mbar_expect_tx(&bar[B_STAGE], bulk_bytes);
+      tma_bulk_g2s(raw, params, bulk_bytes, &bar[B_STAGE]);
+    }
+    for (int i = (int)(bulk_bytes / 4) + tid; i < P; i += nthr) raw[i] = __ldg(params + i);
+    if (bulk_bytes) mbar_wait(&bar[B_STAGE], 0);
+    __syncthreads();
+    // K-major operand images of the 32 x 32 matrices (rows n, contraction index k: umma::tile_offset, SBO = 1024):
+    //   forward  D[p][j] = sum_k a[p][k] K_l[k][j]:  B[n = j][k]      = K_l[k][j]
+    //   adjoint  D[p][k] = sum_j z[p][j] K_l[k][j]:  B[n = k][kk = j] = K_l[k][j]
+    for (int idx = tid; idx < 2 * H * H; idx += nthr) {
+      const int l = idx / (H * H), r = (idx / H) % H, c = idx % H;   // r = row of K_l (k), c = column (j)
+      const float w = raw[Cfg::offK(l + 2) + r * H + c];
+      uint32_t hi, lo;
+      split_hi_lo(w, hi, lo);
+      const uint32_t of = umma::tile_offset(c, r, 1024) / 4, ob = umma::tile_offset(r, c, 1024) / 4;
+      float* base = wimg + l * 4096;   // 4 images of 1024 floats per layer
+      base[of] = __uint_as_float(hi);
+      base[1024 + of] = __uint_as_float(lo);
+      base[2048 + ob] = __uint_as_float(hi);
+      base[3072 + ob] = __uint_as_float(lo);
+    }
+    for (int idx = tid; idx < D * H; idx += nthr) sK1[idx] = raw[idx];
+    for (int idx = tid; idx < 3 * H; idx += nthr) {
+      const int l = idx / H, j = idx % H;
+      sB[idx] = (l == 0) ? raw[D * H + j] : raw[Cfg::offK(l + 1) + H * H + j];
+    }
+    for (int idx = tid; idx < H * 4; idx += nthr) {
+      const int j = idx >> 2, o = idx & 3;
+      sKo[idx] = (o < O) ? raw[Cfg::OFF_KO + j * O + o] : 0.f;
+    }
+    if (tid < 4) sBo[tid] = (tid < O) ? raw[Cfg::OFF_BO + tid] : 0.f;
+    for (int idx = tid; idx < 2 * H * H; idx += nthr) tot[idx] = 0.f;
+    for (int idx = tid; idx < Cfg::NEPI * Cfg::SG_FLOATS; idx += nthr) sg_all[idx] = 0.f;
+    for (int idx = tid; idx < Cfg::NEPI * kMaxLaunchTerms; idx += nthr) ssq_all[idx] = 0.f;
+    if (warp == Cfg::NEPI) umma::tmem_alloc<512>(tslot);
+    umma::fence_proxy_async_smem();
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    umma::fence_after_thread_sync();
+  }
+  const uint32_t tmem = *tslot;
+  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
+
+  if (warp == Cfg::NEPI) {
+    // ================================ MMA warp =====================================================================
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_g = umma::idesc_tf32(128, 32);
+    constexpr uint32_t idesc_w = idesc_bf16(64, 32, 1, 1);
+    uint32_t ph_a = 0, ph_dl = 0, ph_img = 0;   // bit g of ph_a: parity of a_ready[g]
+    bool first_gemm = true;
+    // one forward / adjoint GEMM over the 5 channel tiles: image index 0..3 = (layer, direction)
+    auto gemm = [&](int image) {
+      if (!first_gemm) {                       // the epilogue has read the previous accumulators out of tensor memory
+        mbar_wait(&bar[B_DLOADED], ph_dl);
+        ph_dl ^= 1u;
+      }
+      first_gemm = false;
+      const uint64_t wh = umma::smem_desc(smem_base + Cfg::OFF_W + image * 8192, 128, 1024);
+      const uint64_t wl = umma::smem_desc(smem_base + Cfg::OFF_W + image * 8192 + 4096, 128, 1024);
+#pragma unroll
+      for (int gi = 0; gi < 4; ++gi) {
+        const int g = (gi & 1) * 2 + (gi >> 1);          // readiness order of the k-steps: 0, 2, 1, 3
+        mbar_wait(&bar[B_AREADY + g], (ph_a >> g) & 1u);
+        ph_a ^= 1u << g;
+        umma::fence_after_thread_sync();
+        if (leader) {
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const uint32_t d = tmem + Cfg::COL_D + 32u * c;
+            const uint32_t ah = tmem + Cfg::COL_A + 64u * c + 8u * g, al = ah + 32u;
+            mma_tf32_ts(d, al, wh + (uint64_t)(g * 16), idesc_g, gi > 0 ? 1u : 0u);
+            mma_tf32_ts(d, ah, wl + (uint64_t)(g * 16), idesc_g, 1u);
+            mma_tf32_ts(d, ah, wh + (uint64_t)(g * 16), idesc_g, 1u);
+          }
+        }
+        __syncwarp();
+      }
+      if (leader) umma::commit(&bar[B_DFULL]);
+      __syncwarp();
+    };
+    // weight gradient of one layer: D_w[(k-octet, part, k % 8)][j] = sum_rows a[row][k] z[row][j]
+    auto wgrad = [&](int a_off, int z_off) {
+      mbar_wait(&bar[B_IMG], ph_img);
+      ph_img ^= 1u;
+      umma::fence_after_thread_sync();
+      if (leader) {
+        const uint64_t ad = umma::smem_desc(smem_base + a_off, 1024, 128);          // M = 64: all 8 (octet, part) blocks of a k-block
+        const uint64_t z1 = umma::smem_desc(smem_base + z_off, 1024, 256);          // N = 32: the b1 blocks
+        const uint64_t z2 = umma::smem_desc(smem_base + z_off + 128, 1024, 256);    //         the b2 blocks
+#pragma unroll 4
+        for (int ks = 0; ks < C * Cfg::TP / 16; ++ks) {
+          mma_bf16_ss(tmem + Cfg::COL_W, ad + (uint64_t)(ks * 128), z1 + (uint64_t)(ks * 128), idesc_w, ks > 0 ? 1u : 0u);
+          mma_bf16_ss(tmem + Cfg::COL_W, ad + (uint64_t)(ks * 128), z2 + (uint64_t)(ks * 128), idesc_w, 1u);
+        }
+        umma::commit(&bar[B_WDONE]);
+      }
+      __syncwarp();
+    };
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      gemm(0);                                  // layer 2 forward
+      gemm(2);                                  // layer 3 forward
+      if constexpr (TRAIN) {
+        gemm(3);                                // layer 3 adjoint: a-bar_2 = z-bar_3 K_3^T
+        wgrad(Cfg::OFF_X, Cfg::OFF_Y);          // K-bar_3 = a_2^T z-bar_3
+        gemm(1);                                // layer 2 adjoint
+        wgrad(Cfg::OFF_Y, Cfg::OFF_X);          // K-bar_2 = a_1^T z-bar_2
+      }
+    }
+  } else {
+    // ================================ epilogue warps ================================================================
+    const int q = warp & 3, h = warp >> 2;
+    const int p = 32 * q + lane;                                   // point of the tile = tensor-memory lane
+    const uint32_t tm_lane = tmem + ((uint32_t)(32 * q) << 16);
+    const int img_thr = (p >> 3) * 1024 + (p & 7) * 16;            // byte offset of row (c = 0, p) in an image, neuron octet 0, part b1
+    float* sg = sg_all + warp * Cfg::SG_FLOATS;
+    float* ssq = ssq_all + warp * kMaxLaunchTerms;
+    uint32_t ph_df = 0, ph_wd = 0;
+    bool w_pending = false;                                        // a weight-gradient MMA batch not yet drained
+
+    // accumulator of the finished weight-gradient batch -> FP32 totals of layer index li (0: K_2, 1: K_3)
+    auto drain_w = [&](int li) {
+      mbar_wait(&bar[B_WDONE], ph_wd);
+      ph_wd ^= 1u;
+      umma::fence_after_thread_sync();
+      if (h == 0) {
+        float v[32];
+        tmem_ld32(tm_lane + Cfg::COL_W, v);
+        // quadrant q holds rows 16q..16q+15 of the M = 64 accumulator: lanes 0-7 the b1 part of neurons 8q..8q+7, lanes 8-15 the b2 part
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += __shfl_down_sync(0xffffffffu, v[j], 8);
+        if (lane < 8) {
+          float4* t4 = reinterpret_cast<float4*>(tot + li * 1024 + (8 * q + lane) * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 t = t4[j];
+            t.x += v[4 * j]; t.y += v[4 * j + 1]; t.z += v[4 * j + 2]; t.w += v[4 * j + 3];
+            t4[j] = t;
+          }
+        }
+        umma::fence_before_thread_sync();
+      }
+    };
+
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int si = 0;
+      while (si + 1 < n_segs && tile >= __ldg(&segs[si + 1].chunk_begin)) ++si;
+      const SegDev* __restrict__ seg = segs + si;
+      const long long n = seg->n;
+      const long long pg = (long long)(tile - seg->chunk_begin) * Cfg::TP + p;
+      const bool valid = pg < n;
+      const long long pi = valid ? pg : n - 1;
+      float x[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) x[i] = __ldg(seg->pts + pi * D + i);
+
+      // ---- layer 1: z = x K1 + b1, a = tanh z; jets straight into the operand of the layer-2 GEMM ------------------
+#pragma unroll
+      for (int gi = 0; gi < 2; ++gi) {
+        const int g = 2 * h + gi;
+        float2 v[C][4];
+#pragma unroll
+        for (int pr = 0; pr < 4; ++pr) {
+          const int j = 8 * g + 2 * pr;
+          float2 z = *reinterpret_cast<const float2*>(sB + j);
+          float2 zd[D], a[C];
+#pragma unroll
+          for (int i = 0; i < D; ++i) {
+            zd[i] = *reinterpret_cast<const float2*>(sK1 + i * H + j);
+            z = fma2(bc2(x[i]), zd[i], z);
+          }
+          const float2 a0 = tanh2(z);
+          if constexpr (TRAIN) {
+            a1buf[j * Cfg::TP + p] = a0.x;
+            a1buf[(j + 1) * Cfg::TP + p] = a0.y;
+          }
+          jet2_from_a0<Cfg>(a0, zd, bc2(0.f), bc2(0.f), a);
+#pragma unroll
+          for (int c = 0; c < C; ++c) v[c][pr] = a[c];
+        }
+        emit_operand<C>(v, tm_lane + Cfg::COL_A + 8u * g);
+        tmem_wait_st();
+        umma::fence_before_thread_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar[B_AREADY + g]);
+      }
+
+      // ---- layer 2: accumulators -> tanh jets -> operand of the layer-3 GEMM (+ images of a_2 for the reverse sweep) ---
+      {
+        mbar_wait(&bar[B_DFULL], ph_df);
+        ph_df ^= 1u;
+        umma::fence_after_thread_sync();
+        float d[C][16];
+#pragma unroll
+        for (int c = 0; c < C; ++c) tmem_ld16(tm_lane + Cfg::COL_D + 32u * c + 16u * h, d[c]);
+        umma::fence_before_thread_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar[B_DLOADED]);
+        if constexpr (TRAIN) {
+          if (w_pending) {                     // K-bar_2 batch of the previous tile: drain before image X is overwritten
+            drain_w(0);
+            w_pending = false;
+          }
+        }
+#pragma unroll
+        for (int gi = 0; gi < 2; ++gi) {
+          const int g = 2 * h + gi;
+          float2 v[C][4];
+#pragma unroll
+          for (int pr = 0; pr < 4; ++pr) {
+            const int j = 8 * g + 2 * pr;
+            const float2 b = *reinterpret_cast<const float2*>(sB + H + j);
+            float2 zd[D], a[C];
+#pragma unroll
+            for (int i = 0; i < D; ++i) zd[i] = make_float2(d[1 + i][8 * gi + 2 * pr], d[1 + i][8 * gi + 2 * pr + 1]);
+            const float2 zxx = make_float2(d[1 + D][8 * gi + 2 * pr], d[1 + D][8 * gi + 2 * pr + 1]);
+            const float2 zyy = make_float2(d[2 + D][8 * gi + 2 * pr], d[2 + D][8 * gi + 2 * pr + 1]);
+            const float2 z0 = add2(make_float2(d[0][8 * gi + 2 * pr], d[0][8 * gi + 2 * pr + 1]), b);
+            jet2_from_a0<Cfg>(tanh2(z0), zd, zxx, zyy, a);
+#pragma unroll
+            for (int c = 0; c < C; ++c) v[c][pr] = a[c];
+          }
+          emit_operand<C>(v, tm_lane + Cfg::COL_A + 8u * g);
+          if constexpr (TRAIN) {
+            uint4 p1[C], p2[C];
+            pack_images<C>(v, p1, p2);
+            store_images<C>(imgX + img_thr + g * 256, p1, p2);
+          }
+          tmem_wait_st();
+          umma::fence_before_thread_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar[B_AREADY + g]);
+        }
+      }
+
+      // ---- layer 3 + output layer + residuals (+ z-bar_3) ----------------------------------------------------------
+      float a3[C][16];                         // a-jets of layer 3 of this thread's 16 neurons
+      float J[C][O];
+      {
+        mbar_wait(&bar[B_DFULL], ph_df);
+        ph_df ^= 1u;
+        umma::fence_after_thread_sync();
+        float d[C][16];
+#pragma unroll
+        for (int c = 0; c < C; ++c) tmem_ld16(tm_lane + Cfg::COL_D + 32u * c + 16u * h, d[c]);
+        umma::fence_before_thread_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar[B_DLOADED]);
+        float2 Jp[C][O];
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+#pragma unroll
+          for (int o = 0; o < O; ++o) Jp[c][o] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int n2 = 0; n2 < 8; ++n2) {
+          const int j = 16 * h + 2 * n2;
+          const float2 b = *reinterpret_cast<const float2*>(sB + 2 * H + j);
+          float2 zd[D], a[C];
+#pragma unroll
+          for (int i = 0; i < D; ++i) zd[i] = make_float2(d[1 + i][2 * n2], d[1 + i][2 * n2 + 1]);
+          const float2 zxx = make_float2(d[1 + D][2 * n2], d[1 + D][2 * n2 + 1]);
+          const float2 zyy = make_float2(d[2 + D][2 * n2], d[2 + D][2 * n2 + 1]);
+          const float2 z0 = add2(make_float2(d[0][2 * n2], d[0][2 * n2 + 1]), b);
+          jet2_from_a0<Cfg>(tanh2(z0), zd, zxx, zyy, a);
+          const float4 k0 = *reinterpret_cast<const float4*>(sKo + j * 4), k1 = *reinterpret_cast<const float4*>(sKo + j * 4 + 4);
+          const float kv0[4] = {k0.x, k0.y, k0.z, k0.w}, kv1[4] = {k1.x, k1.y, k1.z, k1.w};
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            a3[c][2 * n2] = a[c].x;
+            a3[c][2 * n2 + 1] = a[c].y;
+#pragma unroll
+            for (int o = 0; o < O; ++o) Jp[c][o] = fma2(a[c], make_float2(kv0[o], kv1[o]), Jp[c][o]);
+          }
+        }
+        // the other half of the neurons lives in the partner warp (same lanes): exchange the partial output jets through
+        // tensor memory -- each thread writes into the columns its partner will later overwrite with its own operand
+        float mine[16], theirs[16];
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+#pragma unroll
+          for (int o = 0; o < O; ++o) mine[c * O + o] = Jp[c][o].x + Jp[c][o].y;
+#pragma unroll
+        for (int i = C * O; i < 16; ++i) mine[i] = 0.f;
+        tmem_st16(tm_lane + Cfg::COL_A + 16u * (1 - h), mine);
+        tmem_wait_st();
+        umma::fence_before_thread_sync();
+        named_bar_sync(1 + q, 64);
+        umma::fence_after_thread_sync();
+        tmem_ld16(tm_lane + Cfg::COL_A + 16u * h, theirs);
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+#pragma unroll
+          for (int o = 0; o < O; ++o) J[c][o] = mine[c * O + o] + theirs[c * O + o] + (c == 0 ? sBo[o] : 0.f);
+      }
+      if (seg->y_out != nullptr && h == 0 && valid) {
+        float* y = seg->y_out;
+#pragma unroll
+        for (int o = 0; o < O; ++o) y[pg * O + o] = J[0][o];
+      }
+
+      // ---- residuals, sums of squares, adjoint of the output jets --------------------------------------------------
+      float Jb[C][O];
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+#pragma unroll
+        for (int o = 0; o < O; ++o) Jb[c][o] = 0.f;
+      const int n_terms = seg->n_terms;
+#pragma unroll 1
+      for (int t = 0; t < n_terms; ++t) {
+        const TermDev* __restrict__ T = seg->terms + t;
+        if (TRAIN && !T->train) continue;
+        float r = 0.f;
+#pragma unroll
+        for (int o = 0; o < O; ++o)
+#pragma unroll
+          for (int c = 0; c < C; ++c) r = fmaf(__ldg(&T->coef[o][c]), J[c][o], r);
+        float cv = 0.f;
+        int ck = 0;
+        if constexpr (O >= 2) {
+          cv = __ldg(&T->conv);
+          ck = __ldg(&T->conv_k);
+          const float ukx = ck == 0 ? J[1 + SX][0] : J[1 + SX][1];
+          const float uky = ck == 0 ? J[1 + SY][0] : J[1 + SY][1];
+          r = fmaf(cv, fmaf(J[0][0], ukx, J[0][1] * uky), r);
+        }
+        const float* rhs = T->rhs;
+        if (rhs != nullptr) r = fmaf(-__ldg(&T->rhs_scale), __ldg(rhs + pi), r);
+        r = valid ? r : 0.f;
+        const bool abs_mean = __ldg(&T->kind) != 0;
+        if (h == 0) {                          // both halves hold the same residual: one of them adds it up
+          float sq = abs_mean ? r : r * r;
+          sq = reduce_warp(sq);
+          if (lane == 0) ssq[T->out_index] += sq;
+        }
+        if constexpr (TRAIN) {
+          float rb = __ldg(&T->scale) * r;
+          if (abs_mean) rb = valid ? __ldg(&T->scale) * __ldg(T->sign) : 0.f;
+#pragma unroll
+          for (int o = 0; o < O; ++o)
+#pragma unroll
+            for (int c = 0; c < C; ++c) Jb[c][o] = fmaf(__ldg(&T->coef[o][c]), rb, Jb[c][o]);
+          if constexpr (O >= 2) {
+            const float ukx = ck == 0 ? J[1 + SX][0] : J[1 + SX][1];
+            const float uky = ck == 0 ? J[1 + SY][0] : J[1 + SY][1];
+            const float m = cv * rb;
+            Jb[0][0] = fmaf(m, ukx, Jb[0][0]);
+            Jb[0][1] = fmaf(m, uky, Jb[0][1]);
+            const float m0 = ck == 0 ? m : 0.f, m1 = ck == 0 ? 0.f : m;
+            Jb[1 + SX][0] = fmaf(m0, J[0][0], Jb[1 + SX][0]);
+            Jb[1 + SY][0] = fmaf(m0, J[0][1], Jb[1 + SY][0]);
+            Jb[1 + SX][1] = fmaf(m1, J[0][0], Jb[1 + SX][1]);
+            Jb[1 + SY][1] = fmaf(m1, J[0][1], Jb[1 + SY][1]);
+          }
+        }
+      }
+
+      if constexpr (TRAIN) {
+        // ---- output layer backward + tanh-jet backward of layer 3: z-bar_3 -> operand of the adjoint GEMM + image Y ----
+        if (h == 0) {
+#pragma unroll
+          for (int o = 0; o < O; ++o) {
+            const float vsum = reduce_warp(Jb[0][o]);
+            if (lane == 0) sg[Cfg::SG_BO + o] += vsum;
+          }
+        }
+#pragma unroll
+        for (int gi = 0; gi < 2; ++gi) {
+          const int g = 2 * h + gi;
+          float2 v[C][4];
+          float gko[24], gb[8];
+#pragma unroll
+          for (int pr = 0; pr < 4; ++pr) {
+            const int n2 = 4 * gi + pr, j = 16 * h + 2 * n2;
+            const float4 k0 = *reinterpret_cast<const float4*>(sKo + j * 4), k1 = *reinterpret_cast<const float4*>(sKo + j * 4 + 4);
+            const float kv0[4] = {k0.x, k0.y, k0.z, k0.w}, kv1[4] = {k1.x, k1.y, k1.z, k1.w};
+            float2 aj[C], ab[C], zb[C], zdummy[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) zdummy[i] = bc2(0.f);
+            float2 pk[O];
+#pragma unroll
+            for (int o = 0; o < O; ++o) pk[o] = bc2(0.f);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              aj[c] = make_float2(a3[c][2 * n2], a3[c][2 * n2 + 1]);
+              float2 b = bc2(0.f);
+#pragma unroll
+              for (int o = 0; o < O; ++o) {
+                b = fma2(bc2(Jb[c][o]), make_float2(kv0[o], kv1[o]), b);
+                pk[o] = fma2(aj[c], bc2(Jb[c][o]), pk[o]);
+              }
+              ab[c] = b;
+            }
+#pragma unroll
+            for (int o = 0; o < 3; ++o) {
+              gko[3 * (2 * pr) + o] = o < O ? pk[o < O ? o : 0].x : 0.f;
+              gko[3 * (2 * pr + 1) + o] = o < O ? pk[o < O ? o : 0].y : 0.f;
+            }
+            tanh_jet2_bwd<Cfg, false>(aj, zdummy, ab, zb);
+            gb[2 * pr] = zb[0].x;
+            gb[2 * pr + 1] = zb[0].y;
+#pragma unroll
+            for (int c = 0; c < C; ++c) v[c][pr] = zb[c];
+          }
+          emit_operand<C>(v, tm_lane + Cfg::COL_A + 8u * g);
+          {
+            uint4 p1[C], p2[C];
+            pack_images<C>(v, p1, p2);
+            store_images<C>(imgY + img_thr + g * 256, p1, p2);
+          }
+          tmem_wait_st();
+          umma::fence_before_thread_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar[B_AREADY + g]);
+          // K_out and b_3 gradients of these 8 neurons: sums over the warp's 32 points
+          xreduce8<3>(gko, lane);
+          xreduce8<1>(gb, lane);
+          if ((lane & 3) == 0) {
+            const int n16 = 8 * gi + (lane >> 2);
+#pragma unroll
+            for (int o = 0; o < 3; ++o) sg[Cfg::SG_KO + n16 * 4 + o] += gko[o];
+            sg[Cfg::SG_B3 + n16] += gb[0];
+          }
+        }
+        umma::fence_proxy_async_smem();        // images X (a_2) and Y (z-bar_3) -> visible to the weight-gradient MMAs
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar[B_IMG]);
+
+        // ---- layer 2 backward: a-bar_2 (accumulators) + a_2 (image X) -> z-bar_2 ------------------------------------
+        {
+          mbar_wait(&bar[B_DFULL], ph_df);
+          ph_df ^= 1u;
+          umma::fence_after_thread_sync();
+          float d[C][16];
+#pragma unroll
+          for (int c = 0; c < C; ++c) tmem_ld16(tm_lane + Cfg::COL_D + 32u * c + 16u * h, d[c]);
+          umma::fence_before_thread_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar[B_DLOADED]);
+          uint4 zp1[2][C], zp2[2][C];          // images of z-bar_2: written once the K-bar_3 MMAs have finished reading X and Y
+#pragma unroll
+          for (int gi = 0; gi < 2; ++gi) {
+            const int g = 2 * h + gi;
+            float2 v[C][4];
+            float gb[8];
+            uint4 q1[C], q2[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              q1[c] = *reinterpret_cast<const uint4*>(imgX + img_thr + g * 256 + c * 16384);
+              q2[c] = *reinterpret_cast<const uint4*>(imgX + img_thr + g * 256 + c * 16384 + 128);
+            }
+#pragma unroll
+            for (int pr = 0; pr < 4; ++pr) {
+              float2 aj[C], ab[C], zb[C], zdummy[D];
+#pragma unroll
+              for (int i = 0; i < D; ++i) zdummy[i] = bc2(0.f);
+#pragma unroll
+              for (int c = 0; c < C; ++c) {
+                const uint32_t w1 = pr == 0 ? q1[c].x : pr == 1 ? q1[c].y : pr == 2 ? q1[c].z : q1[c].w;
+                const uint32_t w2 = pr == 0 ? q2[c].x : pr == 1 ? q2[c].y : pr == 2 ? q2[c].z : q2[c].w;
+                aj[c] = bf16_unpair(w1, w2);
+                ab[c] = make_float2(d[c][8 * gi + 2 * pr], d[c][8 * gi + 2 * pr + 1]);
+              }
+              tanh_jet2_bwd<Cfg, false>(aj, zdummy, ab, zb);
+              gb[2 * pr] = zb[0].x;
+              gb[2 * pr + 1] = zb[0].y;
+#pragma unroll
+              for (int c = 0; c < C; ++c) v[c][pr] = zb[c];
+            }
+            emit_operand<C>(v, tm_lane + Cfg::COL_A + 8u * g);
+            pack_images<C>(v, zp1[gi], zp2[gi]);
+            tmem_wait_st();
+            umma::fence_before_thread_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar[B_AREADY + g]);
+            xreduce8<1>(gb, lane);
+            if ((lane & 3) == 0) sg[Cfg::SG_B2 + 8 * gi + (lane >> 2)] += gb[0];
+          }
+          drain_w(1);                          // K-bar_3 batch finished: its accumulator -> totals; X and Y are free
+#pragma unroll
+          for (int gi = 0; gi < 2; ++gi) {
+            const int g = 2 * h + gi;
+            store_images<C>(imgX + img_thr + g * 256, zp1[gi], zp2[gi]);
+            // a_1 jets re-materialised from tanh(z1) into image Y (left operand of the K-bar_2 MMAs)
+            float2 v[C][4];
+#pragma unroll
+            for (int pr = 0; pr < 4; ++pr) {
+              const int j = 8 * g + 2 * pr;
+              const float2 a0 = make_float2(a1buf[j * Cfg::TP + p], a1buf[(j + 1) * Cfg::TP + p]);
+              float2 zd[D], a[C];
+#pragma unroll
+              for (int i = 0; i < D; ++i) zd[i] = *reinterpret_cast<const float2*>(sK1 + i * H + j);
+              jet2_from_a0<Cfg>(a0, zd, bc2(0.f), bc2(0.f), a);
+#pragma unroll
+              for (int c = 0; c < C; ++c) v[c][pr] = a[c];
+            }
+            uint4 p1[C], p2[C];
+            pack_images<C>(v, p1, p2);
+            store_images<C>(imgY + img_thr + g * 256, p1, p2);
+          }
+          umma::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar[B_IMG]);
+          w_pending = true;
+        }
+
+        // ---- layer 1 backward: a-bar_1 (accumulators) + tanh(z1) -> K1 / b1 gradients --------------------------------
+        {
+          mbar_wait(&bar[B_DFULL], ph_df);
+          ph_df ^= 1u;
+          umma::fence_after_thread_sync();
+          float d[C][16];
+#pragma unroll
+          for (int c = 0; c < C; ++c) tmem_ld16(tm_lane + Cfg::COL_D + 32u * c + 16u * h, d[c]);
+          umma::fence_before_thread_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar[B_DLOADED]);
+#pragma unroll
+          for (int gi = 0; gi < 2; ++gi) {
+            const int g = 2 * h + gi;
+            float gk[8 * (D + 1)];
+#pragma unroll
+            for (int pr = 0; pr < 4; ++pr) {
+              const int j = 8 * g + 2 * pr;
+              float2 aj[C], ab[C], zb[C], zd[D];
+              aj[0] = make_float2(a1buf[j * Cfg::TP + p], a1buf[(j + 1) * Cfg::TP + p]);
+#pragma unroll
+              for (int c = 1; c < C; ++c) aj[c] = bc2(0.f);
+#pragma unroll
+              for (int i = 0; i < D; ++i) zd[i] = *reinterpret_cast<const float2*>(sK1 + i * H + j);
+#pragma unroll
+              for (int c = 0; c < C; ++c) ab[c] = make_float2(d[c][8 * gi + 2 * pr], d[c][8 * gi + 2 * pr + 1]);
+              tanh_jet2_bwd<Cfg, true>(aj, zd, ab, zb);
+#pragma unroll
+              for (int i = 0; i < D; ++i) {
+                gk[(D + 1) * (2 * pr) + i] = fmaf(x[i], zb[0].x, zb[1 + i].x);
+                gk[(D + 1) * (2 * pr + 1) + i] = fmaf(x[i], zb[0].y, zb[1 + i].y);
+              }
+              gk[(D + 1) * (2 * pr) + D] = zb[0].x;
+              gk[(D + 1) * (2 * pr + 1) + D] = zb[0].y;
+            }
+            xreduce8<D + 1>(gk, lane);
+            if ((lane & 3) == 0) {
+              const int n16 = 8 * gi + (lane >> 2);
+#pragma unroll
+              for (int i = 0; i < D; ++i) sg[Cfg::SG_K1 + i * 16 + n16] += gk[i];
+              sg[Cfg::SG_B1 + n16] += gk[D];
+            }
+          }
+        }
+      } else {
+        (void)a3;
+      }
+    }
+    if constexpr (TRAIN) {
+      if (w_pending) drain_w(0);
+    }
+  }
+
+  // ---- CTA reduction: this CTA's workspace row (Keras order, then the term sums) ---------------------------------------
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  umma::fence_after_thread_sync();
+  float* row = ws + (size_t)blockIdx.x * ws_stride;
+  if constexpr (TRAIN) {
+    for (int idx = tid; idx < P; idx += nthr) {
+      float s = 0.f;
+      // small gradients of neuron j live in the 4 epilogue warps of half j / 16 (slot j % 16); b_out in warps 0..3
+      if (idx < D * H) {
+        const int i = idx / H, j = idx % H;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) s += sg_all[(4 * (j >> 4) + w) * Cfg::SG_FLOATS + Cfg::SG_K1 + i * 16 + (j & 15)];
+      } else if (idx < D * H + H) {
+        const int j = idx - D * H;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) s += sg_all[(4 * (j >> 4) + w) * Cfg::SG_FLOATS + Cfg::SG_B1 + (j & 15)];
+      } else if (idx < Cfg::OFF_KO) {
+        const int r = idx - Cfg::offK(2);
+        const int l = r / (H * H + H), qq = r % (H * H + H);
+        if (qq < H * H) {
+          s = tot[l * 1024 + qq];
+        } else {
+          const int j = qq - H * H;
+          const int off = l == 0 ? Cfg::SG_B2 : Cfg::SG_B3;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) s += sg_all[(4 * (j >> 4) + w) * Cfg::SG_FLOATS + off + (j & 15)];
+        }
+      } else if (idx < Cfg::OFF_BO) {
+        const int r = idx - Cfg::OFF_KO, j = r / O, o = r % O;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) s += sg_all[(4 * (j >> 4) + w) * Cfg::SG_FLOATS + Cfg::SG_KO + (j & 15) * 4 + o];
+      } else {
+#pragma unroll
+        for (int w = 0; w < 4; ++w) s += sg_all[w * Cfg::SG_FLOATS + Cfg::SG_BO + (idx - Cfg::OFF_BO)];
+      }
+      row[idx] = s;
+    }
+  }
+  for (int t = tid; t < n_terms_total; t += nthr) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) s += ssq_all[w * kMaxLaunchTerms + t];
+    row[ws_stride - n_terms_total + t] = s;
+  }
+  __syncthreads();
+  if (warp == Cfg::NEPI) umma::tmem_dealloc<512>(tmem);
+}
+
+}  // namespace ftc
+}  // namespace pinn

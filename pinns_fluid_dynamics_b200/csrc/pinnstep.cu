@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "fused_fp32.cuh"
+#include "fused_tc.cuh"
 #include "layered_fp32.cuh"
 #include "layered_tc.cuh"
 
@@ -63,6 +64,7 @@ struct pinn_plan {
   LaunchTable prepass[3];                // sets that carry a |mean| training term (forward pre-pass for its sign)
   bool has_abs_mean = false;
   int fused_tensor = 0;                  // fused engines: 1 = hidden-layer GEMMs on the tensor path (fixed at plan creation)
+  bool tcgen05 = false;                  // fused_tcgen05: the order-2 launch of the 2-32x3-3 network runs fused_tc_kernel (128-point tiles)
   float* signs = nullptr;                // [T] +-1 per term slot (only |mean| slots are read)
   float* prepass_out = nullptr;          // [P + T] scratch of the pre-pass
   float* ws = nullptr;                   // [rows_max][P + T]
@@ -125,13 +127,25 @@ static bool pick_kernel(const pinn_mlp_desc& m, int order, bool train, FusedKern
   return false;
 }
 
+// fused_tcgen05 serves the second-order launch of the 2-32x3-3 network (C = 5 channels: the tensor-memory budget of fused_tc.cuh);
+// every other launch of such a plan stays on the warp-level tensor path
+static bool tcgen05_supported(const pinn_mlp_desc& m) {
+  const char* force = getenv("PINN_ENGINE");
+  if (force && (strcmp(force, "fused_fp32") == 0 || strcmp(force, "fused_tf32x3") == 0)) return false;
+  return m.in_dim == 2 && m.width == 32 && m.n_hidden == 3 && m.out_dim == 3;
+}
+static int table_chunk_points(const pinn_plan* p, int order) { return (p->tcgen05 && order == 2) ? ftc::TcCfg<2, 3>::TP : kChunk; }
+
 static int64_t param_count(const pinn_mlp_desc& m) {
   const int64_t d = m.in_dim, H = m.width, L = m.n_hidden, O = m.out_dim;
   return d * H + H + (L - 1) * (H * H + H) + H * O + O;
 }
 
 // mode 0: every term (pinn_loss); 1: training terms; 2: only the sets with a |mean| training term (sign pre-pass)
+static int table_chunk_points(const pinn_plan* p, int order);
+
 static int build_table(pinn_plan* p, int order, int mode, LaunchTable* out) {
+  const int chunk_pts = table_chunk_points(p, order);
   const bool train_only = mode != 0;
   std::vector<SegDev> segs;
   int chunk = 0;
@@ -170,7 +184,7 @@ static int build_table(pinn_plan* p, int order, int mode, LaunchTable* out) {
     sd.n = ps.n_local;
     sd.n_terms = nt;
     sd.chunk_begin = chunk;
-    sd.n_chunks = (int)((ps.n_local + kChunk - 1) / kChunk);
+    sd.n_chunks = (int)((ps.n_local + chunk_pts - 1) / chunk_pts);
     chunk += sd.n_chunks;
     segs.push_back(sd);
   }
@@ -534,6 +548,7 @@ extern "C" int pinn_plan_create(const pinn_mlp_desc* mlp, const pinn_pointset_de
     for (int o = 0; o < top; ++o) lower += chunks[o];
     if (top > 0 && lower > 0 && lower * 16 <= chunks[top] && !(getenv("PINN_NO_PROMOTE") && atoi(getenv("PINN_NO_PROMOTE"))))
       for (pinn_pointset_desc& ps : p->sets) ps.deriv_order = top;
+    p->tcgen05 = tcgen05_supported(*mlp);
   }
   for (int s = 0; s < n_sets; ++s)
     for (int t = 0; t < sets[s].n_terms; ++t) {
@@ -597,6 +612,17 @@ extern "C" int pinn_plan_create(const pinn_mlp_desc* mlp, const pinn_pointset_de
   // H = 32: hidden-layer GEMMs on the warp-level tensor path (3xTF32), see fused_fp32.cuh
   p->fused_tensor = fused_tensor_path(*mlp) ? 1 : 0;
   if (p->fused_tensor) p->engine = "fused_tf32x3";
+  if (p->tcgen05) {
+    p->engine = "fused_tcgen05";
+    using TCfg = ftc::TcCfg<2, 3>;
+    cudaError_t e = cudaFuncSetAttribute((const void*)ftc::fused_tc_kernel<2, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCfg::SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute((const void*)ftc::fused_tc_kernel<2, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      pinn_plan_destroy(p);
+      return fail(PINN_E_CUDA, "cudaFuncSetAttribute(fused_tc_kernel, smem=%d): %s", TCfg::SMEM_BYTES, cudaGetErrorString(e));
+    }
+  }
   p->rows_max = 3 * p->num_sms;
   p->ws_bytes = (size_t)p->rows_max * (size_t)(p->P + p->T) * sizeof(float);
   if (cudaMalloc(&p->ws, p->ws_bytes) != cudaSuccess) {
@@ -708,8 +734,12 @@ static int fused_pass(pinn_plan* p, const LaunchTable* tables, const float* para
     const LaunchTable& lt = tables[o];
     if (lt.n_segs == 0) continue;
     FusedKernel k;
-    if (!pick_kernel(p->mlp, o, train, &k, p->fused_tensor)) return fail(PINN_E_INVALID, "no kernel");
-    int grid = lt.total_chunks < p->num_sms ? lt.total_chunks : p->num_sms;    // chunks are dealt to CTAs first, then to warps
+    if (p->tcgen05 && o == 2) {
+      using TCfg = ftc::TcCfg<2, 3>;
+      k = FusedKernel{train ? (fused_fn)ftc::fused_tc_kernel<2, 3, true> : (fused_fn)ftc::fused_tc_kernel<2, 3, false>, TCfg::SMEM_BYTES,
+                      TCfg::THREADS / 32};
+    } else if (!pick_kernel(p->mlp, o, train, &k, p->fused_tensor)) return fail(PINN_E_INVALID, "no kernel");
+    int grid = lt.total_chunks < p->num_sms ? lt.total_chunks : p->num_sms;    // chunks (tiles) are dealt to CTAs first, then to warps
     if (rows + grid > p->rows_max) return fail(PINN_E_STATE, "workspace rows exhausted");
     if (timed) CUDA_TRY(cudaEventRecord(p->ev0[o], st));
     k.fn<<<grid, k.nw * 32, k.smem_bytes, st>>>(params, lt.segs_dev, lt.n_segs, lt.total_chunks,

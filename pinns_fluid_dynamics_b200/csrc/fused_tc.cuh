@@ -69,6 +69,21 @@ struct TcCfg {
   static constexpr int OFF_BO = OFF_KO + H * O;
 };
 
+// Development aid (-DPINN_TC_PROFILE, tools/tc_phase_profile.py): cycles per phase and warp, summed over the tiles of CTA 0..147
+#ifdef PINN_TC_PROFILE
+__device__ unsigned long long g_tc_prof[160][9][16];
+#define TC_PROF_DECL long long prof_t = clock64();
+#define TC_PROF(k)                                                                                         \
+  do {                                                                                                     \
+    const long long now_ = clock64();                                                                      \
+    if ((threadIdx.x & 31) == 0) atomicAdd(&g_tc_prof[blockIdx.x][threadIdx.x >> 5][k], (unsigned long long)(now_ - prof_t)); \
+    prof_t = now_;                                                                                         \
+  } while (0)
+#else
+#define TC_PROF_DECL
+#define TC_PROF(k)
+#endif
+
 // barriers (uint64 slots at OFF_BAR)
 enum { B_AREADY = 0 /* ..3 */, B_DLOADED = 4, B_DFULL = 5, B_IMG = 6, B_WDONE = 7, B_STAGE = 8 };
 
@@ -286,12 +301,14 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
     constexpr uint32_t idesc_w = idesc_bf16(64, 32, 1, 1);
     uint32_t ph_a = 0, ph_dl = 0, ph_img = 0;   // bit g of ph_a: parity of a_ready[g]
     bool first_gemm = true;
+    TC_PROF_DECL
     // one forward / adjoint GEMM over the 5 channel tiles: image index 0..3 = (layer, direction)
     auto gemm = [&](int image) {
       if (!first_gemm) {                       // the epilogue has read the previous accumulators out of tensor memory
         mbar_wait(&bar[B_DLOADED], ph_dl);
         ph_dl ^= 1u;
       }
+      TC_PROF(0);
       first_gemm = false;
       const uint64_t wh = umma::smem_desc(smem_base + Cfg::OFF_W + image * 8192, 128, 1024);
       const uint64_t wl = umma::smem_desc(smem_base + Cfg::OFF_W + image * 8192 + 4096, 128, 1024);
@@ -301,6 +318,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
         mbar_wait(&bar[B_AREADY + g], (ph_a >> g) & 1u);
         ph_a ^= 1u << g;
         umma::fence_after_thread_sync();
+        TC_PROF(1 + gi);
         if (leader) {
 #pragma unroll
           for (int c = 0; c < C; ++c) {
@@ -315,12 +333,14 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
       }
       if (leader) umma::commit(&bar[B_DFULL]);
       __syncwarp();
+      TC_PROF(5);
     };
     // weight gradient of one layer: D_w[(k-octet, part, k % 8)][j] = sum_rows a[row][k] z[row][j]
     auto wgrad = [&](int a_off, int z_off) {
       mbar_wait(&bar[B_IMG], ph_img);
       ph_img ^= 1u;
       umma::fence_after_thread_sync();
+      TC_PROF(6);
       if (leader) {
         const uint64_t ad = umma::smem_desc(smem_base + a_off, 1024, 128);          // M = 64: all 8 (octet, part) blocks of a k-block
         const uint64_t z1 = umma::smem_desc(smem_base + z_off, 1024, 256);          // N = 32: the b1 blocks
@@ -333,6 +353,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
         umma::commit(&bar[B_WDONE]);
       }
       __syncwarp();
+      TC_PROF(7);
     };
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       gemm(0);                                  // layer 2 forward
@@ -354,6 +375,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
     float* ssq = ssq_all + warp * kMaxLaunchTerms;
     uint32_t ph_df = 0, ph_wd = 0;
     bool w_pending = false;                                        // a weight-gradient MMA batch not yet drained
+    TC_PROF_DECL
 
     // accumulator of the finished weight-gradient batch -> FP32 totals of layer index li (0: K_2, 1: K_3)
     auto drain_w = [&](int li) {
@@ -422,11 +444,13 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
         if (lane == 0) mbar_arrive(&bar[B_AREADY + g]);
       }
 
+      TC_PROF(0);
       // ---- layer 2: accumulators -> tanh jets -> operand of the layer-3 GEMM (+ images of a_2 for the reverse sweep) ---
       {
         mbar_wait(&bar[B_DFULL], ph_df);
         ph_df ^= 1u;
         umma::fence_after_thread_sync();
+        TC_PROF(1);
         float d[C][16];
 #pragma unroll
         for (int c = 0; c < C; ++c) tmem_ld16(tm_lane + Cfg::COL_D + 32u * c + 16u * h, d[c]);
@@ -434,10 +458,12 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar[B_DLOADED]);
         if constexpr (TRAIN) {
+          TC_PROF(2);
           if (w_pending) {                     // K-bar_2 batch of the previous tile: drain before image X is overwritten
             drain_w(0);
             w_pending = false;
           }
+          TC_PROF(3);
         }
 #pragma unroll
         for (int gi = 0; gi < 2; ++gi) {
@@ -470,6 +496,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
         }
       }
 
+      TC_PROF(2);
       // ---- layer 3 + output layer + residuals (+ z-bar_3) ----------------------------------------------------------
       float a3[C][16];                         // a-jets of layer 3 of this thread's 16 neurons
       float J[C][O];
@@ -477,6 +504,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
         mbar_wait(&bar[B_DFULL], ph_df);
         ph_df ^= 1u;
         umma::fence_after_thread_sync();
+        TC_PROF(4);
         float d[C][16];
 #pragma unroll
         for (int c = 0; c < C; ++c) tmem_ld16(tm_lane + Cfg::COL_D + 32u * c + 16u * h, d[c]);
@@ -535,6 +563,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
         for (int o = 0; o < O; ++o) y[pg * O + o] = J[0][o];
       }
 
+      TC_PROF(5);
       // ---- residuals, sums of squares, adjoint of the output jets --------------------------------------------------
       float Jb[C][O];
 #pragma unroll
@@ -591,6 +620,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
         }
       }
 
+      TC_PROF(6);
       if constexpr (TRAIN) {
         // ---- output layer backward + tanh-jet backward of layer 3: z-bar_3 -> operand of the adjoint GEMM + image Y ----
         if (h == 0) {
@@ -662,11 +692,13 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar[B_IMG]);
 
+        TC_PROF(7);
         // ---- layer 2 backward: a-bar_2 (accumulators) + a_2 (image X) -> z-bar_2 ------------------------------------
         {
           mbar_wait(&bar[B_DFULL], ph_df);
           ph_df ^= 1u;
           umma::fence_after_thread_sync();
+          TC_PROF(8);
           float d[C][16];
 #pragma unroll
           for (int c = 0; c < C; ++c) tmem_ld16(tm_lane + Cfg::COL_D + 32u * c + 16u * h, d[c]);
@@ -712,7 +744,9 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
             xreduce8<1>(gb, lane);
             if ((lane & 3) == 0) sg[Cfg::SG_B2 + 8 * gi + (lane >> 2)] += gb[0];
           }
+          TC_PROF(9);
           drain_w(1);                          // K-bar_3 batch finished: its accumulator -> totals; X and Y are free
+          TC_PROF(10);
 #pragma unroll
           for (int gi = 0; gi < 2; ++gi) {
             const int g = 2 * h + gi;
@@ -740,11 +774,13 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
           w_pending = true;
         }
 
+        TC_PROF(11);
         // ---- layer 1 backward: a-bar_1 (accumulators) + tanh(z1) -> K1 / b1 gradients --------------------------------
         {
           mbar_wait(&bar[B_DFULL], ph_df);
           ph_df ^= 1u;
           umma::fence_after_thread_sync();
+          TC_PROF(12);
           float d[C][16];
 #pragma unroll
           for (int c = 0; c < C; ++c) tmem_ld16(tm_lane + Cfg::COL_D + 32u * c + 16u * h, d[c]);
@@ -784,6 +820,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
             }
           }
         }
+        TC_PROF(13);
       } else {
         (void)a3;
       }

@@ -1003,3 +1003,14 @@ extern "C" int pinn_adam_step_dev(float* params_dev, const float* grad_dev, floa
   CUDA_TRY(cudaGetLastError());
   return PINN_OK;
 }
+
+#ifdef PINN_TC_PROFILE
+// development build only (tools/tc_phase_profile.py): read and clear the per-phase cycle counters of fused_tc_kernel
+extern "C" int pinn_tc_profile_read(unsigned long long* host_out) {
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpyFromSymbol(host_out, pinn::ftc::g_tc_prof, sizeof(pinn::ftc::g_tc_prof)));
+  static unsigned long long zero[160 * 9 * 16];
+  CUDA_TRY(cudaMemcpyToSymbol(pinn::ftc::g_tc_prof, zero, sizeof(zero)));
+  return PINN_OK;
+}
+#endif

@@ -51,7 +51,7 @@ def forward_jets(Ks, bs, x: np.ndarray, order: int):
     aj = None
     for l in range(L):
         if l > 0:
-            zj = np.einsum("cnh,hk->cnk", aj, Ks[l])
+            zj = (aj.reshape(C * N, H) @ Ks[l]).reshape(C, N, -1)
             zj[0] += bs[l]
         a = np.tanh(zj[0])
         s = 1.0 - a * a
@@ -65,7 +65,7 @@ def forward_jets(Ks, bs, x: np.ndarray, order: int):
             aj[1 + d] = q * zj[1 + sx] ** 2 + s * zj[1 + d]
             aj[2 + d] = q * zj[1 + sy] ** 2 + s * zj[2 + d]
         stash.append((a, zj, aj))
-    J = np.einsum("cnh,ho->cno", aj, Ks[L])
+    J = (aj.reshape(C * N, H) @ Ks[L]).reshape(C, N, -1)
     J[0] += bs[L]
     return J, stash
 
@@ -123,9 +123,11 @@ def backward_jets(Ks, x, order, stash, Jbar):
     gb = [np.zeros(K.shape[1]) for K in Ks]
     # output layer
     aj = stash[L - 1][2]
-    gK[L] = np.einsum("cnh,cno->ho", aj, Jbar)
+    C = aj.shape[0]
+    H = aj.shape[2]
+    gK[L] = aj.reshape(C * N, H).T @ Jbar.reshape(C * N, -1)
     gb[L] = Jbar[0].sum(axis=0)
-    ab = np.einsum("cno,ho->cnh", Jbar, Ks[L])
+    ab = (Jbar.reshape(C * N, -1) @ Ks[L].T).reshape(C, N, H)
     for l in range(L - 1, -1, -1):
         a, zj, _ = stash[l]
         s = 1.0 - a * a
@@ -148,9 +150,9 @@ def backward_jets(Ks, x, order, stash, Jbar):
             zb[0] += qp * (zj[1 + sx] ** 2 * ab[1 + d] + zj[1 + sy] ** 2 * ab[2 + d])
         if l > 0:
             aprev = stash[l - 1][2]
-            gK[l] = np.einsum("cnh,cnk->hk", aprev, zb)
+            gK[l] = aprev.reshape(C * N, H).T @ zb.reshape(C * N, H)
             gb[l] = zb[0].sum(axis=0)
-            ab = np.einsum("cnk,hk->cnh", zb, Ks[l])
+            ab = (zb.reshape(C * N, H) @ Ks[l].T).reshape(C, N, H)
         else:
             gK[0] = x.T @ zb[0]
             if order >= 1:
@@ -160,9 +162,10 @@ def backward_jets(Ks, x, order, stash, Jbar):
     return np.concatenate([np.concatenate([k.reshape(-1), b]) for k, b in zip(gK, gb)])
 
 
-def loss_and_grad(cp, theta: np.ndarray, with_grad: bool = True, include_test: bool = False) -> np.ndarray:
+def loss_and_grad(cp, theta: np.ndarray, with_grad: bool = True, include_test: bool = False, chunk: int = 32768) -> np.ndarray:
     """[P + T] float64: local gradient of sum_train w/(nu N_global) sum r^2, then local sum r^2 per
-    term in TABLE order (CompiledTerm.out_index)."""
+    term in TABLE order (CompiledTerm.out_index).  Point sets are walked in chunks of ``chunk`` points (every term
+    is a sum over points), so the BASELINE sizes (1 M / 4 M collocation points) fit host memory."""
     d, H, L, O = cp.mlp
     theta = np.asarray(theta, dtype=np.float64)
     Ks, bs = unpack(theta, d, H, L, O)
@@ -170,28 +173,40 @@ def loss_and_grad(cp, theta: np.ndarray, with_grad: bool = True, include_test: b
     for cs in cp.sets:
         if cs.n_local == 0:
             continue
-        x = cs.pointset.points[cs.start:cs.stop].astype(np.float64)
-        J, stash = forward_jets(Ks, bs, x, cs.deriv_order)
-        Jbar = np.zeros_like(J)
-        for t in cs.terms:
-            if not t.train and not include_test:
-                continue
-            rhs = t.form.rhs_array()
-            rhs = None if rhs is None else rhs[cs.start:cs.stop].astype(np.float64)
-            r = residual(t, J, d, rhs)
-            if t.abs_mean:     # ns.Loss over |mean(roots)|: slot = sum r, adjoint = sign(sum r) w / (nu N)
-                total_r = float(np.sum(r))
-                out[cp.n_params + t.out_index] += total_r
+        # |mean| terms (ns.Loss over |mean(roots)|): the adjoint needs the sign of the sum over the WHOLE set first
+        signs = {}
+        if with_grad and any(t.abs_mean and t.train for t in cs.terms):
+            sums = {id(t): 0.0 for t in cs.terms if t.abs_mean}
+            for a in range(cs.start, cs.stop, chunk):
+                b = min(cs.stop, a + chunk)
+                J, _ = forward_jets(Ks, bs, cs.pointset.points[a:b].astype(np.float64), cs.deriv_order)
+                for t in cs.terms:
+                    if t.abs_mean:
+                        rhs = t.form.rhs_array()
+                        sums[id(t)] += float(np.sum(residual(t, J, d, None if rhs is None else rhs[a:b].astype(np.float64))))
+            signs = {k: (-1.0 if v < 0 else 1.0) for k, v in sums.items()}
+        for a in range(cs.start, cs.stop, chunk):
+            b = min(cs.stop, a + chunk)
+            x = cs.pointset.points[a:b].astype(np.float64)
+            J, stash = forward_jets(Ks, bs, x, cs.deriv_order)
+            Jbar = np.zeros_like(J)
+            for t in cs.terms:
+                if not t.train and not include_test:
+                    continue
+                rhs = t.form.rhs_array()
+                rhs = None if rhs is None else rhs[a:b].astype(np.float64)
+                r = residual(t, J, d, rhs)
+                if t.abs_mean:     # slot = sum r, adjoint = sign(sum r) w / (nu N)
+                    out[cp.n_params + t.out_index] += float(np.sum(r))
+                    if t.train and with_grad:
+                        Jbar += residual_adjoint(t, J, np.full_like(r, signs[id(t)] * t.weight / (t.normalization * t.n_global)), d)
+                    continue
+                out[cp.n_params + t.out_index] += float(np.sum(r * r))
                 if t.train and with_grad:
-                    sgn = -1.0 if total_r < 0 else 1.0
-                    Jbar += residual_adjoint(t, J, np.full_like(r, sgn * t.weight / (t.normalization * t.n_global)), d)
-                continue
-            out[cp.n_params + t.out_index] += float(np.sum(r * r))
-            if t.train and with_grad:
-                scale = 2.0 * t.weight / (t.normalization * t.n_global)
-                Jbar += residual_adjoint(t, J, scale * r, d)
-        if with_grad:
-            out[:cp.n_params] += backward_jets(Ks, x, cs.deriv_order, stash, Jbar)
+                    scale = 2.0 * t.weight / (t.normalization * t.n_global)
+                    Jbar += residual_adjoint(t, J, scale * r, d)
+            if with_grad:
+                out[:cp.n_params] += backward_jets(Ks, x, cs.deriv_order, stash, Jbar)
     return out
 
 

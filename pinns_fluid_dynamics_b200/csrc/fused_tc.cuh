@@ -6,11 +6,13 @@
 // (cavity_steady.py:159-188,212-214,242).
 //
 // Work decomposition (measurements behind every choice: profiles/tc_probes_r02.md)
-//   * a CTA (one per SM, persistent) works on a TILE of 128 points at a time.  TMEM lane = point: the 8 epilogue warps
-//     (2 per lane quadrant) own one point per thread and 16 of the 32 neurons each (warp w: points 32(w&3)..+31, neurons
-//     16(w>>2)..+15), so every channel of a (point, neuron) pair -- value, d/dx, d/dy, d2/dx2, d2/dy2 -- is in one thread and
-//     the tanh-jet math needs no cross-lane traffic.  Warp 8 issues the MMAs (whole warp in the loop, one lane by elect.sync:
-//     bare back-to-back UTCHMMA, 18 cycles each).
+//   * a CTA (one per SM, persistent) works on a TILE of 128 points at a time.  TMEM lane = point: the 16 epilogue warps
+//     (4 per lane quadrant = 4 per scheduler) own one point per thread and 8 of the 32 neurons each -- two half-octets
+//     {8g + 4v .. +3}, g = 2 hs + u, for warp w = 4 (2u + v) + quadrant and hs = 0, 1 -- so every channel of a (point, neuron)
+//     pair (value, d/dx, d/dy, d2/dx2, d2/dy2) is in one thread, the tanh-jet math needs no cross-lane traffic, and the
+//     neuron octets 0, 1 (k-steps 0, 1 of the next GEMM) are complete after the first half of an epilogue phase.
+//     Warp 16 issues the MMAs (whole warp in the loop, one lane by elect.sync: bare back-to-back UTCHMMA, 18 cycles each);
+//     warps 17-19 only fill its warp group (setmaxnreg moves their registers to the epilogue warps: 112 each).
 //   * forward / input-adjoint GEMM of a hidden layer: per channel c an M = 128 (points) x N = 32 (neurons) x K = 32 tile,
 //     kind::tf32 with the 3-pass split x = hi + lo (lo*W_hi + hi*W_lo + hi*W_hi), FP32 accumulators in TENSOR MEMORY
 //     (columns 32c..), the activation operand ALSO in tensor memory (TS form: the epilogue threads write the hi / lo images of
@@ -42,8 +44,9 @@ struct TcCfg {
   static constexpr int C = 3 + D;
   static constexpr int SX = D - 2, SY = D - 1;
   static constexpr int TP = 128;                    // points per tile
-  static constexpr int NEPI = 8;                    // epilogue warps
-  static constexpr int THREADS = 32 * (NEPI + 1);   // + the MMA warp
+  static constexpr int NEPI = 16;                   // epilogue warps
+  static constexpr int THREADS = 32 * (NEPI + 4);   // + the warp group of the MMA warp
+  static constexpr int EPI_REGS = 112, AUX_REGS = 32;      // 16 x 32 x 112 + 4 x 32 x 32 = 640 x 96: setmaxnreg only redistributes the launch allocation
   static_assert(D == 2, "tensor-memory budget: 32C + 64C + 32 columns <= 512 needs C = 5");
   static constexpr uint32_t COL_D = 0, COL_A = 32 * C, COL_W = COL_A + 64 * C;
   static_assert(COL_W + 32 <= 512, "tensor memory exhausted");
@@ -55,13 +58,18 @@ struct TcCfg {
   static constexpr int OFF_TOT = OFF_W + 8 * 4096;                // weight-gradient totals [2][32][32] fp32
   static constexpr int OFF_SMALL = OFF_TOT + 2 * 32 * 32 * 4;     // K1 [D][32] | b [3][32] | K_out [32][4] | b_out [4]
   static constexpr int S_K1 = 0, S_B = D * 32, S_KO = S_B + 3 * 32, S_BO = S_KO + 32 * 4, SMALL_FLOATS = S_BO + 4;
-  static constexpr int OFF_SG = OFF_SMALL + SMALL_FLOATS * 4;     // per epilogue warp: small-gradient accumulators of its 16 neurons
-  static constexpr int SG_K1 = 0, SG_B1 = D * 16, SG_B2 = SG_B1 + 16, SG_B3 = SG_B2 + 16, SG_KO = SG_B3 + 16, SG_BO = SG_KO + 64,
+  static constexpr int OFF_SG = OFF_SMALL + SMALL_FLOATS * 4;     // per epilogue warp: small-gradient accumulators of its 8 neurons
+  static constexpr int SG_K1 = 0, SG_B1 = D * 8, SG_B2 = SG_B1 + 8, SG_B3 = SG_B2 + 8, SG_KO = SG_B3 + 8, SG_BO = SG_KO + 32,
                        SG_FLOATS = SG_BO + 4;
-  static constexpr int OFF_SSQ = OFF_SG + NEPI * SG_FLOATS * 4;   // per epilogue warp: sum r^2 per term slot
-  static constexpr int OFF_BAR = OFF_SSQ + NEPI * kMaxLaunchTerms * 4;
+  static constexpr int OFF_SSQ = OFF_SG + NEPI * SG_FLOATS * 4;   // warps 0..3: sum r^2 per term slot
+  static constexpr int OFF_TERM = OFF_SSQ + 4 * kMaxLaunchTerms * 4;   // the launch's terms, TERM_WORDS words each
+  static constexpr int TERM_WORDS = 24;
+  static constexpr int T_CONV = 15, T_RHS_SCALE = 16, T_SCALE = 17, T_FLAGS = 18, T_OUT = 19, T_RHS = 20, T_SIGN = 22;
+  static constexpr int OFF_SEGT = OFF_TERM + kMaxLaunchTerms * TERM_WORDS * 4;   // first staged term of each segment
+  static constexpr int OFF_BAR = OFF_SEGT + kMaxLaunchTerms * 4;
   static constexpr int SMEM_BYTES = OFF_BAR + 16 * 8;
   static_assert(SMEM_BYTES <= 232448, "shared memory exhausted");
+  static_assert(O * C <= 15, "staged term layout");
   static constexpr int P = D * H + H + (L - 1) * (H * H + H) + H * O + O;
   static_assert(P * 4 <= IMG_BYTES, "parameter staging area");
   __host__ __device__ static constexpr int offK(int l) { return D * H + H + (l - 2) * (H * H + H); }   // l = 2..L
@@ -69,9 +77,9 @@ struct TcCfg {
   static constexpr int OFF_BO = OFF_KO + H * O;
 };
 
-// Development aid (-DPINN_TC_PROFILE, tools/tc_phase_profile.py): cycles per phase and warp, summed over the tiles of CTA 0..147
+// Development aid (-DPINN_TC_PROFILE, tools/tc_phase_profile.py): cycles per phase and warp, summed over the tiles of a CTA
 #ifdef PINN_TC_PROFILE
-__device__ unsigned long long g_tc_prof[160][9][16];
+__device__ unsigned long long g_tc_prof[160][20][16];
 #define TC_PROF_DECL long long prof_t = clock64();
 #define TC_PROF(k)                                                                                         \
   do {                                                                                                     \
@@ -97,6 +105,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
 }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+template <int REGS> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
+template <int REGS> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
 __host__ __device__ constexpr uint32_t idesc_bf16(int m, int n, int a_mn, int b_mn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) |
          ((uint32_t)(m >> 4) << 24);
@@ -111,13 +121,29 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t d, uint64_t a, uint64_t b, 
                "l"(a), "l"(b), "r"(idesc), "r"(acc)
                : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {   // thread i of the warp: lane (quadrant base + i), 16 columns
+// thread i of the warp: tensor-memory lane (quadrant base + i)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
       "tcgen05.wait::ld.sync.aligned;"
       : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]),
         "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
       : "r"(taddr)
+      : "memory");
+}
+// 4 columns of each of the 5 accumulator tiles (stride 32 columns) in one go, one wait
+__device__ __forceinline__ void tmem_ld4x5(uint32_t taddr, float (&v)[5][4]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%20];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%4, %5, %6, %7}, [%21];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%8, %9, %10, %11}, [%22];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%12, %13, %14, %15}, [%23];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%16, %17, %18, %19}, [%24];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=f"(v[0][0]), "=f"(v[0][1]), "=f"(v[0][2]), "=f"(v[0][3]), "=f"(v[1][0]), "=f"(v[1][1]), "=f"(v[1][2]), "=f"(v[1][3]),
+        "=f"(v[2][0]), "=f"(v[2][1]), "=f"(v[2][2]), "=f"(v[2][3]), "=f"(v[3][0]), "=f"(v[3][1]), "=f"(v[3][2]), "=f"(v[3][3]),
+        "=f"(v[4][0]), "=f"(v[4][1]), "=f"(v[4][2]), "=f"(v[4][3])
+      : "r"(taddr), "r"(taddr + 32u), "r"(taddr + 64u), "r"(taddr + 96u), "r"(taddr + 128u)
       : "memory");
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
@@ -127,30 +153,43 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
       "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
       : "memory");
 }
-__device__ __forceinline__ void tmem_st8u(uint32_t taddr, const uint32_t (&v)[8]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
-               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
-               : "memory");
+__device__ __forceinline__ void tmem_st4u(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// x = hi + lo, hi rounded to tf32; the tensor core truncates the 13 low bits of lo: half an ulp added first makes that a rounding
-__device__ __forceinline__ void split_hi_lo(float x, uint32_t& hi, uint32_t& lo) {
-  hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
-  lo = __float_as_uint(x - __uint_as_float(hi)) + 0x1000u;
+// x = hi + lo for two values at once.  ROUND: hi rounded to tf32, half an ulp added to lo before the tensor core truncates its
+// 13 low bits (forward operands: they set the loss values).  !ROUND: the raw value serves as hi (the hardware reads its top
+// 19 bits), lo = x - trunc(x) (adjoint operands: gradients only, tolerance 1e-4; 1.5 instead of 3.5 instructions per value)
+template <bool ROUND>
+__device__ __forceinline__ void split2(float2 x, uint32_t& h0, uint32_t& h1, uint32_t& l0, uint32_t& l1) {
+  if constexpr (ROUND) {
+    h0 = (__float_as_uint(x.x) + 0x1000u) & 0xFFFFE000u;
+    h1 = (__float_as_uint(x.y) + 0x1000u) & 0xFFFFE000u;
+    const float2 lo = fma2(make_float2(__uint_as_float(h0), __uint_as_float(h1)), bc2(-1.0f), x);
+    l0 = __float_as_uint(lo.x) + 0x1000u;
+    l1 = __float_as_uint(lo.y) + 0x1000u;
+  } else {
+    h0 = __float_as_uint(x.x);
+    h1 = __float_as_uint(x.y);
+    const float2 lo = fma2(make_float2(__uint_as_float(h0 & 0xFFFFE000u), __uint_as_float(h1 & 0xFFFFE000u)), bc2(-1.0f), x);
+    l0 = __float_as_uint(lo.x);
+    l1 = __float_as_uint(lo.y);
+  }
 }
 // two neighbouring neurons as bf16 pairs: p1 = (bf16(x0) | bf16(x1) << 16), p2 the same of the remainders
-__device__ __forceinline__ void bf16_pair(float x0, float x1, uint32_t& p1, uint32_t& p2) {
-  p1 = pack_bf16(x0, x1);
-  p2 = pack_bf16(x0 - __uint_as_float(p1 << 16), x1 - __uint_as_float(p1 & 0xFFFF0000u));
+__device__ __forceinline__ void bf16_pair(float2 x, uint32_t& p1, uint32_t& p2) {
+  p1 = pack_bf16(x.x, x.y);
+  const float2 r = fma2(make_float2(__uint_as_float(p1 << 16), __uint_as_float(p1 & 0xFFFF0000u)), bc2(-1.0f), x);
+  p2 = pack_bf16(r.x, r.y);
 }
 __device__ __forceinline__ float2 bf16_unpair(uint32_t p1, uint32_t p2) {
-  return make_float2(__uint_as_float(p1 << 16) + __uint_as_float(p2 << 16),
-                     __uint_as_float(p1 & 0xFFFF0000u) + __uint_as_float(p2 & 0xFFFF0000u));
+  return add2(make_float2(__uint_as_float(p1 << 16), __uint_as_float(p1 & 0xFFFF0000u)),
+              make_float2(__uint_as_float(p2 << 16), __uint_as_float(p2 & 0xFFFF0000u)));
 }
 
 // sums of V per-lane values over the 32 lanes of a warp by halving exchanges: V = 8 m values v[m * n8 + t] (n8 = 0..7) end
-// up in the lanes with (lane & 3) == 0 as v[t], t < m, of n8 = lane >> 2   (V + ~2 shuffles instead of 5 V)
+// up in the lanes with (lane & 3) == 0 as v[t], t < m, of n8 = lane >> 2   (~V shuffles instead of 5 V)
 template <int V, int S>
 __device__ __forceinline__ void xr_step(float* v, int lane) {
   const bool up = (lane & S) != 0;
@@ -173,38 +212,33 @@ __device__ __forceinline__ void xreduce8(float (&v)[8 * M], int lane) {
   }
 }
 
-// hi / lo images of 8 neurons x C channels of this thread's row into tensor memory (operand of the next GEMM)
-template <int C>
-__device__ __forceinline__ void emit_operand(const float2 (&v)[C][4], uint32_t tm_a) {
+// hi / lo images of a half-octet (4 neurons = 2 pairs) x C channels of this thread's row into tensor memory
+template <int C, bool ROUND>
+__device__ __forceinline__ void emit_operand(const float2 (&v)[C][2], uint32_t tm_a) {
 #pragma unroll
   for (int c = 0; c < C; ++c) {
-    uint32_t hi[8], lo[8];
-#pragma unroll
-    for (int pr = 0; pr < 4; ++pr) {
-      split_hi_lo(v[c][pr].x, hi[2 * pr], lo[2 * pr]);
-      split_hi_lo(v[c][pr].y, hi[2 * pr + 1], lo[2 * pr + 1]);
-    }
-    tmem_st8u(tm_a + 64u * c, hi);
-    tmem_st8u(tm_a + 64u * c + 32u, lo);
+    uint32_t h[4], l[4];
+    split2<ROUND>(v[c][0], h[0], h[1], l[0], l[1]);
+    split2<ROUND>(v[c][1], h[2], h[3], l[2], l[3]);
+    tmem_st4u(tm_a + 64u * c, h[0], h[1], h[2], h[3]);
+    tmem_st4u(tm_a + 64u * c + 32u, l[0], l[1], l[2], l[3]);
   }
 }
-// bf16-pair images of the same values: rows (c, p), 8 neurons = 16 bytes per part
+// bf16-pair images of the same values: rows (c, p), 4 neurons = 8 bytes per part
 template <int C>
-__device__ __forceinline__ void pack_images(const float2 (&v)[C][4], uint4 (&p1)[C], uint4 (&p2)[C]) {
+__device__ __forceinline__ void pack_images(const float2 (&v)[C][2], uint2 (&p1)[C], uint2 (&p2)[C]) {
 #pragma unroll
   for (int c = 0; c < C; ++c) {
-    bf16_pair(v[c][0].x, v[c][0].y, p1[c].x, p2[c].x);
-    bf16_pair(v[c][1].x, v[c][1].y, p1[c].y, p2[c].y);
-    bf16_pair(v[c][2].x, v[c][2].y, p1[c].z, p2[c].z);
-    bf16_pair(v[c][3].x, v[c][3].y, p1[c].w, p2[c].w);
+    bf16_pair(v[c][0], p1[c].x, p2[c].x);
+    bf16_pair(v[c][1], p1[c].y, p2[c].y);
   }
 }
 template <int C>
-__device__ __forceinline__ void store_images(uint8_t* img_thr_g, const uint4 (&p1)[C], const uint4 (&p2)[C]) {
+__device__ __forceinline__ void store_images(uint8_t* img_thr_g, const uint2 (&p1)[C], const uint2 (&p2)[C]) {
 #pragma unroll
   for (int c = 0; c < C; ++c) {
-    *reinterpret_cast<uint4*>(img_thr_g + c * 16384) = p1[c];
-    *reinterpret_cast<uint4*>(img_thr_g + c * 16384 + 128) = p2[c];
+    *reinterpret_cast<uint2*>(img_thr_g + c * 16384) = p1[c];
+    *reinterpret_cast<uint2*>(img_thr_g + c * 16384 + 128) = p2[c];
   }
 }
 
@@ -213,7 +247,7 @@ __global__ void __launch_bounds__(TcCfg<D, O>::THREADS, 1)
 fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ segs, int n_segs, int total_tiles,
                 float* __restrict__ ws, int ws_stride, int n_terms_total, int params_aligned) {
   using Cfg = TcCfg<D, O>;
-  constexpr int C = Cfg::C, H = 32, P = Cfg::P, SX = Cfg::SX, SY = Cfg::SY;
+  constexpr int C = Cfg::C, H = 32, P = Cfg::P, SX = Cfg::SX, SY = Cfg::SY, TW = Cfg::TERM_WORDS;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* imgX = smem + Cfg::OFF_X;
   uint8_t* imgY = smem + Cfg::OFF_Y;
@@ -227,21 +261,21 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
   float* sBo = small + Cfg::S_BO;
   float* sg_all = reinterpret_cast<float*>(smem + Cfg::OFF_SG);
   float* ssq_all = reinterpret_cast<float*>(smem + Cfg::OFF_SSQ);
+  float* sterm = reinterpret_cast<float*>(smem + Cfg::OFF_TERM);
+  int* segt = reinterpret_cast<int*>(smem + Cfg::OFF_SEGT);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 12);
 
   const int tid = threadIdx.x, nthr = Cfg::THREADS;
   const int lane = tid & 31, warp = tid >> 5;
 
-  // ---- stage the parameter vector (one TMA bulk copy + tail), build the operand images ------------------------------
+  // ---- stage the parameter vector (one TMA bulk copy + tail), build the operand images, stage the terms ---------------
   {
     float* raw = reinterpret_cast<float*>(imgX);
     const uint32_t bulk_bytes = params_aligned ? ((uint32_t)(P * 4) & ~15u) : 0u;
     if (tid == 0) {
-      mbar_init(&bar[B_AREADY + 0], 4);
-      mbar_init(&bar[B_AREADY + 1], 4);
-      mbar_init(&bar[B_AREADY + 2], 4);
-      mbar_init(&bar[B_AREADY + 3], 4);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) mbar_init(&bar[B_AREADY + g], 8);        // the 8 warps that produce neuron octet g
       mbar_init(&bar[B_DLOADED], Cfg::NEPI);
       mbar_init(&bar[B_DFULL], 1);
       mbar_init(&bar[B_IMG], Cfg::NEPI);
@@ -255,6 +289,36 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
       tma_bulk_g2s(raw, params, bulk_bytes, &bar[B_STAGE]);
     }
     for (int i = (int)(bulk_bytes / 4) + tid; i < P; i += nthr) raw[i] = __ldg(params + i);
+    // the launch's loss terms in a compact form (coefficients of the O x C output jets first): read once per tile and
+    // thread from shared memory instead of through 15 dependent global loads per term
+    if (tid == 0) {
+      int t0 = 0;
+      for (int si = 0; si < n_segs; ++si) {
+        segt[si] = t0;
+        t0 += segs[si].n_terms;
+      }
+    }
+    for (int si = 0; si < n_segs; ++si) {
+      int t0 = 0;
+      for (int sj = 0; sj < si; ++sj) t0 += __ldg(&segs[sj].n_terms);
+      const int nt = __ldg(&segs[si].n_terms);
+      for (int idx = tid; idx < nt * TW; idx += nthr) {
+        const int t = idx / TW, k = idx % TW;
+        const TermDev* T = segs[si].terms + t;
+        float val = 0.f;
+        if (k < O * C) val = T->coef[k / C][k % C];
+        else if (k == Cfg::T_CONV) val = T->conv;
+        else if (k == Cfg::T_RHS_SCALE) val = T->rhs_scale;
+        else if (k == Cfg::T_SCALE) val = T->scale;
+        else if (k == Cfg::T_FLAGS) val = __int_as_float((T->conv_k & 0xff) | ((T->kind & 0xff) << 8) | ((T->train & 0xff) << 16));
+        else if (k == Cfg::T_OUT) val = __int_as_float(T->out_index);
+        else if (k == Cfg::T_RHS) val = __uint_as_float((uint32_t)(reinterpret_cast<uintptr_t>(T->rhs) & 0xffffffffu));
+        else if (k == Cfg::T_RHS + 1) val = __uint_as_float((uint32_t)(reinterpret_cast<uintptr_t>(T->rhs) >> 32));
+        else if (k == Cfg::T_SIGN) val = __uint_as_float((uint32_t)(reinterpret_cast<uintptr_t>(T->sign) & 0xffffffffu));
+        else if (k == Cfg::T_SIGN + 1) val = __uint_as_float((uint32_t)(reinterpret_cast<uintptr_t>(T->sign) >> 32));
+        sterm[(t0 + t) * TW + k] = val;
+      }
+    }
     if (bulk_bytes) mbar_wait(&bar[B_STAGE], 0);
     __syncthreads();
     // K-major operand images of the 32 x 32 matrices (rows n, contraction index k: umma::tile_offset, SBO = 1024):
@@ -263,8 +327,8 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
     for (int idx = tid; idx < 2 * H * H; idx += nthr) {
       const int l = idx / (H * H), r = (idx / H) % H, c = idx % H;   // r = row of K_l (k), c = column (j)
       const float w = raw[Cfg::offK(l + 2) + r * H + c];
-      uint32_t hi, lo;
-      split_hi_lo(w, hi, lo);
+      const uint32_t hi = (__float_as_uint(w) + 0x1000u) & 0xFFFFE000u;
+      const uint32_t lo = __float_as_uint(w - __uint_as_float(hi)) + 0x1000u;
       const uint32_t of = umma::tile_offset(c, r, 1024) / 4, ob = umma::tile_offset(r, c, 1024) / 4;
       float* base = wimg + l * 4096;   // 4 images of 1024 floats per layer
       base[of] = __uint_as_float(hi);
@@ -284,7 +348,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
     if (tid < 4) sBo[tid] = (tid < O) ? raw[Cfg::OFF_BO + tid] : 0.f;
     for (int idx = tid; idx < 2 * H * H; idx += nthr) tot[idx] = 0.f;
     for (int idx = tid; idx < Cfg::NEPI * Cfg::SG_FLOATS; idx += nthr) sg_all[idx] = 0.f;
-    for (int idx = tid; idx < Cfg::NEPI * kMaxLaunchTerms; idx += nthr) ssq_all[idx] = 0.f;
+    for (int idx = tid; idx < 4 * kMaxLaunchTerms; idx += nthr) ssq_all[idx] = 0.f;
     if (warp == Cfg::NEPI) umma::tmem_alloc<512>(tslot);
     umma::fence_proxy_async_smem();
     umma::fence_before_thread_sync();
@@ -294,87 +358,94 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
   const uint32_t tmem = *tslot;
   const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
 
-  if (warp == Cfg::NEPI) {
-    // ================================ MMA warp =====================================================================
-    const bool leader = elect_one();
-    constexpr uint32_t idesc_g = umma::idesc_tf32(128, 32);
-    constexpr uint32_t idesc_w = idesc_bf16(64, 32, 1, 1);
-    uint32_t ph_a = 0, ph_dl = 0, ph_img = 0;   // bit g of ph_a: parity of a_ready[g]
-    bool first_gemm = true;
-    TC_PROF_DECL
-    // one forward / adjoint GEMM over the 5 channel tiles: image index 0..3 = (layer, direction)
-    auto gemm = [&](int image) {
-      if (!first_gemm) {                       // the epilogue has read the previous accumulators out of tensor memory
-        mbar_wait(&bar[B_DLOADED], ph_dl);
-        ph_dl ^= 1u;
-      }
-      TC_PROF(0);
-      first_gemm = false;
-      const uint64_t wh = umma::smem_desc(smem_base + Cfg::OFF_W + image * 8192, 128, 1024);
-      const uint64_t wl = umma::smem_desc(smem_base + Cfg::OFF_W + image * 8192 + 4096, 128, 1024);
+  if (warp >= Cfg::NEPI) {
+    reg_dec<Cfg::AUX_REGS>();
+    if (warp == Cfg::NEPI) {
+      // ================================ MMA warp ===================================================================
+      const bool leader = elect_one();
+      constexpr uint32_t idesc_g = umma::idesc_tf32(128, 32);
+      constexpr uint32_t idesc_w = idesc_bf16(64, 32, 1, 1);
+      uint32_t ph_a = 0, ph_dl = 0, ph_img = 0;   // bit g of ph_a: parity of a_ready[g]
+      bool first_gemm = true;
+      TC_PROF_DECL
+      // one forward / adjoint GEMM over the 5 channel tiles: image index 0..3 = (layer, direction)
+      auto gemm = [&](int image) {
+        const uint64_t wh = umma::smem_desc(smem_base + Cfg::OFF_W + image * 8192, 128, 1024);
+        const uint64_t wl = umma::smem_desc(smem_base + Cfg::OFF_W + image * 8192 + 4096, 128, 1024);
 #pragma unroll
-      for (int gi = 0; gi < 4; ++gi) {
-        const int g = (gi & 1) * 2 + (gi >> 1);          // readiness order of the k-steps: 0, 2, 1, 3
-        mbar_wait(&bar[B_AREADY + g], (ph_a >> g) & 1u);
-        ph_a ^= 1u << g;
-        umma::fence_after_thread_sync();
-        TC_PROF(1 + gi);
-        if (leader) {
-#pragma unroll
-          for (int c = 0; c < C; ++c) {
-            const uint32_t d = tmem + Cfg::COL_D + 32u * c;
-            const uint32_t ah = tmem + Cfg::COL_A + 64u * c + 8u * g, al = ah + 32u;
-            mma_tf32_ts(d, al, wh + (uint64_t)(g * 16), idesc_g, gi > 0 ? 1u : 0u);
-            mma_tf32_ts(d, ah, wl + (uint64_t)(g * 16), idesc_g, 1u);
-            mma_tf32_ts(d, ah, wh + (uint64_t)(g * 16), idesc_g, 1u);
+        for (int g = 0; g < 4; ++g) {            // k-step g contracts over neuron octet g; octets 0, 1 are ready first
+          mbar_wait(&bar[B_AREADY + g], (ph_a >> g) & 1u);
+          ph_a ^= 1u << g;
+          if (g == 0) {
+            if (!first_gemm) {                   // every epilogue warp has read the previous accumulators out of tensor memory
+              mbar_wait(&bar[B_DLOADED], ph_dl);
+              ph_dl ^= 1u;
+            }
+            first_gemm = false;
           }
+          umma::fence_after_thread_sync();
+          TC_PROF(1 + g);
+          if (leader) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              const uint32_t d = tmem + Cfg::COL_D + 32u * c;
+              const uint32_t ah = tmem + Cfg::COL_A + 64u * c + 8u * g, al = ah + 32u;
+              mma_tf32_ts(d, al, wh + (uint64_t)(g * 16), idesc_g, g > 0 ? 1u : 0u);
+              mma_tf32_ts(d, ah, wl + (uint64_t)(g * 16), idesc_g, 1u);
+              mma_tf32_ts(d, ah, wh + (uint64_t)(g * 16), idesc_g, 1u);
+            }
+          }
+          __syncwarp();
+        }
+        if (leader) umma::commit(&bar[B_DFULL]);
+        __syncwarp();
+        TC_PROF(5);
+      };
+      // weight gradient of one layer: D_w[(k-octet, part, k % 8)][j] = sum_rows a[row][k] z[row][j]
+      auto wgrad = [&](int a_off, int z_off) {
+        mbar_wait(&bar[B_IMG], ph_img);
+        ph_img ^= 1u;
+        umma::fence_after_thread_sync();
+        TC_PROF(6);
+        if (leader) {
+          const uint64_t ad = umma::smem_desc(smem_base + a_off, 1024, 128);          // M = 64: all 8 (octet, part) blocks of a k-block
+          const uint64_t z1 = umma::smem_desc(smem_base + z_off, 1024, 256);          // N = 32: the b1 blocks
+          const uint64_t z2 = umma::smem_desc(smem_base + z_off + 128, 1024, 256);    //         the b2 blocks
+#pragma unroll 4
+          for (int ks = 0; ks < C * Cfg::TP / 16; ++ks) {
+            mma_bf16_ss(tmem + Cfg::COL_W, ad + (uint64_t)(ks * 128), z1 + (uint64_t)(ks * 128), idesc_w, ks > 0 ? 1u : 0u);
+            mma_bf16_ss(tmem + Cfg::COL_W, ad + (uint64_t)(ks * 128), z2 + (uint64_t)(ks * 128), idesc_w, 1u);
+          }
+          umma::commit(&bar[B_WDONE]);
         }
         __syncwarp();
-      }
-      if (leader) umma::commit(&bar[B_DFULL]);
-      __syncwarp();
-      TC_PROF(5);
-    };
-    // weight gradient of one layer: D_w[(k-octet, part, k % 8)][j] = sum_rows a[row][k] z[row][j]
-    auto wgrad = [&](int a_off, int z_off) {
-      mbar_wait(&bar[B_IMG], ph_img);
-      ph_img ^= 1u;
-      umma::fence_after_thread_sync();
-      TC_PROF(6);
-      if (leader) {
-        const uint64_t ad = umma::smem_desc(smem_base + a_off, 1024, 128);          // M = 64: all 8 (octet, part) blocks of a k-block
-        const uint64_t z1 = umma::smem_desc(smem_base + z_off, 1024, 256);          // N = 32: the b1 blocks
-        const uint64_t z2 = umma::smem_desc(smem_base + z_off + 128, 1024, 256);    //         the b2 blocks
-#pragma unroll 4
-        for (int ks = 0; ks < C * Cfg::TP / 16; ++ks) {
-          mma_bf16_ss(tmem + Cfg::COL_W, ad + (uint64_t)(ks * 128), z1 + (uint64_t)(ks * 128), idesc_w, ks > 0 ? 1u : 0u);
-          mma_bf16_ss(tmem + Cfg::COL_W, ad + (uint64_t)(ks * 128), z2 + (uint64_t)(ks * 128), idesc_w, 1u);
+        TC_PROF(7);
+      };
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        gemm(0);                                  // layer 2 forward
+        gemm(2);                                  // layer 3 forward
+        if constexpr (TRAIN) {
+          gemm(3);                                // layer 3 adjoint: a-bar_2 = z-bar_3 K_3^T
+          wgrad(Cfg::OFF_X, Cfg::OFF_Y);          // K-bar_3 = a_2^T z-bar_3
+          gemm(1);                                // layer 2 adjoint
+          wgrad(Cfg::OFF_Y, Cfg::OFF_X);          // K-bar_2 = a_1^T z-bar_2
         }
-        umma::commit(&bar[B_WDONE]);
-      }
-      __syncwarp();
-      TC_PROF(7);
-    };
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      gemm(0);                                  // layer 2 forward
-      gemm(2);                                  // layer 3 forward
-      if constexpr (TRAIN) {
-        gemm(3);                                // layer 3 adjoint: a-bar_2 = z-bar_3 K_3^T
-        wgrad(Cfg::OFF_X, Cfg::OFF_Y);          // K-bar_3 = a_2^T z-bar_3
-        gemm(1);                                // layer 2 adjoint
-        wgrad(Cfg::OFF_Y, Cfg::OFF_X);          // K-bar_2 = a_1^T z-bar_2
       }
     }
   } else {
+    reg_inc<Cfg::EPI_REGS>();
     // ================================ epilogue warps ================================================================
-    const int q = warp & 3, h = warp >> 2;
+    const int q = warp & 3, h = warp >> 2, u = h >> 1, v4 = h & 1;
     const int p = 32 * q + lane;                                   // point of the tile = tensor-memory lane
     const uint32_t tm_lane = tmem + ((uint32_t)(32 * q) << 16);
-    const int img_thr = (p >> 3) * 1024 + (p & 7) * 16;            // byte offset of row (c = 0, p) in an image, neuron octet 0, part b1
+    const int img_thr = (p >> 3) * 1024 + (p & 7) * 16 + v4 * 8;   // byte offset of (row (c = 0, p), neuron octet 0, part b1, this half-octet)
     float* sg = sg_all + warp * Cfg::SG_FLOATS;
-    float* ssq = ssq_all + warp * kMaxLaunchTerms;
+    float* ssq = ssq_all + (warp & 3) * kMaxLaunchTerms;
     uint32_t ph_df = 0, ph_wd = 0;
     bool w_pending = false;                                        // a weight-gradient MMA batch not yet drained
+    float gb2acc[8], gb3acc[8];                                    // bias gradients of layers 2, 3: this thread's point share, all tiles
+#pragma unroll
+    for (int i = 0; i < 8; ++i) gb2acc[i] = gb3acc[i] = 0.f;
     TC_PROF_DECL
 
     // accumulator of the finished weight-gradient batch -> FP32 totals of layer index li (0: K_2, 1: K_3)
@@ -383,50 +454,76 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
       ph_wd ^= 1u;
       umma::fence_after_thread_sync();
       if (h == 0) {
-        float v[32];
-        tmem_ld32(tm_lane + Cfg::COL_W, v);
+        float wv[32];
+        tmem_ld32(tm_lane + Cfg::COL_W, wv);
         // quadrant q holds rows 16q..16q+15 of the M = 64 accumulator: lanes 0-7 the b1 part of neurons 8q..8q+7, lanes 8-15 the b2 part
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += __shfl_down_sync(0xffffffffu, v[j], 8);
+        for (int j = 0; j < 32; ++j) wv[j] += __shfl_down_sync(0xffffffffu, wv[j], 8);
         if (lane < 8) {
           float4* t4 = reinterpret_cast<float4*>(tot + li * 1024 + (8 * q + lane) * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float4 t = t4[j];
-            t.x += v[4 * j]; t.y += v[4 * j + 1]; t.z += v[4 * j + 2]; t.w += v[4 * j + 3];
+            t.x += wv[4 * j]; t.y += wv[4 * j + 1]; t.z += wv[4 * j + 2]; t.w += wv[4 * j + 3];
             t4[j] = t;
           }
         }
         umma::fence_before_thread_sync();
       }
     };
+    auto arrive_group = [&](int g) {           // this warp's share of neuron octet g is in tensor memory
+      tmem_wait_st();
+      umma::fence_before_thread_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar[B_AREADY + g]);
+    };
+    auto arrive_dloaded = [&]() {
+      umma::fence_before_thread_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar[B_DLOADED]);
+    };
 
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      int si = 0;
+    // tile state, prepared one tile ahead (the point coordinates are a global load)
+    int si = 0;
+    long long pg = 0, pi = 0, n = 0;
+    bool valid = false;
+    float x[D];
+    const SegDev* __restrict__ seg = segs;
+    auto prepare = [&](int tile) {
       while (si + 1 < n_segs && tile >= __ldg(&segs[si + 1].chunk_begin)) ++si;
-      const SegDev* __restrict__ seg = segs + si;
-      const long long n = seg->n;
-      const long long pg = (long long)(tile - seg->chunk_begin) * Cfg::TP + p;
-      const bool valid = pg < n;
-      const long long pi = valid ? pg : n - 1;
-      float x[D];
+      seg = segs + si;
+      n = seg->n;
+      pg = (long long)(tile - seg->chunk_begin) * Cfg::TP + p;
+      valid = pg < n;
+      pi = valid ? pg : n - 1;
 #pragma unroll
       for (int i = 0; i < D; ++i) x[i] = __ldg(seg->pts + pi * D + i);
+    };
+    if ((int)blockIdx.x < total_tiles) prepare(blockIdx.x);
+
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const SegDev* __restrict__ seg_c = seg;
+      const long long pg_c = pg, pi_c = pi;
+      const bool valid_c = valid;
+      const int term0 = segt[si];
+      float xc[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) xc[i] = x[i];
 
       // ---- layer 1: z = x K1 + b1, a = tanh z; jets straight into the operand of the layer-2 GEMM ------------------
 #pragma unroll
-      for (int gi = 0; gi < 2; ++gi) {
-        const int g = 2 * h + gi;
-        float2 v[C][4];
+      for (int hs = 0; hs < 2; ++hs) {
+        const int g = 2 * hs + u, j0 = 8 * g + 4 * v4;
+        float2 v[C][2];
 #pragma unroll
-        for (int pr = 0; pr < 4; ++pr) {
-          const int j = 8 * g + 2 * pr;
+        for (int pr = 0; pr < 2; ++pr) {
+          const int j = j0 + 2 * pr;
           float2 z = *reinterpret_cast<const float2*>(sB + j);
           float2 zd[D], a[C];
 #pragma unroll
           for (int i = 0; i < D; ++i) {
             zd[i] = *reinterpret_cast<const float2*>(sK1 + i * H + j);
-            z = fma2(bc2(x[i]), zd[i], z);
+            z = fma2(bc2(xc[i]), zd[i], z);
           }
           const float2 a0 = tanh2(z);
           if constexpr (TRAIN) {
@@ -437,28 +534,18 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
 #pragma unroll
           for (int c = 0; c < C; ++c) v[c][pr] = a[c];
         }
-        emit_operand<C>(v, tm_lane + Cfg::COL_A + 8u * g);
-        tmem_wait_st();
-        umma::fence_before_thread_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar[B_AREADY + g]);
+        emit_operand<C, true>(v, tm_lane + Cfg::COL_A + 8u * g + 4u * v4);
+        arrive_group(g);
       }
-
       TC_PROF(0);
+
       // ---- layer 2: accumulators -> tanh jets -> operand of the layer-3 GEMM (+ images of a_2 for the reverse sweep) ---
       {
         mbar_wait(&bar[B_DFULL], ph_df);
         ph_df ^= 1u;
         umma::fence_after_thread_sync();
         TC_PROF(1);
-        float d[C][16];
-#pragma unroll
-        for (int c = 0; c < C; ++c) tmem_ld16(tm_lane + Cfg::COL_D + 32u * c + 16u * h, d[c]);
-        umma::fence_before_thread_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar[B_DLOADED]);
         if constexpr (TRAIN) {
-          TC_PROF(2);
           if (w_pending) {                     // K-bar_2 batch of the previous tile: drain before image X is overwritten
             drain_w(0);
             w_pending = false;
@@ -466,145 +553,160 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
           TC_PROF(3);
         }
 #pragma unroll
-        for (int gi = 0; gi < 2; ++gi) {
-          const int g = 2 * h + gi;
-          float2 v[C][4];
+        for (int hs = 0; hs < 2; ++hs) {
+          const int g = 2 * hs + u, j0 = 8 * g + 4 * v4;
+          float d[C][4];
+          tmem_ld4x5(tm_lane + Cfg::COL_D + 8u * g + 4u * v4, d);
+          if (hs == 1) arrive_dloaded();
+          float2 v[C][2];
 #pragma unroll
-          for (int pr = 0; pr < 4; ++pr) {
-            const int j = 8 * g + 2 * pr;
+          for (int pr = 0; pr < 2; ++pr) {
+            const int j = j0 + 2 * pr;
             const float2 b = *reinterpret_cast<const float2*>(sB + H + j);
             float2 zd[D], a[C];
 #pragma unroll
-            for (int i = 0; i < D; ++i) zd[i] = make_float2(d[1 + i][8 * gi + 2 * pr], d[1 + i][8 * gi + 2 * pr + 1]);
-            const float2 zxx = make_float2(d[1 + D][8 * gi + 2 * pr], d[1 + D][8 * gi + 2 * pr + 1]);
-            const float2 zyy = make_float2(d[2 + D][8 * gi + 2 * pr], d[2 + D][8 * gi + 2 * pr + 1]);
-            const float2 z0 = add2(make_float2(d[0][8 * gi + 2 * pr], d[0][8 * gi + 2 * pr + 1]), b);
+            for (int i = 0; i < D; ++i) zd[i] = make_float2(d[1 + i][2 * pr], d[1 + i][2 * pr + 1]);
+            const float2 zxx = make_float2(d[1 + D][2 * pr], d[1 + D][2 * pr + 1]);
+            const float2 zyy = make_float2(d[2 + D][2 * pr], d[2 + D][2 * pr + 1]);
+            const float2 z0 = add2(make_float2(d[0][2 * pr], d[0][2 * pr + 1]), b);
             jet2_from_a0<Cfg>(tanh2(z0), zd, zxx, zyy, a);
 #pragma unroll
             for (int c = 0; c < C; ++c) v[c][pr] = a[c];
           }
-          emit_operand<C>(v, tm_lane + Cfg::COL_A + 8u * g);
+          emit_operand<C, true>(v, tm_lane + Cfg::COL_A + 8u * g + 4u * v4);
           if constexpr (TRAIN) {
-            uint4 p1[C], p2[C];
+            uint2 p1[C], p2[C];
             pack_images<C>(v, p1, p2);
             store_images<C>(imgX + img_thr + g * 256, p1, p2);
           }
-          tmem_wait_st();
-          umma::fence_before_thread_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bar[B_AREADY + g]);
+          arrive_group(g);
         }
       }
-
       TC_PROF(2);
-      // ---- layer 3 + output layer + residuals (+ z-bar_3) ----------------------------------------------------------
-      float a3[C][16];                         // a-jets of layer 3 of this thread's 16 neurons
+
+      // ---- layer 3 + output layer ------------------------------------------------------------------------------------
+      float a3[C][8];                          // a-jets of layer 3 of this thread's 8 neurons
       float J[C][O];
       {
         mbar_wait(&bar[B_DFULL], ph_df);
         ph_df ^= 1u;
         umma::fence_after_thread_sync();
         TC_PROF(4);
-        float d[C][16];
-#pragma unroll
-        for (int c = 0; c < C; ++c) tmem_ld16(tm_lane + Cfg::COL_D + 32u * c + 16u * h, d[c]);
-        umma::fence_before_thread_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar[B_DLOADED]);
         float2 Jp[C][O];
 #pragma unroll
         for (int c = 0; c < C; ++c)
 #pragma unroll
           for (int o = 0; o < O; ++o) Jp[c][o] = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int n2 = 0; n2 < 8; ++n2) {
-          const int j = 16 * h + 2 * n2;
-          const float2 b = *reinterpret_cast<const float2*>(sB + 2 * H + j);
-          float2 zd[D], a[C];
+        for (int hs = 0; hs < 2; ++hs) {
+          const int g = 2 * hs + u, j0 = 8 * g + 4 * v4;
+          float d[C][4];
+          tmem_ld4x5(tm_lane + Cfg::COL_D + 8u * g + 4u * v4, d);
+          if (hs == 1) arrive_dloaded();
 #pragma unroll
-          for (int i = 0; i < D; ++i) zd[i] = make_float2(d[1 + i][2 * n2], d[1 + i][2 * n2 + 1]);
-          const float2 zxx = make_float2(d[1 + D][2 * n2], d[1 + D][2 * n2 + 1]);
-          const float2 zyy = make_float2(d[2 + D][2 * n2], d[2 + D][2 * n2 + 1]);
-          const float2 z0 = add2(make_float2(d[0][2 * n2], d[0][2 * n2 + 1]), b);
-          jet2_from_a0<Cfg>(tanh2(z0), zd, zxx, zyy, a);
-          const float4 k0 = *reinterpret_cast<const float4*>(sKo + j * 4), k1 = *reinterpret_cast<const float4*>(sKo + j * 4 + 4);
-          const float kv0[4] = {k0.x, k0.y, k0.z, k0.w}, kv1[4] = {k1.x, k1.y, k1.z, k1.w};
+          for (int pr = 0; pr < 2; ++pr) {
+            const int j = j0 + 2 * pr;
+            const float2 b = *reinterpret_cast<const float2*>(sB + 2 * H + j);
+            float2 zd[D], a[C];
 #pragma unroll
-          for (int c = 0; c < C; ++c) {
-            a3[c][2 * n2] = a[c].x;
-            a3[c][2 * n2 + 1] = a[c].y;
+            for (int i = 0; i < D; ++i) zd[i] = make_float2(d[1 + i][2 * pr], d[1 + i][2 * pr + 1]);
+            const float2 zxx = make_float2(d[1 + D][2 * pr], d[1 + D][2 * pr + 1]);
+            const float2 zyy = make_float2(d[2 + D][2 * pr], d[2 + D][2 * pr + 1]);
+            const float2 z0 = add2(make_float2(d[0][2 * pr], d[0][2 * pr + 1]), b);
+            jet2_from_a0<Cfg>(tanh2(z0), zd, zxx, zyy, a);
+            const float4 k0 = *reinterpret_cast<const float4*>(sKo + j * 4), k1 = *reinterpret_cast<const float4*>(sKo + j * 4 + 4);
+            const float kv0[4] = {k0.x, k0.y, k0.z, k0.w}, kv1[4] = {k1.x, k1.y, k1.z, k1.w};
 #pragma unroll
-            for (int o = 0; o < O; ++o) Jp[c][o] = fma2(a[c], make_float2(kv0[o], kv1[o]), Jp[c][o]);
+            for (int c = 0; c < C; ++c) {
+              a3[c][4 * hs + 2 * pr] = a[c].x;
+              a3[c][4 * hs + 2 * pr + 1] = a[c].y;
+#pragma unroll
+              for (int o = 0; o < O; ++o) Jp[c][o] = fma2(a[c], make_float2(kv0[o], kv1[o]), Jp[c][o]);
+            }
           }
         }
-        // the other half of the neurons lives in the partner warp (same lanes): exchange the partial output jets through
-        // tensor memory -- each thread writes into the columns its partner will later overwrite with its own operand
-        float mine[16], theirs[16];
+        // the other 24 neurons live in the 3 partner warps of the quadrant (same lanes): exchange the partial output jets
+        // through tensor memory (columns of the operand region, idle between the forward and the adjoint GEMM)
+        float mine[16], part[16];
 #pragma unroll
         for (int c = 0; c < C; ++c)
 #pragma unroll
           for (int o = 0; o < O; ++o) mine[c * O + o] = Jp[c][o].x + Jp[c][o].y;
 #pragma unroll
         for (int i = C * O; i < 16; ++i) mine[i] = 0.f;
-        tmem_st16(tm_lane + Cfg::COL_A + 16u * (1 - h), mine);
+        tmem_st16(tm_lane + Cfg::COL_A + 16u * h, mine);
         tmem_wait_st();
         umma::fence_before_thread_sync();
-        named_bar_sync(1 + q, 64);
+        named_bar_sync(1 + q, 128);
         umma::fence_after_thread_sync();
-        tmem_ld16(tm_lane + Cfg::COL_A + 16u * h, theirs);
 #pragma unroll
         for (int c = 0; c < C; ++c)
 #pragma unroll
-          for (int o = 0; o < O; ++o) J[c][o] = mine[c * O + o] + theirs[c * O + o] + (c == 0 ? sBo[o] : 0.f);
-      }
-      if (seg->y_out != nullptr && h == 0 && valid) {
-        float* y = seg->y_out;
+          for (int o = 0; o < O; ++o) J[c][o] = (c == 0 ? sBo[o] : 0.f);
 #pragma unroll
-        for (int o = 0; o < O; ++o) y[pg * O + o] = J[0][o];
+        for (int hh = 0; hh < 4; ++hh) {       // same order in all four threads of a point: identical sums
+          tmem_ld16(tm_lane + Cfg::COL_A + 16u * hh, part);
+#pragma unroll
+          for (int c = 0; c < C; ++c)
+#pragma unroll
+            for (int o = 0; o < O; ++o) J[c][o] += part[c * O + o];
+        }
+        umma::fence_before_thread_sync();
+        named_bar_sync(1 + q, 128);             // everybody has read: the columns may take operand data again
+        umma::fence_after_thread_sync();
       }
-
+      if (seg_c->y_out != nullptr && h == 0 && valid_c) {
+        float* y = seg_c->y_out;
+#pragma unroll
+        for (int o = 0; o < O; ++o) y[pg_c * O + o] = J[0][o];
+      }
       TC_PROF(5);
-      // ---- residuals, sums of squares, adjoint of the output jets --------------------------------------------------
+
+      // ---- residuals, sums of squares, adjoint of the output jets (identical in the four threads of a point) ---------
       float Jb[C][O];
 #pragma unroll
       for (int c = 0; c < C; ++c)
 #pragma unroll
         for (int o = 0; o < O; ++o) Jb[c][o] = 0.f;
-      const int n_terms = seg->n_terms;
+      const int n_terms = seg_c->n_terms;
 #pragma unroll 1
       for (int t = 0; t < n_terms; ++t) {
-        const TermDev* __restrict__ T = seg->terms + t;
-        if (TRAIN && !T->train) continue;
+        const float* T = sterm + (term0 + t) * TW;
+        const int flags = __float_as_int(T[Cfg::T_FLAGS]);
+        const int ck = flags & 0xff;
+        const bool abs_mean = ((flags >> 8) & 0xff) != 0;
+        if (TRAIN && ((flags >> 16) & 0xff) == 0) continue;
         float r = 0.f;
 #pragma unroll
         for (int o = 0; o < O; ++o)
 #pragma unroll
-          for (int c = 0; c < C; ++c) r = fmaf(__ldg(&T->coef[o][c]), J[c][o], r);
-        float cv = 0.f;
-        int ck = 0;
+          for (int c = 0; c < C; ++c) r = fmaf(T[o * C + c], J[c][o], r);
+        const float cv = T[Cfg::T_CONV];
         if constexpr (O >= 2) {
-          cv = __ldg(&T->conv);
-          ck = __ldg(&T->conv_k);
           const float ukx = ck == 0 ? J[1 + SX][0] : J[1 + SX][1];
           const float uky = ck == 0 ? J[1 + SY][0] : J[1 + SY][1];
           r = fmaf(cv, fmaf(J[0][0], ukx, J[0][1] * uky), r);
         }
-        const float* rhs = T->rhs;
-        if (rhs != nullptr) r = fmaf(-__ldg(&T->rhs_scale), __ldg(rhs + pi), r);
-        r = valid ? r : 0.f;
-        const bool abs_mean = __ldg(&T->kind) != 0;
-        if (h == 0) {                          // both halves hold the same residual: one of them adds it up
+        const float* rhs = reinterpret_cast<const float*>((uintptr_t)__float_as_uint(T[Cfg::T_RHS]) |
+                                                          ((uintptr_t)__float_as_uint(T[Cfg::T_RHS + 1]) << 32));
+        if (rhs != nullptr) r = fmaf(-T[Cfg::T_RHS_SCALE], __ldg(rhs + pi_c), r);
+        r = valid_c ? r : 0.f;
+        if (h == 0) {                          // one of the four threads of a point adds the residual up
           float sq = abs_mean ? r : r * r;
           sq = reduce_warp(sq);
-          if (lane == 0) ssq[T->out_index] += sq;
+          if (lane == 0) ssq[__float_as_int(T[Cfg::T_OUT])] += sq;
         }
         if constexpr (TRAIN) {
-          float rb = __ldg(&T->scale) * r;
-          if (abs_mean) rb = valid ? __ldg(&T->scale) * __ldg(T->sign) : 0.f;
+          float rb = T[Cfg::T_SCALE] * r;
+          if (abs_mean) {
+            const float* sgn = reinterpret_cast<const float*>((uintptr_t)__float_as_uint(T[Cfg::T_SIGN]) |
+                                                              ((uintptr_t)__float_as_uint(T[Cfg::T_SIGN + 1]) << 32));
+            rb = valid_c ? T[Cfg::T_SCALE] * __ldg(sgn) : 0.f;
+          }
 #pragma unroll
           for (int o = 0; o < O; ++o)
 #pragma unroll
-            for (int c = 0; c < C; ++c) Jb[c][o] = fmaf(__ldg(&T->coef[o][c]), rb, Jb[c][o]);
+            for (int c = 0; c < C; ++c) Jb[c][o] = fmaf(T[o * C + c], rb, Jb[c][o]);
           if constexpr (O >= 2) {
             const float ukx = ck == 0 ? J[1 + SX][0] : J[1 + SX][1];
             const float uky = ck == 0 ? J[1 + SY][0] : J[1 + SY][1];
@@ -619,8 +721,8 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
           }
         }
       }
-
       TC_PROF(6);
+
       if constexpr (TRAIN) {
         // ---- output layer backward + tanh-jet backward of layer 3: z-bar_3 -> operand of the adjoint GEMM + image Y ----
         if (h == 0) {
@@ -630,132 +732,117 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
             if (lane == 0) sg[Cfg::SG_BO + o] += vsum;
           }
         }
+        {
+          float gko[24];
 #pragma unroll
-        for (int gi = 0; gi < 2; ++gi) {
-          const int g = 2 * h + gi;
-          float2 v[C][4];
-          float gko[24], gb[8];
+          for (int hs = 0; hs < 2; ++hs) {
+            const int g = 2 * hs + u, j0 = 8 * g + 4 * v4;
+            float2 v[C][2];
 #pragma unroll
-          for (int pr = 0; pr < 4; ++pr) {
-            const int n2 = 4 * gi + pr, j = 16 * h + 2 * n2;
-            const float4 k0 = *reinterpret_cast<const float4*>(sKo + j * 4), k1 = *reinterpret_cast<const float4*>(sKo + j * 4 + 4);
-            const float kv0[4] = {k0.x, k0.y, k0.z, k0.w}, kv1[4] = {k1.x, k1.y, k1.z, k1.w};
-            float2 aj[C], ab[C], zb[C], zdummy[D];
+            for (int pr = 0; pr < 2; ++pr) {
+              const int n8 = 4 * hs + 2 * pr, j = j0 + 2 * pr;
+              const float4 k0 = *reinterpret_cast<const float4*>(sKo + j * 4), k1 = *reinterpret_cast<const float4*>(sKo + j * 4 + 4);
+              const float kv0[4] = {k0.x, k0.y, k0.z, k0.w}, kv1[4] = {k1.x, k1.y, k1.z, k1.w};
+              float2 aj[C], ab[C], zb[C], zdummy[D];
 #pragma unroll
-            for (int i = 0; i < D; ++i) zdummy[i] = bc2(0.f);
-            float2 pk[O];
+              for (int i = 0; i < D; ++i) zdummy[i] = bc2(0.f);
+              float2 pk[O];
 #pragma unroll
-            for (int o = 0; o < O; ++o) pk[o] = bc2(0.f);
+              for (int o = 0; o < O; ++o) pk[o] = bc2(0.f);
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-              aj[c] = make_float2(a3[c][2 * n2], a3[c][2 * n2 + 1]);
-              float2 b = bc2(0.f);
+              for (int c = 0; c < C; ++c) {
+                aj[c] = make_float2(a3[c][n8], a3[c][n8 + 1]);
+                float2 b = bc2(0.f);
 #pragma unroll
-              for (int o = 0; o < O; ++o) {
-                b = fma2(bc2(Jb[c][o]), make_float2(kv0[o], kv1[o]), b);
-                pk[o] = fma2(aj[c], bc2(Jb[c][o]), pk[o]);
+                for (int o = 0; o < O; ++o) {
+                  b = fma2(bc2(Jb[c][o]), make_float2(kv0[o], kv1[o]), b);
+                  pk[o] = fma2(aj[c], bc2(Jb[c][o]), pk[o]);
+                }
+                ab[c] = b;
               }
-              ab[c] = b;
-            }
 #pragma unroll
-            for (int o = 0; o < 3; ++o) {
-              gko[3 * (2 * pr) + o] = o < O ? pk[o < O ? o : 0].x : 0.f;
-              gko[3 * (2 * pr + 1) + o] = o < O ? pk[o < O ? o : 0].y : 0.f;
-            }
-            tanh_jet2_bwd<Cfg, false>(aj, zdummy, ab, zb);
-            gb[2 * pr] = zb[0].x;
-            gb[2 * pr + 1] = zb[0].y;
+              for (int o = 0; o < 3; ++o) {
+                gko[3 * n8 + o] = o < O ? pk[o < O ? o : 0].x : 0.f;
+                gko[3 * (n8 + 1) + o] = o < O ? pk[o < O ? o : 0].y : 0.f;
+              }
+              tanh_jet2_bwd<Cfg, false>(aj, zdummy, ab, zb);
+              gb3acc[n8] += zb[0].x;
+              gb3acc[n8 + 1] += zb[0].y;
 #pragma unroll
-            for (int c = 0; c < C; ++c) v[c][pr] = zb[c];
+              for (int c = 0; c < C; ++c) v[c][pr] = zb[c];
+            }
+            emit_operand<C, false>(v, tm_lane + Cfg::COL_A + 8u * g + 4u * v4);
+            {
+              uint2 p1[C], p2[C];
+              pack_images<C>(v, p1, p2);
+              store_images<C>(imgY + img_thr + g * 256, p1, p2);
+            }
+            arrive_group(g);
           }
-          emit_operand<C>(v, tm_lane + Cfg::COL_A + 8u * g);
-          {
-            uint4 p1[C], p2[C];
-            pack_images<C>(v, p1, p2);
-            store_images<C>(imgY + img_thr + g * 256, p1, p2);
-          }
-          tmem_wait_st();
-          umma::fence_before_thread_sync();
+          umma::fence_proxy_async_smem();      // images X (a_2) and Y (z-bar_3) -> visible to the weight-gradient MMAs
           __syncwarp();
-          if (lane == 0) mbar_arrive(&bar[B_AREADY + g]);
-          // K_out and b_3 gradients of these 8 neurons: sums over the warp's 32 points
+          if (lane == 0) mbar_arrive(&bar[B_IMG]);
+          // K_out gradient of this warp's 8 neurons: sums over its 32 points
           xreduce8<3>(gko, lane);
-          xreduce8<1>(gb, lane);
           if ((lane & 3) == 0) {
-            const int n16 = 8 * gi + (lane >> 2);
 #pragma unroll
-            for (int o = 0; o < 3; ++o) sg[Cfg::SG_KO + n16 * 4 + o] += gko[o];
-            sg[Cfg::SG_B3 + n16] += gb[0];
+            for (int o = 0; o < 3; ++o) sg[Cfg::SG_KO + (lane >> 2) * 4 + o] += gko[o];
           }
         }
-        umma::fence_proxy_async_smem();        // images X (a_2) and Y (z-bar_3) -> visible to the weight-gradient MMAs
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar[B_IMG]);
-
         TC_PROF(7);
+
         // ---- layer 2 backward: a-bar_2 (accumulators) + a_2 (image X) -> z-bar_2 ------------------------------------
         {
           mbar_wait(&bar[B_DFULL], ph_df);
           ph_df ^= 1u;
           umma::fence_after_thread_sync();
           TC_PROF(8);
-          float d[C][16];
+          uint2 zp1[2][C], zp2[2][C];          // images of z-bar_2: written once the K-bar_3 MMAs have finished reading X and Y
 #pragma unroll
-          for (int c = 0; c < C; ++c) tmem_ld16(tm_lane + Cfg::COL_D + 32u * c + 16u * h, d[c]);
-          umma::fence_before_thread_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bar[B_DLOADED]);
-          uint4 zp1[2][C], zp2[2][C];          // images of z-bar_2: written once the K-bar_3 MMAs have finished reading X and Y
-#pragma unroll
-          for (int gi = 0; gi < 2; ++gi) {
-            const int g = 2 * h + gi;
-            float2 v[C][4];
-            float gb[8];
-            uint4 q1[C], q2[C];
+          for (int hs = 0; hs < 2; ++hs) {
+            const int g = 2 * hs + u;
+            float d[C][4];
+            tmem_ld4x5(tm_lane + Cfg::COL_D + 8u * g + 4u * v4, d);
+            if (hs == 1) arrive_dloaded();
+            uint2 q1[C], q2[C];
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-              q1[c] = *reinterpret_cast<const uint4*>(imgX + img_thr + g * 256 + c * 16384);
-              q2[c] = *reinterpret_cast<const uint4*>(imgX + img_thr + g * 256 + c * 16384 + 128);
+              q1[c] = *reinterpret_cast<const uint2*>(imgX + img_thr + g * 256 + c * 16384);
+              q2[c] = *reinterpret_cast<const uint2*>(imgX + img_thr + g * 256 + c * 16384 + 128);
             }
+            float2 v[C][2];
 #pragma unroll
-            for (int pr = 0; pr < 4; ++pr) {
+            for (int pr = 0; pr < 2; ++pr) {
               float2 aj[C], ab[C], zb[C], zdummy[D];
 #pragma unroll
               for (int i = 0; i < D; ++i) zdummy[i] = bc2(0.f);
 #pragma unroll
               for (int c = 0; c < C; ++c) {
-                const uint32_t w1 = pr == 0 ? q1[c].x : pr == 1 ? q1[c].y : pr == 2 ? q1[c].z : q1[c].w;
-                const uint32_t w2 = pr == 0 ? q2[c].x : pr == 1 ? q2[c].y : pr == 2 ? q2[c].z : q2[c].w;
-                aj[c] = bf16_unpair(w1, w2);
-                ab[c] = make_float2(d[c][8 * gi + 2 * pr], d[c][8 * gi + 2 * pr + 1]);
+                aj[c] = bf16_unpair(pr == 0 ? q1[c].x : q1[c].y, pr == 0 ? q2[c].x : q2[c].y);
+                ab[c] = make_float2(d[c][2 * pr], d[c][2 * pr + 1]);
               }
               tanh_jet2_bwd<Cfg, false>(aj, zdummy, ab, zb);
-              gb[2 * pr] = zb[0].x;
-              gb[2 * pr + 1] = zb[0].y;
+              gb2acc[4 * hs + 2 * pr] += zb[0].x;
+              gb2acc[4 * hs + 2 * pr + 1] += zb[0].y;
 #pragma unroll
               for (int c = 0; c < C; ++c) v[c][pr] = zb[c];
             }
-            emit_operand<C>(v, tm_lane + Cfg::COL_A + 8u * g);
-            pack_images<C>(v, zp1[gi], zp2[gi]);
-            tmem_wait_st();
-            umma::fence_before_thread_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar[B_AREADY + g]);
-            xreduce8<1>(gb, lane);
-            if ((lane & 3) == 0) sg[Cfg::SG_B2 + 8 * gi + (lane >> 2)] += gb[0];
+            emit_operand<C, false>(v, tm_lane + Cfg::COL_A + 8u * g + 4u * v4);
+            pack_images<C>(v, zp1[hs], zp2[hs]);
+            arrive_group(g);
           }
           TC_PROF(9);
           drain_w(1);                          // K-bar_3 batch finished: its accumulator -> totals; X and Y are free
           TC_PROF(10);
 #pragma unroll
-          for (int gi = 0; gi < 2; ++gi) {
-            const int g = 2 * h + gi;
-            store_images<C>(imgX + img_thr + g * 256, zp1[gi], zp2[gi]);
+          for (int hs = 0; hs < 2; ++hs) {
+            const int g = 2 * hs + u, j0 = 8 * g + 4 * v4;
+            store_images<C>(imgX + img_thr + g * 256, zp1[hs], zp2[hs]);
             // a_1 jets re-materialised from tanh(z1) into image Y (left operand of the K-bar_2 MMAs)
-            float2 v[C][4];
+            float2 v[C][2];
 #pragma unroll
-            for (int pr = 0; pr < 4; ++pr) {
-              const int j = 8 * g + 2 * pr;
+            for (int pr = 0; pr < 2; ++pr) {
+              const int j = j0 + 2 * pr;
               const float2 a0 = make_float2(a1buf[j * Cfg::TP + p], a1buf[(j + 1) * Cfg::TP + p]);
               float2 zd[D], a[C];
 #pragma unroll
@@ -764,7 +851,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
 #pragma unroll
               for (int c = 0; c < C; ++c) v[c][pr] = a[c];
             }
-            uint4 p1[C], p2[C];
+            uint2 p1[C], p2[C];
             pack_images<C>(v, p1, p2);
             store_images<C>(imgY + img_thr + g * 256, p1, p2);
           }
@@ -773,52 +860,51 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
           if (lane == 0) mbar_arrive(&bar[B_IMG]);
           w_pending = true;
         }
-
         TC_PROF(11);
+      }
+
+      // the next tile's segment and point coordinates: the global loads fly during the last phase of this tile
+      if (tile + (int)gridDim.x < total_tiles) prepare(tile + gridDim.x);
+
+      if constexpr (TRAIN) {
         // ---- layer 1 backward: a-bar_1 (accumulators) + tanh(z1) -> K1 / b1 gradients --------------------------------
-        {
-          mbar_wait(&bar[B_DFULL], ph_df);
-          ph_df ^= 1u;
-          umma::fence_after_thread_sync();
-          TC_PROF(12);
-          float d[C][16];
+        mbar_wait(&bar[B_DFULL], ph_df);
+        ph_df ^= 1u;
+        umma::fence_after_thread_sync();
+        TC_PROF(12);
+        float gk[8 * (D + 1)];
 #pragma unroll
-          for (int c = 0; c < C; ++c) tmem_ld16(tm_lane + Cfg::COL_D + 32u * c + 16u * h, d[c]);
-          umma::fence_before_thread_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bar[B_DLOADED]);
+        for (int hs = 0; hs < 2; ++hs) {
+          const int g = 2 * hs + u, j0 = 8 * g + 4 * v4;
+          float d[C][4];
+          tmem_ld4x5(tm_lane + Cfg::COL_D + 8u * g + 4u * v4, d);
+          if (hs == 1) arrive_dloaded();
 #pragma unroll
-          for (int gi = 0; gi < 2; ++gi) {
-            const int g = 2 * h + gi;
-            float gk[8 * (D + 1)];
+          for (int pr = 0; pr < 2; ++pr) {
+            const int j = j0 + 2 * pr, n8 = 4 * hs + 2 * pr;
+            float2 aj[C], ab[C], zb[C], zd[D];
+            aj[0] = make_float2(a1buf[j * Cfg::TP + p], a1buf[(j + 1) * Cfg::TP + p]);
 #pragma unroll
-            for (int pr = 0; pr < 4; ++pr) {
-              const int j = 8 * g + 2 * pr;
-              float2 aj[C], ab[C], zb[C], zd[D];
-              aj[0] = make_float2(a1buf[j * Cfg::TP + p], a1buf[(j + 1) * Cfg::TP + p]);
+            for (int c = 1; c < C; ++c) aj[c] = bc2(0.f);
 #pragma unroll
-              for (int c = 1; c < C; ++c) aj[c] = bc2(0.f);
+            for (int i = 0; i < D; ++i) zd[i] = *reinterpret_cast<const float2*>(sK1 + i * H + j);
 #pragma unroll
-              for (int i = 0; i < D; ++i) zd[i] = *reinterpret_cast<const float2*>(sK1 + i * H + j);
+            for (int c = 0; c < C; ++c) ab[c] = make_float2(d[c][2 * pr], d[c][2 * pr + 1]);
+            tanh_jet2_bwd<Cfg, true>(aj, zd, ab, zb);
 #pragma unroll
-              for (int c = 0; c < C; ++c) ab[c] = make_float2(d[c][8 * gi + 2 * pr], d[c][8 * gi + 2 * pr + 1]);
-              tanh_jet2_bwd<Cfg, true>(aj, zd, ab, zb);
-#pragma unroll
-              for (int i = 0; i < D; ++i) {
-                gk[(D + 1) * (2 * pr) + i] = fmaf(x[i], zb[0].x, zb[1 + i].x);
-                gk[(D + 1) * (2 * pr + 1) + i] = fmaf(x[i], zb[0].y, zb[1 + i].y);
-              }
-              gk[(D + 1) * (2 * pr) + D] = zb[0].x;
-              gk[(D + 1) * (2 * pr + 1) + D] = zb[0].y;
+            for (int i = 0; i < D; ++i) {
+              gk[(D + 1) * n8 + i] = fmaf(xc[i], zb[0].x, zb[1 + i].x);
+              gk[(D + 1) * (n8 + 1) + i] = fmaf(xc[i], zb[0].y, zb[1 + i].y);
             }
-            xreduce8<D + 1>(gk, lane);
-            if ((lane & 3) == 0) {
-              const int n16 = 8 * gi + (lane >> 2);
-#pragma unroll
-              for (int i = 0; i < D; ++i) sg[Cfg::SG_K1 + i * 16 + n16] += gk[i];
-              sg[Cfg::SG_B1 + n16] += gk[D];
-            }
+            gk[(D + 1) * n8 + D] = zb[0].x;
+            gk[(D + 1) * (n8 + 1) + D] = zb[0].y;
           }
+        }
+        xreduce8<D + 1>(gk, lane);
+        if ((lane & 3) == 0) {
+#pragma unroll
+          for (int i = 0; i < D; ++i) sg[Cfg::SG_K1 + i * 8 + (lane >> 2)] += gk[i];
+          sg[Cfg::SG_B1 + (lane >> 2)] += gk[D];
         }
         TC_PROF(13);
       } else {
@@ -827,54 +913,55 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
     }
     if constexpr (TRAIN) {
       if (w_pending) drain_w(0);
+      xreduce8<1>(gb2acc, lane);
+      xreduce8<1>(gb3acc, lane);
+      if ((lane & 3) == 0) {
+        sg[Cfg::SG_B2 + (lane >> 2)] += gb2acc[0];
+        sg[Cfg::SG_B3 + (lane >> 2)] += gb3acc[0];
+      }
+    }
+
+    // ---- CTA reduction over the epilogue warps: this CTA's workspace row (Keras order, then the term sums) -----------
+    umma::fence_before_thread_sync();
+    named_bar_sync(5, Cfg::NEPI * 32);
+    float* row = ws + (size_t)blockIdx.x * ws_stride;
+    constexpr int nepi = Cfg::NEPI * 32;
+    if constexpr (TRAIN) {
+      // neuron j = 8 (2 hs + u) + 4 v + e lives in the warps 4 (2u + v) + quadrant, slot n8 = 4 hs + e
+      for (int idx = tid; idx < P; idx += nepi) {
+        float s = 0.f;
+        int j = -1, off = 0, stride = 1;
+        if (idx < D * H) { j = idx % H; off = Cfg::SG_K1 + (idx / H) * 8; }
+        else if (idx < D * H + H) { j = idx - D * H; off = Cfg::SG_B1; }
+        else if (idx < Cfg::OFF_KO) {
+          const int r = idx - Cfg::offK(2);
+          const int l = r / (H * H + H), qq = r % (H * H + H);
+          if (qq < H * H) s = tot[l * 1024 + qq];
+          else { j = qq - H * H; off = l == 0 ? Cfg::SG_B2 : Cfg::SG_B3; }
+        } else if (idx < Cfg::OFF_BO) {
+          const int r = idx - Cfg::OFF_KO;
+          j = r / O; off = Cfg::SG_KO + (r % O); stride = 4;
+        } else {
+#pragma unroll
+          for (int w = 0; w < 4; ++w) s += sg_all[w * Cfg::SG_FLOATS + Cfg::SG_BO + (idx - Cfg::OFF_BO)];
+        }
+        if (j >= 0) {
+          const int hh = 2 * ((j >> 3) & 1) + ((j >> 2) & 1), n8 = 4 * (j >> 4) + (j & 3);
+#pragma unroll
+          for (int w = 0; w < 4; ++w) s += sg_all[(4 * hh + w) * Cfg::SG_FLOATS + off + n8 * stride];
+        }
+        row[idx] = s;
+      }
+    }
+    for (int t = tid; t < n_terms_total; t += nepi) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) s += ssq_all[w * kMaxLaunchTerms + t];
+      row[ws_stride - n_terms_total + t] = s;
     }
   }
 
-  // ---- CTA reduction: this CTA's workspace row (Keras order, then the term sums) ---------------------------------------
   umma::fence_before_thread_sync();
-  __syncthreads();
-  umma::fence_after_thread_sync();
-  float* row = ws + (size_t)blockIdx.x * ws_stride;
-  if constexpr (TRAIN) {
-    for (int idx = tid; idx < P; idx += nthr) {
-      float s = 0.f;
-      // small gradients of neuron j live in the 4 epilogue warps of half j / 16 (slot j % 16); b_out in warps 0..3
-      if (idx < D * H) {
-        const int i = idx / H, j = idx % H;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) s += sg_all[(4 * (j >> 4) + w) * Cfg::SG_FLOATS + Cfg::SG_K1 + i * 16 + (j & 15)];
-      } else if (idx < D * H + H) {
-        const int j = idx - D * H;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) s += sg_all[(4 * (j >> 4) + w) * Cfg::SG_FLOATS + Cfg::SG_B1 + (j & 15)];
-      } else if (idx < Cfg::OFF_KO) {
-        const int r = idx - Cfg::offK(2);
-        const int l = r / (H * H + H), qq = r % (H * H + H);
-        if (qq < H * H) {
-          s = tot[l * 1024 + qq];
-        } else {
-          const int j = qq - H * H;
-          const int off = l == 0 ? Cfg::SG_B2 : Cfg::SG_B3;
-#pragma unroll
-          for (int w = 0; w < 4; ++w) s += sg_all[(4 * (j >> 4) + w) * Cfg::SG_FLOATS + off + (j & 15)];
-        }
-      } else if (idx < Cfg::OFF_BO) {
-        const int r = idx - Cfg::OFF_KO, j = r / O, o = r % O;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) s += sg_all[(4 * (j >> 4) + w) * Cfg::SG_FLOATS + Cfg::SG_KO + (j & 15) * 4 + o];
-      } else {
-#pragma unroll
-        for (int w = 0; w < 4; ++w) s += sg_all[w * Cfg::SG_FLOATS + Cfg::SG_BO + (idx - Cfg::OFF_BO)];
-      }
-      row[idx] = s;
-    }
-  }
-  for (int t = tid; t < n_terms_total; t += nthr) {
-    float s = 0.f;
-#pragma unroll
-    for (int w = 0; w < 4; ++w) s += ssq_all[w * kMaxLaunchTerms + t];
-    row[ws_stride - n_terms_total + t] = s;
-  }
   __syncthreads();
   if (warp == Cfg::NEPI) umma::tmem_dealloc<512>(tmem);
 }

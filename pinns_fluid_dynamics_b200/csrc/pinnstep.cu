@@ -1009,7 +1009,7 @@ extern "C" int pinn_adam_step_dev(float* params_dev, const float* grad_dev, floa
 extern "C" int pinn_tc_profile_read(unsigned long long* host_out) {
   CUDA_TRY(cudaDeviceSynchronize());
   CUDA_TRY(cudaMemcpyFromSymbol(host_out, pinn::ftc::g_tc_prof, sizeof(pinn::ftc::g_tc_prof)));
-  static unsigned long long zero[160 * 9 * 16];
+  static unsigned long long zero[160 * 20 * 16];
   CUDA_TRY(cudaMemcpyToSymbol(pinn::ftc::g_tc_prof, zero, sizeof(zero)));
   return PINN_OK;
 }

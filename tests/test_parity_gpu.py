@@ -448,3 +448,126 @@ def test_prefetched_inputs_restore_the_device_arena():
     pb.plan.upload_inputs()
     t2, _, g2 = pb.evaluate()
     assert t2 == t0 and torch.equal(g2, g0)
+
+
+# ---- parity at the BASELINE.json sizes (configs 2, 4, 5) and across ranks ---------------------------
+
+def test_poiseuille_at_baseline_size_matches_reference_restatement():
+    """BASELINE config 2 at its own size (10 000 collocation points, 4 x 250 boundary points, 10 velocity fit points),
+    faithful closures (poiseuille_flow.py:173-254), against the nested reverse-mode restatement."""
+    from oracle import reference_step
+    kw = dict(PDE=10_000, BC=250, Vel=10, Pres=0, Test=100)
+    data, var, model, pb = _setup("poiseuille_flow", kw)
+    total, values, grad = pb.evaluate()
+    ref = reference_step.build(data, var)
+    ref_values, ref_total, ref_grad = ref.loss_and_grad()
+    assert _rel(total, ref_total) < LOSS_RTOL
+    for l, v, rv in zip(pb.losses, values, ref_values):
+        if rv == 0.0:
+            assert v == 0.0, l.name
+        else:
+            assert _term_close(v, rv), (l.name, v, rv)
+    g, rg = grad.double().cpu().numpy(), ref_grad.numpy()
+    assert np.linalg.norm(g - rg) / np.linalg.norm(rg) < GRAD_RTOL
+
+
+def test_cavity_steady_20k_matches_reference_restatement():
+    """the benchmarked loss table (14 terms, faithful cavity_steady.py:159-231 closures) on 20 000 collocation points
+    against the nested reverse-mode restatement: the engine the bench times, checked against the reference's formulation"""
+    from oracle import reference_step
+    kw = dict(PDE=20_000, BC=1000, Vel=100, Pres=1, Test=100, noise_bnd=0.01, noise_fit=0.01)
+    data, var, model, pb = _setup("cavity_steady", kw)
+    assert pb.plan.engine == "fused_tcgen05"
+    total, values, grad = pb.evaluate()
+    ref = reference_step.build(data, var)
+    ref_values, ref_total, ref_grad = ref.loss_and_grad()
+    assert _rel(total, ref_total) < LOSS_RTOL
+    for l, v, rv in zip(pb.losses, values, ref_values):
+        assert _term_close(v, rv), (l.name, v, rv)
+    g, rg = grad.double().cpu().numpy(), ref_grad.numpy()
+    assert np.linalg.norm(g - rg) / np.linalg.norm(rg) < GRAD_RTOL
+
+
+def test_cavity_steady_at_baseline_size_matches_taylor_oracle():
+    """BASELINE config 4 at its own size -- the configuration bench.py times: 1 000 000 collocation points, 4 x 1000
+    boundary points, 100 + 1 fit points, 14 terms -- against the float64 Taylor-mode oracle (chunked over the points)."""
+    from oracle import taylor
+    kw = dict(PDE=1_000_000, BC=1000, Vel=100, Pres=1, Test=100, noise_bnd=0.01, noise_fit=0.01)
+    data, var, model, pb = _setup("cavity_steady", kw)
+    assert pb.plan.engine == "fused_tcgen05"
+    total, values, grad = pb.evaluate()
+    theta = torch.cat([v.reshape(-1) for v in var]).numpy()
+    out = taylor.loss_and_grad(pb.compiled, theta, chunk=131072)
+    ref_total, ref_vals, _ = assemble_losses(pb.compiled, out[pb.compiled.n_params:])
+    assert _rel(total, ref_total) < LOSS_RTOL
+    for l, v, rv in zip(pb.losses, values, ref_vals):
+        assert _term_close(v, rv), (l.name, v, rv)
+    g, rg = grad.double().cpu().numpy(), out[:pb.compiled.n_params]
+    assert np.linalg.norm(g - rg) / np.linalg.norm(rg) < GRAD_RTOL
+
+
+_WIDE_200K = {}
+
+
+def _wide_200k_reference():
+    """float64 Taylor-mode oracle of the 8x128 unsteady network on 200 000 collocation points (computed once)"""
+    from oracle import reference_step, taylor
+    if not _WIDE_200K:
+        kw = dict(PDE=200_000, BC=500, IC=500, Vel=1, Pres=1, Test=50, noise_bnd=0.05, noise_fit=0.05, n_times=4, hidden=(128,) * 8)
+        data = problems.cavity_unsteady(seed=1, **kw)
+        var = reference_step.glorot_uniform_variables(data.dim, data.hidden, data.out_dim, seed=11, bias_std=0.1)
+        _WIDE_200K.update(data=data, var=var)
+    return _WIDE_200K
+
+
+@pytest.mark.parametrize("workspace_mb", [None, 2048])
+def test_tensor_core_engine_200k_points_matches_taylor_oracle(monkeypatch, workspace_mb):
+    """BASELINE config 5 network (3-128x8-3) on 200 000 space-time collocation points against the Taylor oracle, with the
+    default 16 GiB workspace (one batch) and with a 2 GiB workspace (3 batches of 83 160 points, ragged last batch)."""
+    from oracle import taylor
+    if workspace_mb is not None:
+        monkeypatch.setenv("PINN_TC_WORKSPACE_MB", str(workspace_mb))
+    else:
+        monkeypatch.delenv("PINN_TC_WORKSPACE_MB", raising=False)
+    ref = _wide_200k_reference()
+    data, var = ref["data"], ref["var"]
+    model = ns.TanhMLP(data.dim, data.hidden, data.out_dim, device="cuda")
+    model.set_weights([v.numpy() for v in var])
+    losses, ltest = loss_tables.build_loss_table(data)
+    pb = ns.OptimizationProblem(model.variables, losses, ltest)
+    assert pb.plan.engine.startswith("layered_tf32x3") or pb.plan.engine.startswith("fused_wide")
+    total, values, grad = pb.evaluate()
+    if "out" not in ref:
+        theta = torch.cat([v.reshape(-1) for v in var]).numpy()
+        ref["out"] = taylor.loss_and_grad(pb.compiled, theta, chunk=16384)
+    out = ref["out"]
+    ref_total, ref_vals, _ = assemble_losses(pb.compiled, out[pb.compiled.n_params:])
+    assert _rel(total, ref_total) < LOSS_RTOL
+    for l, v, rv in zip(pb.losses, values, ref_vals):
+        assert _term_close(v, rv), (l.name, v, rv)
+    g, rg = grad.double().cpu().numpy(), out[:pb.compiled.n_params]
+    assert np.linalg.norm(g - rg) / np.linalg.norm(rg) < GRAD_RTOL
+
+
+def test_two_nccl_ranks_match_the_unsharded_oracle():
+    """N > 1 on the device: two ranks (torchrun, NCCL) evaluate their shards of every point set, one all-reduce joins
+    them, and the global loss terms and gradient must match the float64 oracle of the WHOLE problem (both engines).
+    Skipped on a single-GPU box; tests/test_distributed_gloo.py covers the same host logic on CPU."""
+    import re
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(root, "tools", "multi_gpu_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if "world=2" in l]
+    assert len(lines) == 2, res.stdout
+    for l in lines:
+        m = re.search(r"total rel err ([0-9.e+-]+), worst term ([0-9.e+-]+), grad rel L2 ([0-9.e+-]+)", l)
+        assert m, l
+        assert float(m.group(1)) < LOSS_RTOL and float(m.group(2)) < 2e-5 and float(m.group(3)) < GRAD_RTOL, l

@@ -19,7 +19,7 @@ model = ns.TanhMLP(data.dim, data.hidden, data.out_dim, device="cuda", seed=3)
 losses, ltest = loss_tables.build_loss_table(data)
 pb = ns.OptimizationProblem(model.variables, losses, ltest)
 lib = _capi.load()
-buf = np.zeros((160, 9, 16), dtype=np.uint64)
+buf = np.zeros((160, 20, 16), dtype=np.uint64)
 ptr = buf.ctypes.data_as(C.POINTER(C.c_ulonglong))
 for _ in range(3):
     pb.plan.loss_and_grad(pb.flat)
@@ -28,8 +28,8 @@ pb.plan.loss_and_grad(pb.flat)
 lib.pinn_tc_profile_read(ptr)
 tiles = (n + 127) // 128 + 4 * 8 + 2
 per_cta = tiles / 148.0
-epi = buf[:148, :8, :].astype(np.float64).mean(axis=(0, 1)) / per_cta
-mma = buf[:148, 8, :].astype(np.float64).mean(axis=0) / per_cta
+epi = buf[:148, :16, :].astype(np.float64).mean(axis=(0, 1)) / per_cta
+mma = buf[:148, 16, :].astype(np.float64).mean(axis=0) / per_cta
 names = ["layer 1 (F1)", "wait G2", "E2: load D", "E2: wait/drain W2", "wait G3", "E3: jets + exchange", "residuals", "E3: adjoint + z3",
          "wait GB3", "EB2: adjoint", "EB2: wait/drain W3", "EB2: images + a1 remat", "wait GB2", "EB1"]
 print(f"fused_tc_kernel, {n} points, cycles per tile (mean over CTAs and epilogue warps), engine {pb.plan.engine}")

@@ -66,7 +66,8 @@ struct TcCfg {
   static constexpr int TERM_WORDS = 24;
   static constexpr int T_CONV = 15, T_RHS_SCALE = 16, T_SCALE = 17, T_FLAGS = 18, T_OUT = 19, T_RHS = 20, T_SIGN = 22;
   static constexpr int OFF_SEGT = OFF_TERM + kMaxLaunchTerms * TERM_WORDS * 4;   // first staged term of each segment
-  static constexpr int OFF_BAR = OFF_SEGT + kMaxLaunchTerms * 4;
+  static constexpr int OFF_SEG = OFF_SEGT + kMaxLaunchTerms * 4;                 // per segment: chunk_begin | n_terms | n | pts | y_out (8 words)
+  static constexpr int OFF_BAR = OFF_SEG + kMaxLaunchTerms * 32;
   static constexpr int SMEM_BYTES = OFF_BAR + 16 * 8;
   static_assert(SMEM_BYTES <= 232448, "shared memory exhausted");
   static_assert(O * C <= 15, "staged term layout");
@@ -101,8 +102,24 @@ __device__ __forceinline__ bool elect_one() {
   asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
   return pred != 0;
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+// barriers by their 32-bit shared-memory address (computed once: a generic-to-shared conversion per use costs an S2R)
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 template <int REGS> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
@@ -118,6 +135,17 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d, uint32_t a, uint64_t b, 
 }
 __device__ __forceinline__ void mma_bf16_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d),
+               "l"(a), "l"(b), "r"(idesc), "r"(acc)
+               : "memory");
+}
+// the same with the A operand kept in / taken from the collector buffer (two MMAs of a k-step share their A operand)
+__device__ __forceinline__ void mma_bf16_ss_keep_a(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d),
+               "l"(a), "l"(b), "r"(idesc), "r"(acc)
+               : "memory");
+}
+__device__ __forceinline__ void mma_bf16_ss_reuse_a(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d),
                "l"(a), "l"(b), "r"(idesc), "r"(acc)
                : "memory");
 }
@@ -263,11 +291,12 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
   float* ssq_all = reinterpret_cast<float*>(smem + Cfg::OFF_SSQ);
   float* sterm = reinterpret_cast<float*>(smem + Cfg::OFF_TERM);
   int* segt = reinterpret_cast<int*>(smem + Cfg::OFF_SEGT);
+  long long* sseg = reinterpret_cast<long long*>(smem + Cfg::OFF_SEG);    // [si][4]: (chunk_begin | n_terms << 32), n, pts, y_out
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 12);
 
   const int tid = threadIdx.x, nthr = Cfg::THREADS;
-  const int lane = tid & 31, warp = tid >> 5;
+  const int lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform for the compiler: tensor-memory addresses stay in uniform registers
 
   // ---- stage the parameter vector (one TMA bulk copy + tail), build the operand images, stage the terms ---------------
   {
@@ -298,6 +327,12 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
         t0 += segs[si].n_terms;
       }
     }
+    for (int si = tid; si < n_segs; si += nthr) {
+      sseg[4 * si + 0] = (long long)(unsigned)segs[si].chunk_begin | ((long long)segs[si].n_terms << 32);
+      sseg[4 * si + 1] = segs[si].n;
+      sseg[4 * si + 2] = (long long)reinterpret_cast<uintptr_t>(segs[si].pts);
+      sseg[4 * si + 3] = (long long)reinterpret_cast<uintptr_t>(segs[si].y_out);
+    }
     for (int si = 0; si < n_segs; ++si) {
       int t0 = 0;
       for (int sj = 0; sj < si; ++sj) t0 += __ldg(&segs[sj].n_terms);
@@ -319,7 +354,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
         sterm[(t0 + t) * TW + k] = val;
       }
     }
-    if (bulk_bytes) mbar_wait(&bar[B_STAGE], 0);
+    if (bulk_bytes) pinn::mbar_wait(&bar[B_STAGE], 0);
     __syncthreads();
     // K-major operand images of the 32 x 32 matrices (rows n, contraction index k: umma::tile_offset, SBO = 1024):
     //   forward  D[p][j] = sum_k a[p][k] K_l[k][j]:  B[n = j][k]      = K_l[k][j]
@@ -357,6 +392,8 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
   }
   const uint32_t tmem = *tslot;
   const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
+  const uint32_t bar_base = smem_base + Cfg::OFF_BAR;
+  auto BAR = [&](int i) -> uint32_t { return bar_base + 8u * (uint32_t)i; };
 
   if (warp >= Cfg::NEPI) {
     reg_dec<Cfg::AUX_REGS>();
@@ -374,11 +411,11 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
         const uint64_t wl = umma::smem_desc(smem_base + Cfg::OFF_W + image * 8192 + 4096, 128, 1024);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {            // k-step g contracts over neuron octet g; octets 0, 1 are ready first
-          mbar_wait(&bar[B_AREADY + g], (ph_a >> g) & 1u);
+          mbar_wait(BAR(B_AREADY + g), (ph_a >> g) & 1u);
           ph_a ^= 1u << g;
           if (g == 0) {
             if (!first_gemm) {                   // every epilogue warp has read the previous accumulators out of tensor memory
-              mbar_wait(&bar[B_DLOADED], ph_dl);
+              mbar_wait(BAR(B_DLOADED), ph_dl);
               ph_dl ^= 1u;
             }
             first_gemm = false;
@@ -397,13 +434,13 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
           }
           __syncwarp();
         }
-        if (leader) umma::commit(&bar[B_DFULL]);
+        if (leader) mma_commit(BAR(B_DFULL));
         __syncwarp();
         TC_PROF(5);
       };
       // weight gradient of one layer: D_w[(k-octet, part, k % 8)][j] = sum_rows a[row][k] z[row][j]
       auto wgrad = [&](int a_off, int z_off) {
-        mbar_wait(&bar[B_IMG], ph_img);
+        mbar_wait(BAR(B_IMG), ph_img);
         ph_img ^= 1u;
         umma::fence_after_thread_sync();
         TC_PROF(6);
@@ -413,10 +450,15 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
           const uint64_t z2 = umma::smem_desc(smem_base + z_off + 128, 1024, 256);    //         the b2 blocks
 #pragma unroll 4
           for (int ks = 0; ks < C * Cfg::TP / 16; ++ks) {
+#ifdef PINN_TC_NO_COLLECTOR
             mma_bf16_ss(tmem + Cfg::COL_W, ad + (uint64_t)(ks * 128), z1 + (uint64_t)(ks * 128), idesc_w, ks > 0 ? 1u : 0u);
             mma_bf16_ss(tmem + Cfg::COL_W, ad + (uint64_t)(ks * 128), z2 + (uint64_t)(ks * 128), idesc_w, 1u);
+#else
+            mma_bf16_ss_keep_a(tmem + Cfg::COL_W, ad + (uint64_t)(ks * 128), z1 + (uint64_t)(ks * 128), idesc_w, ks > 0 ? 1u : 0u);
+            mma_bf16_ss_reuse_a(tmem + Cfg::COL_W, ad + (uint64_t)(ks * 128), z2 + (uint64_t)(ks * 128), idesc_w, 1u);
+#endif
           }
-          umma::commit(&bar[B_WDONE]);
+          mma_commit(BAR(B_WDONE));
         }
         __syncwarp();
         TC_PROF(7);
@@ -450,7 +492,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
 
     // accumulator of the finished weight-gradient batch -> FP32 totals of layer index li (0: K_2, 1: K_3)
     auto drain_w = [&](int li) {
-      mbar_wait(&bar[B_WDONE], ph_wd);
+      mbar_wait(BAR(B_WDONE), ph_wd);
       ph_wd ^= 1u;
       umma::fence_after_thread_sync();
       if (h == 0) {
@@ -475,42 +517,33 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
       tmem_wait_st();
       umma::fence_before_thread_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar[B_AREADY + g]);
+      if (lane == 0) mbar_arrive(BAR(B_AREADY + g));
     };
     auto arrive_dloaded = [&]() {
       umma::fence_before_thread_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar[B_DLOADED]);
+      if (lane == 0) mbar_arrive(BAR(B_DLOADED));
     };
 
     // tile state, prepared one tile ahead (the point coordinates are a global load)
     int si = 0;
-    long long pg = 0, pi = 0, n = 0;
+    long long pg = 0, pi = 0;
     bool valid = false;
     float x[D];
-    const SegDev* __restrict__ seg = segs;
-    auto prepare = [&](int tile) {
-      while (si + 1 < n_segs && tile >= __ldg(&segs[si + 1].chunk_begin)) ++si;
-      seg = segs + si;
-      n = seg->n;
-      pg = (long long)(tile - seg->chunk_begin) * Cfg::TP + p;
+    auto prepare = [&](int tile) {             // segment table in shared memory; only the coordinates are a global load
+      while (si + 1 < n_segs && tile >= (int)(unsigned)sseg[4 * (si + 1)]) ++si;
+      const long long n = sseg[4 * si + 1];
+      pg = (long long)(tile - (int)(unsigned)sseg[4 * si]) * Cfg::TP + p;
       valid = pg < n;
       pi = valid ? pg : n - 1;
+      const float* pts = reinterpret_cast<const float*>((uintptr_t)sseg[4 * si + 2]);
 #pragma unroll
-      for (int i = 0; i < D; ++i) x[i] = __ldg(seg->pts + pi * D + i);
+      for (int i = 0; i < D; ++i) x[i] = __ldg(pts + pi * D + i);
     };
-    if ((int)blockIdx.x < total_tiles) prepare(blockIdx.x);
-
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const SegDev* __restrict__ seg_c = seg;
-      const long long pg_c = pg, pi_c = pi;
-      const bool valid_c = valid;
-      const int term0 = segt[si];
-      float xc[D];
-#pragma unroll
-      for (int i = 0; i < D; ++i) xc[i] = x[i];
-
-      // ---- layer 1: z = x K1 + b1, a = tanh z; jets straight into the operand of the layer-2 GEMM ------------------
+    // layer 1 of the prepared tile: z = x K1 + b1, a = tanh z; jets straight into the operand of the layer-2 GEMM.
+    // Runs one phase EARLY (before the layer-1 backward math of the previous tile), so that GEMM is done when its
+    // epilogue starts.
+    auto layer1 = [&]() {
 #pragma unroll
       for (int hs = 0; hs < 2; ++hs) {
         const int g = 2 * hs + u, j0 = 8 * g + 4 * v4;
@@ -523,7 +556,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
 #pragma unroll
           for (int i = 0; i < D; ++i) {
             zd[i] = *reinterpret_cast<const float2*>(sK1 + i * H + j);
-            z = fma2(bc2(xc[i]), zd[i], z);
+            z = fma2(bc2(x[i]), zd[i], z);
           }
           const float2 a0 = tanh2(z);
           if constexpr (TRAIN) {
@@ -537,11 +570,42 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
         emit_operand<C, true>(v, tm_lane + Cfg::COL_A + 8u * g + 4u * v4);
         arrive_group(g);
       }
+    };
+    if ((int)blockIdx.x < total_tiles) {
+      prepare(blockIdx.x);
+      layer1();
+    }
+    float sqacc[4] = {0.f, 0.f, 0.f, 0.f};     // sum r^2 of the first 4 terms of the current segment: this thread's points
+    int sq_si = si;
+    auto flush_sq = [&]() {                    // (warps 0..3) registers -> per-warp slots, when the segment changes
+      if (h == 0) {
+        const int nt = (int)(sseg[4 * sq_si] >> 32);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float tsum = reduce_warp(sqacc[t]);
+          if (lane == 0 && t < nt) ssq[__float_as_int(sterm[(segt[sq_si] + t) * TW + Cfg::T_OUT])] += tsum;
+          sqacc[t] = 0.f;
+        }
+      }
+    };
+
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int si_c = si;
+      const long long pg_c = pg, pi_c = pi;
+      const bool valid_c = valid;
+      const int term0 = segt[si];
+      float xc[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) xc[i] = x[i];
+      if (si != sq_si) {
+        flush_sq();
+        sq_si = si;
+      }
       TC_PROF(0);
 
       // ---- layer 2: accumulators -> tanh jets -> operand of the layer-3 GEMM (+ images of a_2 for the reverse sweep) ---
       {
-        mbar_wait(&bar[B_DFULL], ph_df);
+        mbar_wait(BAR(B_DFULL), ph_df);
         ph_df ^= 1u;
         umma::fence_after_thread_sync();
         TC_PROF(1);
@@ -588,7 +652,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
       float a3[C][8];                          // a-jets of layer 3 of this thread's 8 neurons
       float J[C][O];
       {
-        mbar_wait(&bar[B_DFULL], ph_df);
+        mbar_wait(BAR(B_DFULL), ph_df);
         ph_df ^= 1u;
         umma::fence_after_thread_sync();
         TC_PROF(4);
@@ -655,8 +719,8 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
         named_bar_sync(1 + q, 128);             // everybody has read: the columns may take operand data again
         umma::fence_after_thread_sync();
       }
-      if (seg_c->y_out != nullptr && h == 0 && valid_c) {
-        float* y = seg_c->y_out;
+      if (h == 0 && valid_c && sseg[4 * si_c + 3] != 0) {
+        float* y = reinterpret_cast<float*>((uintptr_t)sseg[4 * si_c + 3]);
 #pragma unroll
         for (int o = 0; o < O; ++o) y[pg_c * O + o] = J[0][o];
       }
@@ -668,7 +732,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
       for (int c = 0; c < C; ++c)
 #pragma unroll
         for (int o = 0; o < O; ++o) Jb[c][o] = 0.f;
-      const int n_terms = seg_c->n_terms;
+      const int n_terms = (int)(sseg[4 * si_c] >> 32);
 #pragma unroll 1
       for (int t = 0; t < n_terms; ++t) {
         const float* T = sterm + (term0 + t) * TW;
@@ -692,9 +756,16 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
         if (rhs != nullptr) r = fmaf(-T[Cfg::T_RHS_SCALE], __ldg(rhs + pi_c), r);
         r = valid_c ? r : 0.f;
         if (h == 0) {                          // one of the four threads of a point adds the residual up
-          float sq = abs_mean ? r : r * r;
-          sq = reduce_warp(sq);
-          if (lane == 0) ssq[__float_as_int(T[Cfg::T_OUT])] += sq;
+          const float sq = abs_mean ? r : r * r;
+          if (t < 4) {
+            sqacc[0] += t == 0 ? sq : 0.f;
+            sqacc[1] += t == 1 ? sq : 0.f;
+            sqacc[2] += t == 2 ? sq : 0.f;
+            sqacc[3] += t == 3 ? sq : 0.f;
+          } else {
+            const float tsum = reduce_warp(sq);
+            if (lane == 0) ssq[__float_as_int(T[Cfg::T_OUT])] += tsum;
+          }
         }
         if constexpr (TRAIN) {
           float rb = T[Cfg::T_SCALE] * r;
@@ -781,7 +852,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
           }
           umma::fence_proxy_async_smem();      // images X (a_2) and Y (z-bar_3) -> visible to the weight-gradient MMAs
           __syncwarp();
-          if (lane == 0) mbar_arrive(&bar[B_IMG]);
+          if (lane == 0) mbar_arrive(BAR(B_IMG));
           // K_out gradient of this warp's 8 neurons: sums over its 32 points
           xreduce8<3>(gko, lane);
           if ((lane & 3) == 0) {
@@ -793,7 +864,15 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
 
         // ---- layer 2 backward: a-bar_2 (accumulators) + a_2 (image X) -> z-bar_2 ------------------------------------
         {
-          mbar_wait(&bar[B_DFULL], ph_df);
+          uint2 q1[2][C], q2[2][C];            // a_2 of this thread's 8 neurons (its own image entries): loaded ahead of the wait
+#pragma unroll
+          for (int hs = 0; hs < 2; ++hs)
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              q1[hs][c] = *reinterpret_cast<const uint2*>(imgX + img_thr + (2 * hs + u) * 256 + c * 16384);
+              q2[hs][c] = *reinterpret_cast<const uint2*>(imgX + img_thr + (2 * hs + u) * 256 + c * 16384 + 128);
+            }
+          mbar_wait(BAR(B_DFULL), ph_df);
           ph_df ^= 1u;
           umma::fence_after_thread_sync();
           TC_PROF(8);
@@ -804,12 +883,6 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
             float d[C][4];
             tmem_ld4x5(tm_lane + Cfg::COL_D + 8u * g + 4u * v4, d);
             if (hs == 1) arrive_dloaded();
-            uint2 q1[C], q2[C];
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-              q1[c] = *reinterpret_cast<const uint2*>(imgX + img_thr + g * 256 + c * 16384);
-              q2[c] = *reinterpret_cast<const uint2*>(imgX + img_thr + g * 256 + c * 16384 + 128);
-            }
             float2 v[C][2];
 #pragma unroll
             for (int pr = 0; pr < 2; ++pr) {
@@ -818,7 +891,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
               for (int i = 0; i < D; ++i) zdummy[i] = bc2(0.f);
 #pragma unroll
               for (int c = 0; c < C; ++c) {
-                aj[c] = bf16_unpair(pr == 0 ? q1[c].x : q1[c].y, pr == 0 ? q2[c].x : q2[c].y);
+                aj[c] = bf16_unpair(pr == 0 ? q1[hs][c].x : q1[hs][c].y, pr == 0 ? q2[hs][c].x : q2[hs][c].y);
                 ab[c] = make_float2(d[c][2 * pr], d[c][2 * pr + 1]);
               }
               tanh_jet2_bwd<Cfg, false>(aj, zdummy, ab, zb);
@@ -857,39 +930,52 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
           }
           umma::fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&bar[B_IMG]);
+          if (lane == 0) mbar_arrive(BAR(B_IMG));
           w_pending = true;
         }
         TC_PROF(11);
       }
 
-      // the next tile's segment and point coordinates: the global loads fly during the last phase of this tile
-      if (tile + (int)gridDim.x < total_tiles) prepare(tile + gridDim.x);
+      // the next tile's segment and point coordinates (global loads), then its layer 1 as soon as the operand columns of
+      // tensor memory are free again
+      const bool more = tile + (int)gridDim.x < total_tiles;
+      if (more) prepare(tile + gridDim.x);
 
       if constexpr (TRAIN) {
         // ---- layer 1 backward: a-bar_1 (accumulators) + tanh(z1) -> K1 / b1 gradients --------------------------------
-        mbar_wait(&bar[B_DFULL], ph_df);
+        float2 a1v[4];                         // tanh(z1) of this thread's 8 neurons: read before the next tile's layer 1 overwrites it
+#pragma unroll
+        for (int hs = 0; hs < 2; ++hs)
+#pragma unroll
+          for (int pr = 0; pr < 2; ++pr) {
+            const int j = 8 * (2 * hs + u) + 4 * v4 + 2 * pr;
+            a1v[2 * hs + pr] = make_float2(a1buf[j * Cfg::TP + p], a1buf[(j + 1) * Cfg::TP + p]);
+          }
+        mbar_wait(BAR(B_DFULL), ph_df);
         ph_df ^= 1u;
         umma::fence_after_thread_sync();
         TC_PROF(12);
+        float d[2][C][4];
+        tmem_ld4x5(tm_lane + Cfg::COL_D + 8u * u + 4u * v4, d[0]);
+        tmem_ld4x5(tm_lane + Cfg::COL_D + 8u * (2 + u) + 4u * v4, d[1]);
+        arrive_dloaded();
+        if (more) layer1();                    // the adjoint GEMM has released the operand columns: next tile's layer 1 -> its GEMM runs during the math below
+        TC_PROF(13);
         float gk[8 * (D + 1)];
 #pragma unroll
         for (int hs = 0; hs < 2; ++hs) {
           const int g = 2 * hs + u, j0 = 8 * g + 4 * v4;
-          float d[C][4];
-          tmem_ld4x5(tm_lane + Cfg::COL_D + 8u * g + 4u * v4, d);
-          if (hs == 1) arrive_dloaded();
 #pragma unroll
           for (int pr = 0; pr < 2; ++pr) {
             const int j = j0 + 2 * pr, n8 = 4 * hs + 2 * pr;
             float2 aj[C], ab[C], zb[C], zd[D];
-            aj[0] = make_float2(a1buf[j * Cfg::TP + p], a1buf[(j + 1) * Cfg::TP + p]);
+            aj[0] = a1v[2 * hs + pr];
 #pragma unroll
             for (int c = 1; c < C; ++c) aj[c] = bc2(0.f);
 #pragma unroll
             for (int i = 0; i < D; ++i) zd[i] = *reinterpret_cast<const float2*>(sK1 + i * H + j);
 #pragma unroll
-            for (int c = 0; c < C; ++c) ab[c] = make_float2(d[c][2 * pr], d[c][2 * pr + 1]);
+            for (int c = 0; c < C; ++c) ab[c] = make_float2(d[hs][c][2 * pr], d[hs][c][2 * pr + 1]);
             tanh_jet2_bwd<Cfg, true>(aj, zd, ab, zb);
 #pragma unroll
             for (int i = 0; i < D; ++i) {
@@ -906,11 +992,13 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
           for (int i = 0; i < D; ++i) sg[Cfg::SG_K1 + i * 8 + (lane >> 2)] += gk[i];
           sg[Cfg::SG_B1 + (lane >> 2)] += gk[D];
         }
-        TC_PROF(13);
+        TC_PROF(14);
       } else {
         (void)a3;
+        if (more) layer1();
       }
     }
+    flush_sq();
     if constexpr (TRAIN) {
       if (w_pending) drain_w(0);
       xreduce8<1>(gb2acc, lane);

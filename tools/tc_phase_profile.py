@@ -30,15 +30,12 @@ tiles = (n + 127) // 128 + 4 * 8 + 2
 per_cta = tiles / 148.0
 epi = buf[:148, :16, :].astype(np.float64).mean(axis=(0, 1)) / per_cta
 mma = buf[:148, 16, :].astype(np.float64).mean(axis=0) / per_cta
-names = ["layer 1 (F1)", "wait G2", "E2: load D", "E2: wait/drain W2", "wait G3", "E3: jets + exchange", "residuals", "E3: adjoint + z3",
-         "wait GB3", "EB2: adjoint", "EB2: wait/drain W3", "EB2: images + a1 remat", "wait GB2", "EB1"]
 print(f"fused_tc_kernel, {n} points, cycles per tile (mean over CTAs and epilogue warps), engine {pb.plan.engine}")
-# slot 2 is hit twice (E2 load D, and the E2 body up to the E3 wait): reported as recorded
-labels = {0: "F1 (layer 1)", 1: "wait d_full(G2)", 2: "E2 load D + E2 body (two marks)", 3: "E2 wait/drain W2", 4: "wait d_full(G3)",
-          5: "E3 jets + exchange", 6: "residuals", 7: "E3 adjoint, z-bar_3, images", 8: "wait d_full(GB3)", 9: "EB2 adjoint",
-          10: "EB2 wait/drain W3", 11: "EB2 images + a_1 jets", 12: "wait d_full(GB2)", 13: "EB1"}
+labels = {0: "tile bookkeeping", 1: "wait d_full(G2)", 2: "E2 (layer-2 jets, operand, images)", 3: "E2 wait/drain W2", 4: "wait d_full(G3)",
+          5: "E3 jets + output-jet exchange", 6: "residuals", 7: "E3 adjoint, z-bar_3, images", 8: "wait d_full(GB3)", 9: "EB2 adjoint",
+          10: "EB2 wait/drain W3", 11: "EB2 images + a_1 jets", 12: "wait d_full(GB2)", 13: "load a-bar_1 + layer 1 of next tile", 14: "EB1 math"}
 tot = 0.0
-for k in range(14):
+for k in range(15):
     print(f"  epilogue {labels[k]:34s} {epi[k]:8.0f}")
     tot += epi[k]
 print(f"  epilogue total per tile              {tot:8.0f}")

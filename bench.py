@@ -12,12 +12,14 @@ Printed keys (one JSON line on rank 0):
   value      whole-job pts/s with inputs resident in HBM (device-timed per step, L2 flushed between steps)
   e2e        the same through the public facade with HOST inputs: every step copies all point / target
              arrays from pinned host memory, runs the step, and reads the per-term sums back
-  roofline   the collocation kernel(s) against the pipe that bounds them: fused_step_kernel<...,ORDER=2,TRAIN>
-             against the MEASURED FP32 FFMA peak of this pool's B200 (profiles/fp32_peak_r01.json), the
-             tensor-core engine of the 8x128 network against the MEASURED tcgen05 kind::tf32 rate / 3 passes
-             (profiles/tf32_peak_r01.json); MEASURED_PEAKS.json holds neither figure
-  cpu_baseline   oracle/reference_step.py (torch float64 nested autodiff, the reference's step
-             structure) timed on this box's host cores on a bounded sample
+  roofline   the collocation kernel against the tensor roofline of its precision mode (3xTF32: the MEASURED tcgen05 kind::tf32
+             rate / 3, profiles/tf32_peak_r01.json -- MEASURED_PEAKS.json holds no TF32 figure), and, in `two_pipe`, against the
+             floors of BOTH pipes it needs: the tensor pipe (MMAs issued x measured cycles per MMA) and the FMA / issue pipes
+             (FP32-pipe and total warp instructions per point of the shipped kernel, ncu capture named in `source`)
+  cpu_baseline   oracle/reference_step.py (torch float64 nested autodiff, the reference's step structure) timed on this
+             box's host cores on the SAME workload when ~25 s of CPU time allow it, else on the largest sample that fits
+  other_configs  device-timed step of the four other BASELINE.json configs (N = 1: their own sizes; N > 1: sharded)
+  strong_scaling (N > 1) the 1 000 000-point Cavity_Steady workload sharded over the N GPUs
 `--impl reference` times that CPU restatement alone (the real nisaba/TensorFlow stack cannot be
 installed: see DESIGN.md) on the same config/metric/unit.
 """
@@ -34,7 +36,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-CPU_SAMPLE_PDE = 20_000
+CPU_SAMPLE_PDE = 20_000          # timing probe of the CPU arm; the sample grows from here up to the full workload
 
 
 def flops_per_point(d, H, L, O, C):
@@ -93,21 +95,17 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-def cpu_reference_step_rate(config: str, steps: int, warmup: int, sample_pde: int = CPU_SAMPLE_PDE):
-    """Time oracle/reference_step.py (the reference's step structure, torch float64, all host
-    threads) on a bounded sample of the workload.  Returns (pts/s, ms/step, cores, sample text)."""
-    import numpy as np
+def _cpu_step_fn(config: str, n_pde: int):
+    """(one_step(t), variables) of oracle/reference_step.py on `n_pde` collocation points + every boundary / fit set."""
     import torch
     from oracle import reference_step
     from pinns_fluid_dynamics_b200 import problems
 
-    torch.set_num_threads(os.cpu_count() or 1)
-    data = problems.build_baseline_config(config, seed=1, PDE=sample_pde)
+    data = problems.build_baseline_config(config, seed=1, PDE=n_pde)
     var = reference_step.glorot_uniform_variables(data.dim, data.hidden, data.out_dim, seed=3)
     pb = reference_step.build(data, var)
-    theta = [v.detach().clone() for v in pb.variables]
-    m = [torch.zeros_like(v) for v in theta]
-    v2 = [torch.zeros_like(v) for v in theta]
+    m = [torch.zeros_like(v) for v in pb.variables]
+    v2 = [torch.zeros_like(v) for v in pb.variables]
 
     def one_step(t):
         _, _, grad = pb.loss_and_grad()
@@ -119,29 +117,73 @@ def cpu_reference_step_rate(config: str, steps: int, warmup: int, sample_pde: in
                 v2[i].mul_(0.999).addcmul_(g, g, value=0.001)
                 step = 1e-2 * (1 - 0.999 ** t) ** 0.5 / (1 - 0.9 ** t)
                 p.addcdiv_(m[i], v2[i].sqrt().add_(1e-7), value=-step)
+    return one_step
 
+
+def cpu_reference_step_rate(config: str, steps: int, warmup: int, budget_s: float, full_pde: int):
+    """Time oracle/reference_step.py (the reference's step structure, torch float64, all host threads).  The sample is the
+    FULL workload (`full_pde` collocation points) when (steps + warmup) steps of it fit `budget_s` seconds of CPU time and
+    host memory, else the largest power-of-two fraction that does; a 20 000-point probe sets the scale.
+    Returns (pts/s, ms/step, cores, sample text, sample points)."""
+    import torch
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    probe_n = min(CPU_SAMPLE_PDE, full_pde)
+    step = _cpu_step_fn(config, probe_n)
+    step(1)
+    t0 = time.perf_counter()
+    step(2)
+    t_probe = time.perf_counter() - t0
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 32 << 30
+    n = full_pde
+    # measured on this image: the step is ~3x slower per point once the tape leaves the caches (200 k points), 40 KB of tape per point
+    while n > probe_n and ((steps + warmup) * t_probe * (n / probe_n) * 3.0 > budget_s or n * 40_000 > 0.5 * avail):
+        n //= 2
+    n = max(n, probe_n)
+    if n != probe_n:
+        step = _cpu_step_fn(config, n)
     for i in range(warmup):
-        one_step(i + 1)
+        step(i + 1)
     t0 = time.perf_counter()
     for i in range(steps):
-        one_step(warmup + i + 1)
+        step(warmup + i + 1)
     dt = time.perf_counter() - t0
-    sample = (f"{config}: {sample_pde} of the collocation points + all boundary/fit sets, "
-              f"{steps} steps after {warmup} warm-up, torch {torch.__version__} float64")
-    return sample_pde * steps / dt, dt / steps * 1e3, torch.get_num_threads(), sample
+    what = "the full workload" if n == full_pde else f"{n} of the {full_pde} collocation points"
+    sample = (f"{config}: {what} + all boundary/fit sets, {steps} steps after {warmup} warm-up, "
+              f"torch {torch.__version__} float64, {torch.get_num_threads()} threads")
+    return n * steps / dt, dt / steps * 1e3, torch.get_num_threads(), sample, n
+
+
+def workload_text(config, per_gpu, n_global, data, d, H, L, O, n_params, n_terms):
+    return (f"{config}: {per_gpu} uniform collocation points per GPU ({n_global} total), "
+            f"{data.options.n_pts['BC']}x4 boundary, {data.options.n_pts['Vel']} velocity + "
+            f"{data.options.n_pts['Pres']} pressure fitting points, tanh MLP "
+            f"{d}-{H}x{L}-{O} ({n_params} parameters), {n_terms} loss terms")
 
 
 def run_reference(args):
+    """The reference arm: the CPU restatement of the nisaba / TensorFlow step on this box's host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    value, ms, cores, sample = cpu_reference_step_rate(args.config, args.steps, max(args.warmup, 1))
+    from pinns_fluid_dynamics_b200 import loss_tables, problems
+    full = args.pde_per_gpu or problems.BASELINE_CONFIGS[args.config].get("PDE", 200)
+    warm = max(args.warmup, 1)
+    value, ms, cores, sample, n = cpu_reference_step_rate(args.config, args.steps, warm, budget_s=150.0, full_pde=full)
+    data = problems.build_baseline_config(args.config, seed=1, PDE=1000)
+    losses, _ = loss_tables.build_loss_table(data, faithful=data.name.startswith("cavity"))
+    L = len(data.hidden)
+    n_params = data.dim * data.hidden[0] + data.hidden[0] + (L - 1) * (data.hidden[0] ** 2 + data.hidden[0]) + data.hidden[0] * data.out_dim + data.out_dim
     line = {
         "impl": "reference", "metric": "collocation_points_per_second_per_training_step", "value": value,
-        "unit": "pts/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms,
+        "unit": "pts/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": warm, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.config}: bounded CPU sample of {CPU_SAMPLE_PDE} collocation points per step "
-                               "+ the script's boundary/fit sets, tanh MLP of the config"},
+        "config": {"workload": workload_text(args.config, full, full, data, data.dim, data.hidden[0], L, data.out_dim, n_params, len(losses)),
+                   "cpu_sample_points_per_step": n, "full_workload": n == full},
         "cpu_baseline": {"value": value, "unit": "pts/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "pts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -251,6 +293,43 @@ def run_ours(args):
                 traffic = json.load(fh)["dram_bytes_per_point"] * n_local_pde
         except Exception:
             pass
+    elif plan.engine == "fused_tcgen05":
+        # hidden-layer forward / adjoint GEMMs on tcgen05 kind::tf32 (3 passes per product, operands in tensor memory), weight
+        # gradient as bf16-pair kind::f16 MMAs; `peak` is the chip's 3xTF32 tensor roofline.  The kernel also needs the FMA /
+        # ALU pipes for the tanh-jet math and the operand splits: `two_pipe` holds the floors of both.
+        bound, peak, peak_src = "tensor", 368.4, "fallback"
+        kernel_name = ("fused_tc_kernel<D=2,O=3,TRAIN> (tcgen05.mma kind::tf32 3-pass forward / adjoint GEMMs with TMEM operands and "
+                       "accumulators, kind::f16 bf16-pair MN-major weight-gradient MMAs, FFMA2 tanh-jet epilogue warps)")
+        try:
+            with open(os.path.join(ROOT, "profiles", "tf32_peak_r01.json")) as fh:
+                pk = json.load(fh)
+            peak = pk["tf32_mma_tflops_n256"] / pk["passes_per_product"]
+            peak_src = ("profiles/tf32_peak_r01.json: measured tcgen05 kind::tf32 MMA rate (tools/tc_probe.cu) / 3 passes; "
+                        "MEASURED_PEAKS.json holds no TF32 figure")
+        except Exception:
+            pass
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_fused_tcgen05_r02.json")) as fh:
+                nk = json.load(fh)
+            traffic = nk["dram_bytes_per_point"] * n_local_pde
+            clk = (sampler.summary()["sm_mhz"] or 1965) * 1e6
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            tiles_sm = -(-(-(-n_local_pde // 128)) // sms)             # 128-point tiles of the busiest SM
+            pts_sm = tiles_sm * 128
+            t_tensor = tiles_sm * (nk["mma_tf32_per_tile"] * nk["cycles_per_mma_tf32"] + nk["mma_bf16_per_tile"] * nk["cycles_per_mma_bf16"]) / clk
+            t_fma = pts_sm * nk["fma_pipe_warp_inst_per_point"] / 4.0 / clk
+            t_issue = pts_sm * nk["warp_inst_per_point"] / 4.0 / clk
+            extra = {"two_pipe": {"tensor_floor_ms": t_tensor * 1e3, "fma_floor_ms": t_fma * 1e3, "issue_floor_ms": t_issue * 1e3,
+                                  "frac_of_floor": max(t_tensor, t_fma, t_issue) * 1e3 / k_ms,
+                                  "tensor_pipe_active_pct_ncu": nk.get("tensor_pipe_active_pct"),
+                                  "fma_pipe_active_pct_ncu": nk.get("fma_pipe_active_pct"),
+                                  "issue_active_pct_ncu": nk.get("issue_active_pct"),
+                                  "source": nk.get("source"),
+                                  "note": "floors = work the shipped kernel issues on each pipe / that pipe's rate at the sampled SM clock: "
+                                          "MMAs x measured cycles per MMA (profiles/tc_probes_r02.md); FMA-pipe and all warp instructions "
+                                          "per point (ncu) at 1 per scheduler and cycle"}}
+        except Exception:
+            pass
     elif plan.engine == "fused_tf32x3":
         # hidden-layer GEMMs (97 % of the algorithmic flops) on the warp-level tensor path, 3 mma.sync passes per product;
         # `peak` is the chip's tensor roofline for 3xTF32 (tcgen05 rate / 3); the path the kernel actually uses
@@ -325,21 +404,65 @@ def run_ours(args):
     e2e_value = n_global_pde * args.steps / (ms_e2e * 1e-3)
     sampler.stop()
 
+    # ---- the other BASELINE.json configs and strong scaling: device-timed steps, a few iterations each -----------------
+    def time_config(config, total_pde, steps, warm):
+        dat = problems.build_baseline_config(config, seed=1, PDE=total_pde) if total_pde else problems.build_baseline_config(config, seed=1)
+        mdl = ns.TanhMLP(dat.dim, dat.hidden, dat.out_dim, device=dev, seed=3)
+        ls, lt = loss_tables.build_loss_table(dat, faithful=dat.name.startswith("cavity"))
+        pbx = ns.OptimizationProblem(mdl.variables, ls, lt)
+        optx = ns.Adam(learning_rate=1e-2)
+        for _ in range(warm):
+            pbx.training_step(optx)
+        extra_w = 0
+        while getattr(pbx, "_graph", None) is None and pbx._graph_eligible(optx) and extra_w < 8:
+            pbx.training_step(optx)
+            extra_w += 1
+        barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in evs:
+            flush.fill_(1.0)
+            a.record()
+            pbx.training_step(optx)
+            b.record()
+        barrier()
+        tt = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        n_pde = sum(cs.pointset.n for cs in pbx.compiled.sets if cs.pointset.name.upper() == "PDE") or 1
+        ms = float(tt.item()) / steps
+        res = {"config": config, "engine": pbx.plan.engine, "collocation_points_total": int(n_pde), "ms_per_step": ms,
+               "value": n_pde / (ms * 1e-3), "unit": "pts/s", "mlp": "-".join(str(v) for v in (dat.dim, f"{dat.hidden[0]}x{len(dat.hidden)}", dat.out_dim))}
+        del pbx, mdl
+        torch.cuda.empty_cache()
+        return res
+
+    others, strong = [], None
+    if not args.no_other_configs:
+        for cfg_name in ("Poisson_Problem", "Poiseuille_Flow", "Colliding_Flow", "Cavity_Steady", "Cavity_Unsteady"):
+            if cfg_name == args.config:
+                continue
+            base = problems.BASELINE_CONFIGS[cfg_name].get("PDE", 0)
+            try:
+                others.append(time_config(cfg_name, base, steps=20 if cfg_name != "Cavity_Unsteady" else 3, warm=5 if cfg_name != "Cavity_Unsteady" else 2))
+            except Exception as exc:          # a config that cannot run here is reported, not hidden
+                others.append({"config": cfg_name, "error": repr(exc)[:200]})
+        if world > 1:
+            strong = time_config(args.config, per_gpu, steps=20, warm=5)      # the N = 1 workload sharded over N GPUs
+            strong["note"] = f"strong scaling: {per_gpu} collocation points in total over {world} GPUs"
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, ms, cores, sample = cpu_reference_step_rate(args.config, steps=5, warmup=2)
-        cpu = {"value": v, "unit": "pts/s", "cores": cores, "kind": "port", "sample": sample, "ms_per_step": ms}
+        v, ms, cores, sample, n_cpu = cpu_reference_step_rate(args.config, steps=3, warmup=1, budget_s=25.0, full_pde=per_gpu)
+        cpu = {"value": v, "unit": "pts/s", "cores": cores, "kind": "port", "sample": sample, "ms_per_step": ms,
+               "sample_points": n_cpu, "full_workload": n_cpu == per_gpu}
 
     if rank == 0:
         line = {
             "metric": "collocation_points_per_second_per_training_step", "value": value, "unit": "pts/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (3xtf32 tensor-core products, fp32 accumulate)" if plan.engine.endswith("tf32x3") else "f32", "data": "synthetic",
-            "config": {"workload": f"{args.config}: {per_gpu} uniform collocation points per GPU ({n_global_pde} total), "
-                                   f"{data.options.n_pts['BC']}x4 boundary, {data.options.n_pts['Vel']} velocity + "
-                                   f"{data.options.n_pts['Pres']} pressure fitting points, tanh MLP "
-                                   f"{d}-{H}x{L}-{O} ({pb.compiled.n_params} parameters), {len(losses)} loss terms",
+            "dtype": "f32 (3xtf32 tensor-core products, fp32 accumulate)" if plan.engine.endswith("tf32x3") or plan.engine == "fused_tcgen05" else "f32", "data": "synthetic",
+            "config": {"workload": workload_text(args.config, per_gpu, n_global_pde, data, d, H, L, O, pb.compiled.n_params, len(losses)),
                        "engine": plan.engine, "parallelism": f"dp{world} (points sharded, NCCL all-reduce of {pb.compiled.n_params + T} floats)",
                        "l2": "256 MiB device buffer rewritten between timed steps", "optimizer": "Adam(1e-2) update inside the step"},
             "e2e": {"value": e2e_value, "unit": "pts/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(T * 4),
@@ -353,6 +476,8 @@ def run_ours(args):
                          "peak_source": peak_src,
                          "hbm_GBps": (n_local_pde * 4 * d) / (k_ms * 1e-3) * 1e-9, **extra},
             "cpu_baseline": cpu,
+            "other_configs": others,
+            "strong_scaling": strong,
             "clocks": sampler.summary(),
         }
         print(json.dumps(line), flush=True)
@@ -361,6 +486,9 @@ def run_ours(args):
 
 
 def main():
+    if os.environ.get("PINN_BENCH_WATCHDOG"):      # development aid: python stacks of a hung rank after N seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["PINN_BENCH_WATCHDOG"]), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -369,6 +497,7 @@ def main():
     ap.add_argument("--config", default="Cavity_Steady")
     ap.add_argument("--pde-per-gpu", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

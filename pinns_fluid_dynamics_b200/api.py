@@ -16,6 +16,7 @@ test losses excluded from the total, rounds named ``keras_<Optimizer>`` / ``scip
 """
 from __future__ import annotations
 
+import ctypes as C
 import json
 import os
 import math
@@ -160,6 +161,11 @@ class Loss:
 # problem
 # ------------------------------------------------------------------------------------------------
 
+def out_of_env(name: str) -> bool:
+    """True when the environment switches feature ``name`` off (NAME=0)."""
+    return os.environ.get(name, "1") == "0"
+
+
 class OptimizationProblem:
     def __init__(self, variables, losses, losses_test=None, callbacks=None, *, engine_factory=None,
                  process_group=None):
@@ -181,6 +187,7 @@ class OptimizationProblem:
                                                          self.losses, self.losses_test, self.rank, self.world)
         self.plan = (engine_factory or CudaPlan)(self.compiled)
         self._graph, self._graph_opt, self._graph_sumsq, self._eager_steps = None, None, None, 0
+        self._comm, self._comm_tried = None, False
         self._h_theta = self._h_out = self._perm_np = None      # pinned staging of evaluate_host
         self.iteration = 0
         self.history = {
@@ -208,9 +215,40 @@ class OptimizationProblem:
 
     # ---- evaluation ---------------------------------------------------------------------------
     def _reduce(self, out: torch.Tensor) -> torch.Tensor:
+        """SUM of the [P+T] vector over the ranks: the only cross-GPU dependency of a step.  On CUDA it goes through the
+        library's own NCCL communicator (``pinn_allreduce_sum``: a plain ncclAllReduce on the current stream, which a CUDA
+        graph captures as one node); ``torch.distributed`` serves CPU / gloo groups and ``PINN_OWN_NCCL=0``."""
         if self._dist is not None and self.world > 1:
-            self._dist.all_reduce(out, op=self._dist.ReduceOp.SUM, group=self.group)
+            comm = self._own_comm() if out.is_cuda else None
+            if comm is not None:
+                stream = C.c_void_p(torch.cuda.current_stream(out.device).cuda_stream)
+                _capi.check(self.plan.lib.pinn_allreduce_sum(comm, C.c_void_p(out.data_ptr()), out.numel(), stream), "pinn_allreduce_sum")
+            else:
+                self._dist.all_reduce(out, op=self._dist.ReduceOp.SUM, group=self.group)
         return out
+
+    def _own_comm(self):
+        """NCCL communicator of the default group created through the C ABI (the 128-byte unique id travels over
+        torch.distributed once).  None when it cannot be used (sub-groups, non-CUDA plans, PINN_OWN_NCCL=0)."""
+        if self._comm_tried:
+            return self._comm
+        self._comm_tried = True
+        if (self.group is not None or not isinstance(self.plan, CudaPlan) or out_of_env("PINN_OWN_NCCL")):
+            return None
+        lib, dev = self.plan.lib, self.flat.device
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = (C.c_ubyte * 128)()
+            _capi.check(lib.pinn_nccl_unique_id(buf), "pinn_nccl_unique_id")
+            uid = torch.tensor(list(buf), dtype=torch.uint8)
+        uid = uid.to(dev)
+        self._dist.broadcast(uid, src=0)
+        raw = (C.c_ubyte * 128)(*uid.cpu().tolist())
+        comm = C.c_void_p()
+        _capi.check(lib.pinn_comm_create(raw, self.world, self.rank, dev.index if dev.index is not None else torch.cuda.current_device(),
+                                         C.byref(comm)), "pinn_comm_create")
+        self._comm = comm
+        return comm
 
     def loss_and_grad_device(self):
         """One training-step evaluation, everything left on the device:
@@ -222,9 +260,11 @@ class OptimizationProblem:
         """One full training step, asynchronous: loss step (+ all-reduce) + optimiser update.
         Returns the device vector of per-term sums of squares (table order).
 
-        On one GPU the step is the same launch sequence every time (fixed point sets, device-side Adam step
-        number), so after three eager steps it is captured once in a CUDA graph and replayed: the small configs
-        (Poiseuille 10 k, Colliding 100 k points) are launch-bound otherwise.  ``PINN_CUDA_GRAPH=0`` disables it."""
+        The step is the same launch sequence every time (fixed point sets, device-side Adam step number), so after three
+        eager steps it is captured once in a CUDA graph and replayed: the small configs (Poiseuille 10 k, Colliding 100 k
+        points) are launch-bound otherwise.  With several ranks the NCCL all-reduce of the [P+T] vector is captured with it
+        (every rank captures at the same step), which removes the eager launch gaps around the 9 KB collective.
+        ``PINN_CUDA_GRAPH=0`` disables the replay, ``PINN_CUDA_GRAPH_DIST=0`` only the multi-rank one."""
         if self._graph is not None and optimizer is self._graph_opt and not self.plan.timing_enabled:
             self._graph.replay()
             optimizer.t += 1
@@ -238,14 +278,16 @@ class OptimizationProblem:
         return sumsq
 
     def _graph_eligible(self, optimizer) -> bool:
-        return (self.flat.is_cuda and self.world == 1 and isinstance(optimizer, Adam) and isinstance(self.plan, CudaPlan)
+        return (self.flat.is_cuda and (self.world == 1 or os.environ.get("PINN_CUDA_GRAPH_DIST", "1") != "0")
+                and isinstance(optimizer, Adam) and isinstance(self.plan, CudaPlan)
                 and not self.plan.timing_enabled and os.environ.get("PINN_CUDA_GRAPH", "1") != "0"
                 and (self._graph_opt is None or self._graph_opt is optimizer))
 
     def _capture_step(self, optimizer):
         torch.cuda.synchronize(self.flat.device)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        # several ranks: torch's NCCL watchdog thread may touch the CUDA API while this thread captures
+        with torch.cuda.graph(g, capture_error_mode="thread_local" if self.world > 1 else "global"):
             grad, sumsq = self.loss_and_grad_device()
             optimizer.apply(self.flat, grad)
         optimizer.t -= 1                 # capture launches nothing: the step is taken by the replay below

@@ -55,7 +55,7 @@
 extern "C" {
 #endif
 
-#define PINN_VERSION 101 /* 0.1.1: pinn_term_desc.kind, pinn_adam_step_dev */
+#define PINN_VERSION 102 /* 0.1.2: pinn_bfgs_* (quasi-Newton algebra of the BFGS round); 0.1.1: pinn_term_desc.kind, pinn_adam_step_dev */
 
 #define PINN_MAX_OUT 4   /* network outputs (u, v, p) padded to 4 */
 #define PINN_MAX_CH 6    /* value, d/dt, d/dx, d/dy, d2/dx2, d2/dy2 */
@@ -173,6 +173,28 @@ int pinn_adam_step(float* params_dev, const float* grad_dev, float* m_dev, float
  * (pinn_loss_and_grad + this) can be captured once in a CUDA graph and replayed. */
 int pinn_adam_step_dev(float* params_dev, const float* grad_dev, float* m_dev, float* v_dev, int64_t count,
                        float lr, float beta1, float beta2, float eps, int64_t* step_dev, void* stream);
+
+/* BFGS round (ns.minimize(pb, 'scipy', 'BFGS', epochs), cavity_steady.py:247; nisaba hands it to scipy.optimize.minimize):
+ * the quasi-Newton algebra on the device.  State, all float64 device arrays of the caller: the iterate x [n], its gradient
+ * g [n], the direction p [n], trial point / gradient xt, gt [n], s, y, u [n], the dense inverse Hessian H [n x n] row-major,
+ * and scal [PINN_BFGS_SCALARS]: [0] phi(alpha), [1] phi'(alpha) = gt . p, [2] |gt|_inf, [3] y . s, [4] g . p of the new
+ * direction, [5] |p|_2.  Everything is enqueued on `stream`; the host reads back scal only. */
+#define PINN_BFGS_SCALARS 8
+int pinn_bfgs_identity(double* H_dev, int64_t n, void* stream);                       /* H = I (SciPy's start) */
+/* xt = x + alpha p, theta = float(xt): the parameters of the next loss step */
+int pinn_bfgs_trial(const double* x_dev, const double* p_dev, double alpha, double* xt_dev, float* theta_dev, int64_t n, void* stream);
+/* after pinn_loss_and_grad (+ the SUM over ranks) into out [n + n_terms]: gt = double(gradient), scal[0] = sum_t coef[t] *
+ * (kind[t] ? |out[n+t]| : out[n+t]) (the total loss: coef = weight / (normalization N_global), kind 1 = |mean| term),
+ * scal[1] = gt . p, scal[2] = |gt|_inf */
+int pinn_bfgs_eval(const float* out_dev, const double* coef_dev, const int32_t* kind_dev, int32_t n_terms, const double* p_dev,
+                   double* gt_dev, double* scal_dev, int64_t n, void* stream);
+/* p = -H g, scal[4] = g . p, scal[5] = |p|_2 */
+int pinn_bfgs_direction(const double* H_dev, const double* g_dev, double* p_dev, double* scal_dev, int64_t n, void* stream);
+/* accept the trial point: s = xt - x, y = gt - g, x = xt, g = gt, scal[3] = y . s; with update_h != 0 also
+ * H <- H - rho (s u^T + u s^T) + (rho^2 y.u + rho) s s^T, u = H y, rho = 1 / (y . s) (1000 if y . s == 0, like SciPy), and the next
+ * direction p = -H g with scal[4], scal[5] -- one pass over H for the update and the direction together */
+int pinn_bfgs_accept_update(double* H_dev, double* x_dev, double* g_dev, const double* xt_dev, const double* gt_dev, double* s_dev,
+                            double* y_dev, double* u_dev, double* p_dev, double* scal_dev, int32_t update_h, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -13,6 +13,7 @@
 
 #include "fused_fp32.cuh"
 #include "fused_tc.cuh"
+#include "bfgs.cuh"
 #include "layered_fp32.cuh"
 #include "layered_tc.cuh"
 
@@ -1000,6 +1001,55 @@ extern "C" int pinn_adam_step_dev(float* params_dev, const float* grad_dev, floa
     adam_dev_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(params_dev, grad_dev, m_dev, v_dev, count, lr, beta1, beta2,
                                                                      eps, step_dev);
   bump_step_kernel<<<1, 1, 0, st>>>(step_dev);
+  CUDA_TRY(cudaGetLastError());
+  return PINN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// BFGS round: quasi-Newton algebra on the device (csrc/bfgs.cuh).  All pointers are device pointers of the caller; everything
+// is enqueued on the caller's stream; `scal` is a device array of PINN_BFGS_SCALARS doubles the caller reads back.
+// ------------------------------------------------------------------------------------------------
+extern "C" int pinn_bfgs_identity(double* H, int64_t n, void* stream) {
+  if (!H || n <= 0) return fail(PINN_E_INVALID, "bad argument");
+  const int64_t total = n * n;
+  pinn::bfgs::bfgs_identity_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(H, n);
+  CUDA_TRY(cudaGetLastError());
+  return PINN_OK;
+}
+
+extern "C" int pinn_bfgs_trial(const double* x, const double* p, double alpha, double* xt, float* theta, int64_t n, void* stream) {
+  if (!x || !p || !xt || !theta || n <= 0) return fail(PINN_E_INVALID, "bad argument");
+  pinn::bfgs::bfgs_trial_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, p, alpha, xt, theta, n);
+  CUDA_TRY(cudaGetLastError());
+  return PINN_OK;
+}
+
+extern "C" int pinn_bfgs_eval(const float* out, const double* coef, const int32_t* kind, int32_t n_terms, const double* p, double* gt,
+                              double* scal, int64_t n, void* stream) {
+  if (!out || !p || !gt || !scal || n <= 0 || n_terms < 0 || (n_terms > 0 && (!coef || !kind))) return fail(PINN_E_INVALID, "bad argument");
+  pinn::bfgs::bfgs_eval_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(out, coef, kind, n_terms, p, gt, scal, n);
+  CUDA_TRY(cudaGetLastError());
+  return PINN_OK;
+}
+
+extern "C" int pinn_bfgs_direction(const double* H, const double* g, double* p, double* scal, int64_t n, void* stream) {
+  if (!H || !g || !p || !scal || n <= 0) return fail(PINN_E_INVALID, "bad argument");
+  pinn::bfgs::bfgs_matvec_kernel<<<(unsigned)((n + 7) / 8), 256, 0, (cudaStream_t)stream>>>(H, g, p, -1.0, n);
+  pinn::bfgs::bfgs_slope_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(g, p, scal, n);
+  CUDA_TRY(cudaGetLastError());
+  return PINN_OK;
+}
+
+extern "C" int pinn_bfgs_accept_update(double* H, double* x, double* g, const double* xt, const double* gt, double* s, double* y, double* u,
+                                       double* p, double* scal, int32_t update_h, int64_t n, void* stream) {
+  if (!H || !x || !g || !xt || !gt || !s || !y || !u || !p || !scal || n <= 0) return fail(PINN_E_INVALID, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  pinn::bfgs::bfgs_accept_kernel<<<1, 1024, 0, st>>>(x, g, xt, gt, s, y, scal, n);
+  if (update_h) {
+    pinn::bfgs::bfgs_matvec_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(H, y, u, 1.0, n);
+    pinn::bfgs::bfgs_update_direction_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(H, s, y, u, g, p, scal, n);
+    pinn::bfgs::bfgs_slope_kernel<<<1, 1024, 0, st>>>(g, p, scal, n);
+  }
   CUDA_TRY(cudaGetLastError());
   return PINN_OK;
 }

@@ -212,3 +212,140 @@ def load_keras_dense_weights(path: str) -> List[np.ndarray]:
     for name in sorted(layers, key=key):
         out += [layers[name]["kernel:0"], layers[name]["bias:0"]]
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# writer: the same structural subset (superblock v0, old-style groups, contiguous datasets)
+# ------------------------------------------------------------------------------------------------
+
+_LEAF_K, _INT_K = 4, 16          # group B-tree parameters recorded in the superblock
+
+
+def _pad8(b: bytes) -> bytes:
+    return b + b"\x00" * (-len(b) % 8)
+
+
+def _message(mtype: int, body: bytes) -> bytes:
+    body = _pad8(body)
+    return struct.pack("<HHB3x", mtype, len(body), 0) + body
+
+
+def _object_header(messages: List[bytes]) -> bytes:
+    data = b"".join(messages)
+    return struct.pack("<BBHII4x", 1, 0, len(messages), 1, len(data)) + data
+
+
+def _datatype_message(dt: np.dtype) -> bytes:
+    dt = np.dtype(dt)
+    if dt.kind == "f" and dt.itemsize in (4, 8):
+        size = dt.itemsize
+        exp_bits, man_bits, bias = (8, 23, 127) if size == 4 else (11, 52, 1023)
+        # class 1 (floating point), version 1; bit field 0: little-endian, mantissa normalisation 2 (implied msb); bit field 1: sign position
+        head = struct.pack("<BBBBI", 0x11, 0x20, 8 * size - 1, 0, size)
+        return head + struct.pack("<HHBBBBI", 0, 8 * size, man_bits, exp_bits, 0, man_bits, bias)
+    if dt.kind in "iu" and dt.itemsize in (1, 2, 4, 8):
+        head = struct.pack("<BBBBI", 0x10, 0x08 if dt.kind == "i" else 0x00, 0, 0, dt.itemsize)
+        return head + struct.pack("<HH", 0, 8 * dt.itemsize)
+    raise H5Error(f"dtype {dt} not supported by the writer")
+
+
+class _Writer:
+    def __init__(self):
+        self.buf = bytearray(96)      # superblock placeholder
+
+    def alloc(self, data: bytes) -> int:
+        self.buf += b"\x00" * (-len(self.buf) % 8)
+        addr = len(self.buf)
+        self.buf += data
+        return addr
+
+    def dataset(self, arr: np.ndarray) -> int:
+        arr = np.ascontiguousarray(arr)
+        if arr.dtype.byteorder == ">":
+            arr = arr.astype(arr.dtype.newbyteorder("<"))
+        raw = arr.tobytes()
+        data_addr = self.alloc(raw) if raw else _UNDEF
+        space = struct.pack("<BBB5x", 1, arr.ndim, 0) + b"".join(struct.pack("<Q", d) for d in arr.shape)
+        layout = struct.pack("<BBQQ", 3, 1, data_addr, len(raw))
+        return self.alloc(_object_header([_message(0x0001, space), _message(0x0003, _datatype_message(arr.dtype)),
+                                          _message(0x0008, layout)]))
+
+    def group(self, children: Dict[str, int], is_group: Dict[str, Tuple[int, int]]) -> Tuple[int, int, int]:
+        """children: name -> object header address.  Returns (header address, B-tree address, heap address)."""
+        names = sorted(children)
+        if len(names) > 2 * _LEAF_K * 2 * _INT_K:
+            raise H5Error("too many links in one group for the single-level B-tree of this writer")
+        heap_data = bytearray(8)      # offset 0: the empty name
+        offs = {}
+        for n in names:
+            offs[n] = len(heap_data)
+            heap_data += _pad8(n.encode() + b"\x00")
+        heap_seg = self.alloc(bytes(heap_data))
+        heap = self.alloc(b"HEAP" + struct.pack("<B3xQQQ", 0, len(heap_data), _UNDEF, heap_seg))
+        snods, keys = [], [0]
+        for i in range(0, max(len(names), 1), 2 * _LEAF_K):
+            part = names[i:i + 2 * _LEAF_K]
+            body = b"SNOD" + struct.pack("<BBH", 1, 0, len(part))
+            for n in part:
+                if n in is_group:
+                    body += struct.pack("<QQII", offs[n], children[n], 1, 0) + struct.pack("<QQ", *is_group[n])
+                else:
+                    body += struct.pack("<QQII16x", offs[n], children[n], 0, 0)
+            body += b"\x00" * (8 + 2 * _LEAF_K * 40 - len(body))
+            snods.append(self.alloc(body))
+            keys.append(offs[part[-1]] if part else 0)
+        node = b"TREE" + struct.pack("<BBHQQ", 0, 0, len(snods), _UNDEF, _UNDEF)
+        for i, a in enumerate(snods):
+            node += struct.pack("<QQ", keys[i], a)
+        node += struct.pack("<Q", keys[len(snods)])
+        node += b"\x00" * (24 + (2 * _INT_K) * 8 + (2 * _INT_K + 1) * 8 - len(node))
+        btree = self.alloc(node)
+        header = self.alloc(_object_header([_message(0x0011, struct.pack("<QQ", btree, heap))]))
+        return header, btree, heap
+
+
+def write_h5(path: str, datasets: Dict[str, np.ndarray]) -> None:
+    """Write ``{"group/sub/name": array}`` as an HDF5 file of the subset ``H5File`` reads (and h5py / Keras read too):
+    superblock v0, old-style groups, contiguous little-endian float / integer datasets, no attributes."""
+    tree: Dict[str, object] = {}
+    for key, arr in datasets.items():
+        parts = [p for p in key.split("/") if p]
+        node = tree
+        for p in parts[:-1]:
+            node = node.setdefault(p, {})
+            if not isinstance(node, dict):
+                raise H5Error(f"{key}: a dataset is in the way")
+        node[parts[-1]] = np.asarray(arr)
+    w = _Writer()
+
+    def emit(node) -> Tuple[int, int, int]:
+        children, groups = {}, {}
+        for name, val in node.items():
+            if isinstance(val, dict):
+                h, b, hp = emit(val)
+                children[name], groups[name] = h, (b, hp)
+            else:
+                children[name] = w.dataset(val)
+        return w.group(children, groups)
+
+    root, btree, heap = emit(tree)
+    sb = _SIG + struct.pack("<BBBBBBBBHHI", 0, 0, 0, 0, 0, 8, 8, 0, _LEAF_K, _INT_K, 0)
+    sb += struct.pack("<QQQQ", 0, _UNDEF, len(w.buf), _UNDEF)
+    sb += struct.pack("<QQII", 0, root, 1, 0) + struct.pack("<QQ", btree, heap)
+    assert len(sb) == 96
+    w.buf[:96] = sb
+    with open(path, "wb") as fh:
+        fh.write(bytes(w.buf))
+
+
+def save_keras_dense_weights(path: str, variables: List[np.ndarray], dtype=np.float64) -> None:
+    """``[K1, b1, K2, b2, ...]`` -> a ``Weights.h5`` with the dataset paths Keras 2.7's ``model.save_weights`` uses for a
+    Sequential of Dense layers (``dense/dense/kernel:0``, ``dense_1/dense_1/bias:0``, ...; cavity_steady.py:249-252).
+    The reference's files also carry string attributes (``layer_names``, ``weight_names``) that this writer does not emit:
+    ``load_keras_dense_weights`` and any reader that walks the groups do not need them."""
+    out = {}
+    for i in range(len(variables) // 2):
+        name = "dense" if i == 0 else f"dense_{i}"
+        out[f"{name}/{name}/kernel:0"] = np.asarray(variables[2 * i], dtype=dtype)
+        out[f"{name}/{name}/bias:0"] = np.asarray(variables[2 * i + 1], dtype=dtype)
+    write_h5(path, out)

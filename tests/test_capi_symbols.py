@@ -27,7 +27,7 @@ def test_header_symbols_are_exported():
 def test_library_loads_and_reports_errors_without_a_gpu():
     _ensure_built()
     lib = _capi.load()
-    assert lib.pinn_version() == 101
+    assert lib.pinn_version() == 102
     import ctypes as C
     out = C.c_void_p()
     rc = lib.pinn_plan_create(None, None, 0, 0, C.byref(out))

@@ -24,7 +24,9 @@
  *   - work is enqueued asynchronously on the caller's stream (a cudaStream_t passed as void*);
  *     pinn_loss_and_grad / pinn_loss do not allocate and do not synchronise, so they can be
  *     captured in a CUDA graph.
- *   - a plan is bound to one device and is not thread-safe; one plan per rank.
+ *   - a plan is bound to one device and is not thread-safe; one plan per rank.  The entry points that take a plan switch
+ *     to its device for the call and restore the caller's current device; several plans on several devices may live in
+ *     one process (per-device kernel attributes are set on first use on each device).
  *
  * Residual model.  Let J[o][c] be the Taylor jet of network output o at a point:
  *   c = 0               value
@@ -150,7 +152,11 @@ int pinn_loss_and_grad(pinn_plan* plan, const float* params_dev, float* out_dev,
  * Replaces: the evaluation of `losses_test` at every log point (cavity_steady.py:233-235). */
 int pinn_loss(pinn_plan* plan, const float* params_dev, float* out_dev, void* stream);
 /* Forward-only network evaluation, values only: y[n, o] = model(x)[n, o].
- * Replaces: model(grid) in the scripts' post-processing (cavity_steady.py:254-268). */
+ * Replaces: model(grid) in the scripts' post-processing (cavity_steady.py:254-268).
+ * Fused engines (H <= 32): asynchronous on `stream` (stream-ordered scratch), graph-capturable.  Layered engines (H = 64,
+ * 128): the EXCEPTION to the conventions above -- the call allocates a temporary activation workspace sized for n points,
+ * and returns after the work has completed and the workspace is freed (post-processing is not a hot path; the training
+ * entry points never do this). */
 int pinn_forward(const pinn_mlp_desc* mlp, const float* params_dev, const float* points_dev,
                  int64_t n, float* y_dev, int32_t device, void* stream);
 
@@ -183,6 +189,10 @@ int pinn_adam_step_dev(float* params_dev, const float* grad_dev, float* m_dev, f
 int pinn_bfgs_identity(double* H_dev, int64_t n, void* stream);                       /* H = I (SciPy's start) */
 /* xt = x + alpha p, theta = float(xt): the parameters of the next loss step */
 int pinn_bfgs_trial(const double* x_dev, const double* p_dev, double alpha, double* xt_dev, float* theta_dev, int64_t n, void* stream);
+/* the same with alpha read from device memory at execution time: lets the caller capture trial point + loss step + evaluation in
+ * ONE CUDA graph and replay it for every step length of the line search */
+int pinn_bfgs_trial_dev(const double* x_dev, const double* p_dev, const double* alpha_dev, double* xt_dev, float* theta_dev, int64_t n,
+                        void* stream);
 /* after pinn_loss_and_grad (+ the SUM over ranks) into out [n + n_terms]: gt = double(gradient), scal[0] = sum_t coef[t] *
  * (kind[t] ? |out[n+t]| : out[n+t]) (the total loss: coef = weight / (normalization N_global), kind 1 = |mean| term),
  * scal[1] = gt . p, scal[2] = |gt|_inf */

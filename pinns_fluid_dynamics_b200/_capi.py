@@ -17,7 +17,7 @@ EXPORTED_SYMBOLS = (
     "pinn_plan_term_count", "pinn_plan_workspace_bytes", "pinn_plan_engine", "pinn_plan_last_launch_count",
     "pinn_plan_set_rhs", "pinn_plan_enable_timing", "pinn_plan_kernel_time_ms", "pinn_loss_and_grad", "pinn_loss", "pinn_forward", "pinn_nccl_unique_id",
     "pinn_comm_create", "pinn_comm_destroy", "pinn_allreduce_sum", "pinn_adam_step", "pinn_adam_step_dev",
-    "pinn_bfgs_identity", "pinn_bfgs_trial", "pinn_bfgs_eval", "pinn_bfgs_direction", "pinn_bfgs_accept_update",
+    "pinn_bfgs_identity", "pinn_bfgs_trial", "pinn_bfgs_trial_dev", "pinn_bfgs_eval", "pinn_bfgs_direction", "pinn_bfgs_accept_update",
 )
 
 
@@ -94,6 +94,7 @@ def load(path: Optional[str] = None) -> C.CDLL:
     lib.pinn_adam_step_dev.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, vp, vp]
     lib.pinn_bfgs_identity.argtypes = [vp, i64, vp]
     lib.pinn_bfgs_trial.argtypes = [vp, vp, C.c_double, vp, vp, i64, vp]
+    lib.pinn_bfgs_trial_dev.argtypes = [vp, vp, vp, vp, vp, i64, vp]
     lib.pinn_bfgs_eval.argtypes = [vp, vp, vp, i32, vp, vp, vp, i64, vp]
     lib.pinn_bfgs_direction.argtypes = [vp, vp, vp, vp, i64, vp]
     lib.pinn_bfgs_accept_update.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i64, vp]

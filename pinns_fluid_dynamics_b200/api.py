@@ -92,6 +92,8 @@ class TanhMLP:
             raise _capi.PinnLibraryError("model(x) runs on the GPU only (no CPU fallback)")
         lib = _capi.load()
         x = torch.as_tensor(x, dtype=torch.float32, device=self.flat.device).contiguous()
+        if x.dim() != 2 or x.shape[1] != self.dim:
+            raise ValueError(f"model(x) takes [n, {self.dim}] points, got {tuple(x.shape)}")
         y = torch.empty(x.shape[0], self.out_dim, dtype=torch.float32, device=self.flat.device)
         mlp = _capi.MlpDesc(self.dim, self.hidden[0], len(self.hidden), self.out_dim)
         stream = C.c_void_p(torch.cuda.current_stream(self.flat.device).cuda_stream)
@@ -113,12 +115,42 @@ class TanhMLP:
                            "backend": "pinns_fluid_dynamics_b200"})
 
     def save_weights(self, path: str) -> None:
-        """h5py is unavailable: weights go to ``.npz`` with Keras' dataset names as keys."""
+        """``model.save_weights(f"{saving_folder}/Weights.h5")`` (cavity_steady.py:252).  ``*.h5`` / ``*.hdf5``: an HDF5 file
+        with Keras' dataset paths (``dense/dense/kernel:0``, ``dense_1/dense_1/bias:0``, ...; float64 like the reference's
+        files) written by ``h5lite`` -- the reference's tooling and ``load_weights`` read it back.  Anything else: ``.npz``
+        with the same dataset paths as keys."""
+        from . import h5lite
+        arrays = self.get_weights()
+        if path.endswith((".h5", ".hdf5")):
+            h5lite.save_keras_dense_weights(path, arrays)
+            return
         names = {}
-        for i in range(len(self.variables) // 2):
-            names[f"dense_{i}/kernel:0"] = self.variables[2 * i].detach().cpu().numpy()
-            names[f"dense_{i}/bias:0"] = self.variables[2 * i + 1].detach().cpu().numpy()
+        for i in range(len(arrays) // 2):
+            layer = "dense" if i == 0 else f"dense_{i}"
+            names[f"{layer}/{layer}/kernel:0"] = arrays[2 * i]
+            names[f"{layer}/{layer}/bias:0"] = arrays[2 * i + 1]
         np.savez(path, **names)
+
+    def load_weights(self, path: str) -> None:
+        """``model.load_weights(path)``: a Keras ``Weights.h5`` (the reference's Test_Case folders, or ``save_weights``) or
+        the ``.npz`` of ``save_weights``.  Layers are taken in the order of their Keras index (dense, dense_1, ...)."""
+        from . import h5lite
+        if path.endswith((".h5", ".hdf5")):
+            self.set_weights(h5lite.load_keras_dense_weights(path))
+            return
+        with np.load(path if path.endswith(".npz") else path + ".npz") as z:
+            layers = {}
+            for key in z.files:
+                parts = key.split("/")
+                layers.setdefault(parts[0], {})[parts[-1]] = z[key]
+
+        def index(name: str) -> int:
+            tail = name.rsplit("_", 1)
+            return int(tail[1]) if len(tail) == 2 and tail[1].isdigit() else 0
+        arrays = []
+        for name in sorted(layers, key=index):
+            arrays += [layers[name]["kernel:0"], layers[name]["bias:0"]]
+        self.set_weights(arrays)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -128,7 +160,7 @@ class TanhMLP:
 class LossMeanSquares:
     """value = mean(roots**2) / normalization; history fields weight / non_negative / display_sqrt."""
 
-    def __init__(self, name: str, eval_roots: Union[ResidualForm, Callable[[], ResidualForm]],
+    def __init__(self, name: str, eval_roots: Union[ResidualForm, Callable[[], ResidualForm]], *,
                  weight: float = 1.0, normalization: float = 1.0):
         form = eval_roots() if callable(eval_roots) and not isinstance(eval_roots, ResidualForm) else eval_roots
         if not isinstance(form, ResidualForm):
@@ -146,7 +178,7 @@ class Loss:
     that scalar is served on the fused path as the ``abs_mean`` reduction of a residual form
     (``residuals.mean_value``).  Any other scalar closure is rejected loudly."""
 
-    def __init__(self, name, eval_loss, weight=1.0, normalization=1.0, non_negative=False):
+    def __init__(self, name, eval_loss, *, weight=1.0, normalization=1.0, non_negative=False):
         form = eval_loss() if callable(eval_loss) and not isinstance(eval_loss, ResidualForm) else eval_loss
         if not isinstance(form, ResidualForm) or form.reduction != "abs_mean":
             raise NotImplementedError(
@@ -185,7 +217,8 @@ class OptimizationProblem:
         self.world = self._dist.get_world_size(self.group) if self._dist else 1
         self.compiled: CompiledProblem = compile_problem([tuple(v.shape) for v in self.variables],
                                                          self.losses, self.losses_test, self.rank, self.world)
-        self.plan = (engine_factory or CudaPlan)(self.compiled)
+        # the plan (device copies of the point sets, workspace) lives on the device of the parameters
+        self.plan = engine_factory(self.compiled) if engine_factory else CudaPlan(self.compiled, device=self.flat.device)
         self._graph, self._graph_opt, self._graph_sumsq, self._eager_steps = None, None, None, 0
         self._comm, self._comm_tried = None, False
         self._h_theta = self._h_out = self._perm_np = None      # pinned staging of evaluate_host
@@ -431,7 +464,7 @@ def minimize(pb: OptimizationProblem, backend: str, optimizer, num_epochs: int) 
             # SciPy's BFGS algorithm and line search with the quasi-Newton algebra in hand-written kernels on the device
             # (scipy.optimize.minimize spends 133 ms per iteration in two P^3 products for P = 2307): bfgs.py, csrc/bfgs.cuh
             from .bfgs import minimize_bfgs_device
-            minimize_bfgs_device(pb, maxiter=maxiter, callback=pb.step_done)
+            pb.last_result = minimize_bfgs_device(pb, maxiter=maxiter, callback=pb.step_done)
             return
 
         def fun(theta: np.ndarray):
@@ -448,6 +481,7 @@ def minimize(pb: OptimizationProblem, backend: str, optimizer, num_epochs: int) 
             res = minimize_bfgs(fun, x0, maxiter=maxiter, callback=cb, device=pb.flat.device)
         else:
             res = scipy.optimize.minimize(fun, x0, jac=True, method=method, callback=cb, options={"maxiter": maxiter})
+        pb.last_result = res
         pb.flat.copy_(torch.as_tensor(res.x, dtype=torch.float32))
     else:
         raise ValueError(f"unknown backend {backend!r} (expected 'keras' or 'scipy')")

@@ -22,6 +22,8 @@ switches to the limited-memory two-loop recursion (m = 20 pairs) on the same lin
 from __future__ import annotations
 
 import ctypes as C
+import os
+import time
 from typing import Callable, Optional, Tuple
 
 import numpy as np
@@ -188,15 +190,64 @@ def minimize_bfgs_device(pb, maxiter: int, callback: Optional[Callable[[], None]
         return scal_host
 
     nfev = [0]
+    # One evaluation = trial point + loss step (+ SUM over ranks) + evaluation kernel + read-back of 8 doubles.  The same
+    # launch sequence every time (the step length travels through a pinned host scalar), so it is captured once in a CUDA
+    # graph and replayed: an evaluation costs one graph launch and one stream synchronisation instead of ~8 launches
+    # (at 10 k collocation points the launches, not the kernels, set the pace).  PINN_BFGS_GRAPH=0 keeps it eager.
+    use_graph = os.environ.get("PINN_BFGS_GRAPH", "1") != "0" and not getattr(plan, "timing_enabled", False)
+    alpha_host = torch.zeros(1, dtype=torch.float64, pin_memory=True)
+    alpha_dev = torch.zeros(1, **f64)
+    graphs = {"eval": None, "accept": None}
 
-    def evaluate(alpha: float):
-        """phi(alpha), phi'(alpha), |g|_inf at x + alpha p: trial kernel, loss step (+ SUM over ranks), evaluation kernel."""
-        _capi.check(lib.pinn_bfgs_trial(ptr(x), ptr(p), float(alpha), ptr(xt), ptr(pb.flat), n, stream()), "pinn_bfgs_trial")
+    def enqueue_eval():
+        alpha_dev.copy_(alpha_host, non_blocking=True)
+        _capi.check(lib.pinn_bfgs_trial_dev(ptr(x), ptr(p), ptr(alpha_dev), ptr(xt), ptr(pb.flat), n, stream()), "pinn_bfgs_trial_dev")
         out = pb._reduce(plan.loss_and_grad(pb.flat))
         _capi.check(lib.pinn_bfgs_eval(ptr(out), ptr(coef), ptr(kind), len(terms), ptr(p), ptr(gt), ptr(scal), n, stream()),
                     "pinn_bfgs_eval")
+        scal_host.copy_(scal, non_blocking=True)
+
+    def enqueue_accept():
+        _capi.check(lib.pinn_bfgs_accept_update(ptr(H), ptr(x), ptr(g), ptr(xt), ptr(gt), ptr(s), ptr(y), ptr(u), ptr(p), ptr(scal),
+                                                1, n, stream()), "pinn_bfgs_accept_update")
+        pb.flat.copy_(x)                               # FP32 copy of the accepted iterate
+        scal_host.copy_(scal, non_blocking=True)
+
+    spent = {"eval": 0.0, "accept": 0.0, "n_eval": 0, "n_accept": 0}
+
+    def run(name, enqueue):
+        t_begin = time.perf_counter()
+        try:
+            return _run(name, enqueue)
+        finally:
+            spent[name] += time.perf_counter() - t_begin
+            spent["n_" + name] += 1
+
+    def _run(name, enqueue):
+        """replay the captured sequence (captured on its second use: the first one runs eagerly and creates whatever the
+        step creates lazily -- NCCL communicator, kernel attributes), then wait for the scalars"""
+        if use_graph and graphs[name] is None:
+            graphs[name] = False                       # next call captures
+            enqueue()
+        elif use_graph and graphs[name] is False:
+            torch.cuda.synchronize(dev)
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, capture_error_mode="thread_local" if pb.world > 1 else "global"):
+                enqueue()
+            graphs[name] = gr
+            gr.replay()
+        elif use_graph:
+            graphs[name].replay()
+        else:
+            enqueue()
+        torch.cuda.current_stream(dev).synchronize()
+        return scal_host
+
+    def evaluate(alpha: float):
+        """phi(alpha), phi'(alpha), |g|_inf at x + alpha p"""
+        alpha_host[0] = float(alpha)
+        h = run("eval", enqueue_eval)
         nfev[0] += 1
-        h = read_scalars()
         return float(h[0]), float(h[1]), float(h[2])
 
     def direction_lbfgs():
@@ -227,8 +278,8 @@ def minimize_bfgs_device(pb, maxiter: int, callback: Optional[Callable[[], None]
     old_fval = phi0
     old_old_fval = old_fval + float(torch.linalg.vector_norm(g)) / 2      # first step ~ 1 (SciPy)
     k, warnflag = 0, 0
+    derphi0 = float(read_scalars()[4])
     while gnorm > gtol and k < maxiter:
-        derphi0 = float(read_scalars()[4])
         last = {}
 
         def phi(a):
@@ -254,9 +305,12 @@ def minimize_bfgs_device(pb, maxiter: int, callback: Optional[Callable[[], None]
         k += 1
         # the accepted point is x_t; pb.flat already holds float(x_t) unless the last trial was another alpha
         update = gnorm > gtol and np.isfinite(old_fval)
-        if dense:
+        if dense and update:
+            derphi0 = float(run("accept", enqueue_accept)[4])
+        elif dense:
             _capi.check(lib.pinn_bfgs_accept_update(ptr(H), ptr(x), ptr(g), ptr(xt), ptr(gt), ptr(s), ptr(y), ptr(u), ptr(p), ptr(scal),
-                                                    1 if update else 0, n, stream()), "pinn_bfgs_accept_update")
+                                                    0, n, stream()), "pinn_bfgs_accept_update")
+            pb.flat.copy_(x)
         else:
             s.copy_(xt).sub_(x)
             y.copy_(gt).sub_(g)
@@ -268,7 +322,8 @@ def minimize_bfgs_device(pb, maxiter: int, callback: Optional[Callable[[], None]
                     if len(S) > history_m:
                         S.pop(0); Y.pop(0)
                 direction_lbfgs()
-        pb.flat.copy_(x)                               # FP32 copy of the accepted iterate
+                derphi0 = float(read_scalars()[4])
+            pb.flat.copy_(x)                           # FP32 copy of the accepted iterate
         if callback is not None:
             callback()
         if not update:
@@ -278,5 +333,5 @@ def minimize_bfgs_device(pb, maxiter: int, callback: Optional[Callable[[], None]
     if warnflag == 0 and k >= maxiter:
         warnflag = 1
     pb.flat.copy_(x)
-    return BfgsResult(x=x, fun=old_fval, nit=k, nfev=nfev[0], status=warnflag, success=(warnflag == 0), hess_inv=H,
+    return BfgsResult(x=x, fun=old_fval, nit=k, nfev=nfev[0], status=warnflag, success=(warnflag == 0), hess_inv=H, seconds=spent,
                       algebra="dense float64 inverse Hessian on the device" if dense else f"L-BFGS two-loop, m = {history_m}")

@@ -27,6 +27,17 @@ __global__ void bfgs_trial_kernel(const double* __restrict__ x, const double* __
   }
 }
 
+// the same with the step length read from device memory (the caller's CUDA graph replays with a new alpha every time)
+__global__ void bfgs_trial_dev_kernel(const double* __restrict__ x, const double* __restrict__ p, const double* __restrict__ alpha,
+                                      double* __restrict__ xt, float* __restrict__ theta, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const double v = fma(*alpha, p[i], x[i]);
+    xt[i] = v;
+    theta[i] = (float)v;
+  }
+}
+
 __device__ __forceinline__ double block_sum(double v, double* sh) {      // fixed-order sum over a 1024-thread CTA
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;

@@ -495,16 +495,17 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
       mbar_wait(BAR(B_WDONE), ph_wd);
       ph_wd ^= 1u;
       umma::fence_after_thread_sync();
-      if (h == 0) {
-        float wv[32];
-        tmem_ld32(tm_lane + Cfg::COL_W, wv);
+      {
+        // the four warps of a quadrant share the drain: warp h takes columns 8h .. 8h+7 (neurons j) of the quadrant's 16 rows
+        float wv[8];
+        tmem_ld8(tm_lane + Cfg::COL_W + 8u * (uint32_t)h, wv);
         // quadrant q holds rows 16q..16q+15 of the M = 64 accumulator: lanes 0-7 the b1 part of neurons 8q..8q+7, lanes 8-15 the b2 part
 #pragma unroll
-        for (int j = 0; j < 32; ++j) wv[j] += __shfl_down_sync(0xffffffffu, wv[j], 8);
+        for (int j = 0; j < 8; ++j) wv[j] += __shfl_down_sync(0xffffffffu, wv[j], 8);
         if (lane < 8) {
-          float4* t4 = reinterpret_cast<float4*>(tot + li * 1024 + (8 * q + lane) * 32);
+          float4* t4 = reinterpret_cast<float4*>(tot + li * 1024 + (8 * q + lane) * 32 + 8 * h);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < 2; ++j) {
             float4 t = t4[j];
             t.x += wv[4 * j]; t.y += wv[4 * j + 1]; t.z += wv[4 * j + 2]; t.w += wv[4 * j + 3];
             t4[j] = t;
@@ -638,12 +639,12 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
             for (int c = 0; c < C; ++c) v[c][pr] = a[c];
           }
           emit_operand<C, true>(v, tm_lane + Cfg::COL_A + 8u * g + 4u * v4);
+          arrive_group(g);                     // the GEMM only needs the operand: the images below are written under its MMAs
           if constexpr (TRAIN) {
             uint2 p1[C], p2[C];
             pack_images<C>(v, p1, p2);
             store_images<C>(imgX + img_thr + g * 256, p1, p2);
           }
-          arrive_group(g);
         }
       }
       TC_PROF(2);
@@ -843,12 +844,12 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
               for (int c = 0; c < C; ++c) v[c][pr] = zb[c];
             }
             emit_operand<C, false>(v, tm_lane + Cfg::COL_A + 8u * g + 4u * v4);
+            arrive_group(g);
             {
               uint2 p1[C], p2[C];
               pack_images<C>(v, p1, p2);
               store_images<C>(imgY + img_thr + g * 256, p1, p2);
             }
-            arrive_group(g);
           }
           umma::fence_proxy_async_smem();      // images X (a_2) and Y (z-bar_3) -> visible to the weight-gradient MMAs
           __syncwarp();
@@ -901,8 +902,8 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
               for (int c = 0; c < C; ++c) v[c][pr] = zb[c];
             }
             emit_operand<C, false>(v, tm_lane + Cfg::COL_A + 8u * g + 4u * v4);
-            pack_images<C>(v, zp1[hs], zp2[hs]);
             arrive_group(g);
+            pack_images<C>(v, zp1[hs], zp2[hs]);
           }
           TC_PROF(9);
           drain_w(1);                          // K-bar_3 batch finished: its accumulator -> totals; X and Y are free

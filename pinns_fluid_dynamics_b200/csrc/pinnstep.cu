@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -38,6 +39,30 @@ static int fail(int code, const char* fmt, ...) {
     if (e_ != cudaSuccess)                                                                     \
       return fail(PINN_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
+
+// The opt-in shared-memory size of a kernel is a per-DEVICE attribute: one bit per device ordinal records where it has been set
+// (a process may drive several GPUs).
+struct DeviceOnce {
+  std::atomic<unsigned long long> done{0};
+  bool needed(int device) const { return device < 0 || device >= 64 || !((done.load(std::memory_order_acquire) >> device) & 1ull); }
+  void mark(int device) { if (device >= 0 && device < 64) done.fetch_or(1ull << device, std::memory_order_release); }
+};
+
+// Launches go to the thread's current device: the entry points that run a plan switch to the plan's device for the call and
+// restore the caller's afterwards (no-op in the usual one-GPU-per-process case).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != device) {
+      err = cudaSetDevice(device);
+      switched = err == cudaSuccess;
+    }
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
 
 // ------------------------------------------------------------------------------------------------
 // plan
@@ -236,12 +261,12 @@ static int layered_run_set(pinn_plan* p, const float* params, float* out, cudaSt
   const int L = p->mlp.n_hidden;
   const size_t layer_stride = (size_t)p->batch * kMaxCh * H;   // floats between Act[l] buffers
   const int smem = gemm_smem_bytes<C>();
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attrs;
+  if (attrs.needed(p->device)) {
     CUDA_TRY(cudaFuncSetAttribute((const void*)fwd_layer_kernel<D, H, ORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CUDA_TRY(cudaFuncSetAttribute((const void*)bwd_layer_kernel<D, H, ORDER, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CUDA_TRY(cudaFuncSetAttribute((const void*)bwd_layer_kernel<D, H, ORDER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_done = true;
+    attrs.mark(p->device);
   }
   const int off_ko = D * H + H + (L - 1) * (H * H + H);
   for (long long b0 = 0; b0 < seg.n; b0 += p->batch) {
@@ -398,11 +423,11 @@ static int tc_run_order(pinn_plan* p, const float* params, float* out, cudaStrea
   using S = tc::LayerSmem<G::NR>;
   constexpr int H = tc::kH;
   const int L = p->mlp.n_hidden;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attrs;
+  if (attrs.needed(p->device)) {
     int rc = tc_set_attrs<D, ORDER>();
     if (rc != PINN_OK) return rc;
-    attr_done = true;
+    attrs.mark(p->device);
   }
   const int off_ko = D * H + H + (L - 1) * (H * H + H);
   const long long total_tiles = (long long)lt.tiles_host.size();
@@ -768,6 +793,8 @@ static int fused_pass(pinn_plan* p, const LaunchTable* tables, const float* para
 
 static int run(pinn_plan* p, const float* params, float* out, cudaStream_t st, bool train) {
   if (!p || !params || !out) return fail(PINN_E_INVALID, "null argument");
+  DeviceGuard on_device(p->device);
+  if (on_device.err != cudaSuccess) return fail(PINN_E_CUDA, "cannot switch to device %d: %s", p->device, cudaGetErrorString(on_device.err));
   if (p->tc) return run_tc(p, params, out, st, train);
   if (p->layered) return run_layered(p, params, out, st, train);
   int launches = 0;
@@ -1020,6 +1047,14 @@ extern "C" int pinn_bfgs_identity(double* H, int64_t n, void* stream) {
 extern "C" int pinn_bfgs_trial(const double* x, const double* p, double alpha, double* xt, float* theta, int64_t n, void* stream) {
   if (!x || !p || !xt || !theta || n <= 0) return fail(PINN_E_INVALID, "bad argument");
   pinn::bfgs::bfgs_trial_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, p, alpha, xt, theta, n);
+  CUDA_TRY(cudaGetLastError());
+  return PINN_OK;
+}
+
+extern "C" int pinn_bfgs_trial_dev(const double* x, const double* p, const double* alpha_dev, double* xt, float* theta, int64_t n,
+                                   void* stream) {
+  if (!x || !p || !alpha_dev || !xt || !theta || n <= 0) return fail(PINN_E_INVALID, "bad argument");
+  pinn::bfgs::bfgs_trial_dev_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, p, alpha_dev, xt, theta, n);
   CUDA_TRY(cudaGetLastError());
   return PINN_OK;
 }

@@ -177,6 +177,10 @@ class CudaPlan:
         self.lib = _capi.load()
         self.cp = cp
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise _capi.PinnLibraryError(f"CUDA device required, got {self.device}: the PINN loss step has no CPU fallback")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         # every local point / rhs shard lives in ONE device arena (views below), mirrored by one host arena:
         # the end-to-end path moves all inputs of a step with a single host->device copy
         hosts, where = [], {}
@@ -243,13 +247,21 @@ class CudaPlan:
     def loss_and_grad(self, params_flat):
         """Enqueue one step; returns the device vector [P + T] (gradient, then per-term sum r^2 in
         KERNEL term order -- use ``to_table_order``)."""
-        assert params_flat.is_cuda and params_flat.dtype.is_floating_point and params_flat.is_contiguous()
+        self._check_params(params_flat)
         _capi.check(self.lib.pinn_loss_and_grad(self.handle, C.c_void_p(params_flat.data_ptr()),
                                                 C.c_void_p(self.out.data_ptr()), self._stream()),
                     "pinn_loss_and_grad")
         return self.out
 
+    def _check_params(self, params_flat):
+        import torch
+        if not (params_flat.is_cuda and params_flat.dtype == torch.float32 and params_flat.is_contiguous()):
+            raise ValueError("the parameter vector must be a contiguous FP32 CUDA tensor")
+        if params_flat.device != self.device:
+            raise ValueError(f"parameters live on {params_flat.device}, the plan (point sets, workspace) on {self.device}")
+
     def loss_only(self, params_flat):
+        self._check_params(params_flat)
         _capi.check(self.lib.pinn_loss(self.handle, C.c_void_p(params_flat.data_ptr()),
                                        C.c_void_p(self.out.data_ptr()), self._stream()), "pinn_loss")
         return self.out

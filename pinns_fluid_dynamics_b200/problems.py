@@ -222,6 +222,26 @@ def load_fem_fields(path: str):
     return vel[:, 0], vel[:, 1], pre - np.mean(pre)
 
 
+def load_unsteady_fem_fields(folder: str, n_times: int, pattern: str = "navier-stokes_SI_cavity_unsteady_{:05d}.h5"):
+    """The per-time-step FEniCS files of DataGeneration/fluid_solver_unsteady.py as the unsteady script reads them
+    (cavity_unsteady.py:103-113): file ``x`` holds VisualisationVector/0 = velocity [n, 2|3] and /1 = pressure [n] on
+    the grid vertices at time step ``x``; the pressure of EVERY step has its own mean subtracted (:109); the steps are
+    concatenated in time order, matching the (t, y, x) ordering of ``dom_grid`` (:95)."""
+    import os
+    from .h5lite import H5File
+    u, v, p = [], [], []
+    for step in range(int(n_times)):
+        path = os.path.join(folder, pattern.format(step))
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path}: time step {step} of {n_times} is missing")
+        f = H5File(path)
+        vel, pre = f["VisualisationVector/0"], np.asarray(f["VisualisationVector/1"]).reshape(-1)
+        u.append(np.asarray(vel[:, 0], dtype=np.float64))
+        v.append(np.asarray(vel[:, 1], dtype=np.float64))
+        p.append(pre.astype(np.float64) - np.mean(pre))
+    return np.concatenate(u), np.concatenate(v), np.concatenate(p)
+
+
 def read_gmsh_nodes(path: str) -> np.ndarray:
     """Node coordinates ``[n, 3]`` (ordered by node tag) of an ASCII gmsh 4.x mesh -- the ``$Nodes`` section of
     Examples/Coronary_Flow/coroParam.msh.  dolfin keeps this order: the arrays of sol_pinn.h5
@@ -286,9 +306,11 @@ def cavity_steady(options: Optional[SimulationOptions] = None, seed: int = 1, fe
 
 def cavity_unsteady(options: Optional[SimulationOptions] = None, seed: int = 1, hidden=(32, 32, 32),
                     lid_velocity: float = 1.0, T: float = 1e-2, dt: float = 1e-4, n_times: Optional[int] = None,
-                    **counts) -> ProblemData:
+                    fem_fields=None, **counts) -> ProblemData:
     """Examples/Cavity_Unsteady/cavity_unsteady.py:60-163; rows are (t, x, y).  ``hidden`` lets the
-    BASELINE config 5 ask for the 8x128 network."""
+    BASELINE config 5 ask for the 8x128 network.  ``fem_fields``: the folder of the per-time-step FEniCS files
+    (``../../DataGeneration/data/UnsteadyCase``, cavity_unsteady.py:104-105; read by ``load_unsteady_fem_fields``) or
+    a ready ``(u, v, p)`` triple over the (t, y, x) grid; without it a smooth synthetic field stands in."""
     o = _opts(options, **counts)
     rng = np.random.default_rng(seed)
     d = ProblemData("cavity_unsteady", 3, list(hidden), 3, o)
@@ -297,10 +319,17 @@ def cavity_unsteady(options: Optional[SimulationOptions] = None, seed: int = 1, 
     grid2 = build_grid(0, 1, 0, 1, 100, 100)
     grid = build_grid(0, 1, 0, 1, 100, 100, times=time_vec)
     idx = split_indices(grid.shape[0], _split_counts(o.n_pts, grid.shape[0]), rng)
-    u_ex, v_ex, p_ex = synthetic_cavity_field(grid[:, 1:], lid_velocity, t=grid[:, 0], T=T)
-    # per-time-step mean subtraction of the pressure (cavity_unsteady.py:109)
     n2 = grid2.shape[0]
-    p_ex = (p_ex.reshape(-1, n2) - p_ex.reshape(-1, n2).mean(axis=1, keepdims=True)).reshape(-1)
+    if fem_fields is None:
+        u_ex, v_ex, p_ex = synthetic_cavity_field(grid[:, 1:], lid_velocity, t=grid[:, 0], T=T)
+        # per-time-step mean subtraction of the pressure (cavity_unsteady.py:109)
+        p_ex = (p_ex.reshape(-1, n2) - p_ex.reshape(-1, n2).mean(axis=1, keepdims=True)).reshape(-1)
+    else:
+        u_ex, v_ex, p_ex = (load_unsteady_fem_fields(fem_fields, len(time_vec)) if isinstance(fem_fields, str)
+                            else tuple(np.asarray(a, dtype=np.float64).reshape(-1) for a in fem_fields))
+        if not (u_ex.shape[0] == v_ex.shape[0] == p_ex.shape[0] == grid.shape[0]):
+            raise ValueError(f"FEM fields hold {u_ex.shape[0]} values, the space-time grid {grid.shape[0]} "
+                             f"({len(time_vec)} time steps x {n2} vertices)")
     d.consts = {"norm_vel": max(spread(u_ex), spread(v_ex)), "norm_pre": spread(p_ex), "T": T}
     fields_norm = [u_ex / d.norm_vel, v_ex / d.norm_vel, p_ex / d.norm_pre]
     d.x_pde = _collocation(grid, idx, o.n_pts["PDE"], rng, [0, 0, 0], [T, 1, 1])

@@ -131,12 +131,103 @@ def test_model_json_and_weights_export(tmp_path):
     assert [l["config"].get("units") for l in j["config"]["layers"][1:]] == [32, 32, 32, 3]
     model.save_weights(str(tmp_path / "Weights.npz"))
     w = np.load(tmp_path / "Weights.npz")
-    assert w["dense_0/kernel:0"].shape == (2, 32) and w["dense_3/bias:0"].shape == (3,)
+    # the dataset paths of Keras' Weights.h5 (Test_Case folders: dense_N/dense_N/kernel:0)
+    assert w["dense/dense/kernel:0"].shape == (2, 32) and w["dense_3/dense_3/bias:0"].shape == (3,)
     m2 = ns.TanhMLP(2, [32, 32, 32], 3, device="cpu")
     m2.set_weights(model.get_weights())
     assert torch.equal(m2.flat, model.flat)
     lim = np.sqrt(6.0 / (2 + 32))
     assert float(model.variables[0].abs().max()) <= lim and float(model.variables[1].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("name", ["Weights.h5", "Weights.npz"])
+def test_weights_round_trip(tmp_path, name):
+    """model.save_weights / load_weights (cavity_steady.py:252): the HDF5 file carries Keras' dataset paths, is read
+    back by the same reader that reads the reference's Weights.h5, and restores the flat vector bit for bit."""
+    from pinns_fluid_dynamics_b200 import h5lite
+    model = ns.TanhMLP(3, [32] * 3, 3, device="cpu", seed=7)
+    with torch.no_grad():
+        model.variables[1].uniform_(-0.1, 0.1)          # non-zero biases so their order matters
+        model.variables[5].uniform_(-0.1, 0.1)
+    path = str(tmp_path / name)
+    model.save_weights(path)
+    if name.endswith(".h5"):
+        f = h5lite.H5File(path)
+        assert f["dense_2/dense_2/kernel:0"].shape == (32, 32) and f["dense/dense/bias:0"].shape == (32,)
+        assert f["dense_3/dense_3/kernel:0"].dtype == np.float64      # the reference's files are float64 (Model.json)
+    other = ns.TanhMLP(3, [32] * 3, 3, device="cpu", seed=8)
+    assert not torch.equal(other.flat, model.flat)
+    other.load_weights(path)
+    assert torch.equal(other.flat, model.flat)
+    with pytest.raises(ValueError):
+        ns.TanhMLP(2, [32] * 3, 3, device="cpu").load_weights(path)     # wrong architecture
+
+
+def test_h5_writer_many_layers_and_nested_groups(tmp_path):
+    """the writer's group B-tree over more links than one symbol-table node holds (8x128 network: 9 layers + nesting)"""
+    from pinns_fluid_dynamics_b200 import h5lite
+    rng = np.random.default_rng(0)
+    data = {f"g{i}/sub/x{j}": rng.standard_normal((i + 1, j + 2)).astype(np.float32 if j % 2 else np.float64)
+            for i in range(11) for j in range(3)}
+    data["top"] = np.arange(5, dtype=np.int32)
+    h5lite.write_h5(str(tmp_path / "t.h5"), data)
+    f = h5lite.H5File(str(tmp_path / "t.h5"))
+    for k, v in data.items():
+        got = f[k]
+        assert got.dtype == v.dtype and np.array_equal(got, v), k
+    m = ns.TanhMLP(3, [128] * 8, 3, device="cpu", seed=1)
+    m.save_weights(str(tmp_path / "w.h5"))
+    m2 = ns.TanhMLP(3, [128] * 8, 3, device="cpu", seed=2)
+    m2.load_weights(str(tmp_path / "w.h5"))
+    assert torch.equal(m.flat, m2.flat)
+
+
+def test_unsteady_fem_files_are_read_like_the_script(tmp_path):
+    """cavity_unsteady.py:103-113: one HDF5 file per time step (VisualisationVector/0 velocity, /1 pressure), the pressure
+    of every step minus ITS OWN mean, steps concatenated in time order over the (t, y, x) grid."""
+    from pinns_fluid_dynamics_b200 import h5lite
+    n_times, n = 3, 101 * 101
+    rng = np.random.default_rng(5)
+    vel = rng.standard_normal((n_times, n, 3))
+    pre = rng.standard_normal((n_times, n)) + np.array([10.0, -3.0, 0.5])[:, None]
+    for t in range(n_times):
+        h5lite.write_h5(str(tmp_path / f"navier-stokes_SI_cavity_unsteady_{t:05d}.h5"),
+                        {"VisualisationVector/0": vel[t], "VisualisationVector/1": pre[t][:, None],
+                         "Mesh/0/mesh/geometry": np.zeros((n, 2))})
+    u, v, p = problems.load_unsteady_fem_fields(str(tmp_path), n_times)
+    assert np.array_equal(u, vel[:, :, 0].reshape(-1)) and np.array_equal(v, vel[:, :, 1].reshape(-1))
+    assert np.allclose(p.reshape(n_times, n).mean(axis=1), 0.0, atol=1e-12)
+    assert np.allclose(p, (pre - pre.mean(axis=1, keepdims=True)).reshape(-1))
+    kw = dict(PDE=300, BC=20, IC=20, Vel=10, Pres=5, Test=10, noise_bnd=0.0, noise_fit=0.0, n_times=n_times)
+    d = problems.cavity_unsteady(seed=2, fem_fields=str(tmp_path), **kw)
+    assert d.norm_vel == pytest.approx(max(np.ptp(u), np.ptp(v))) and d.norm_pre == pytest.approx(np.ptp(p))
+    # the fitting targets are the file values at the sampled grid rows over the normalisation (cavity_unsteady.py:115-123,163)
+    d2 = problems.cavity_unsteady(seed=2, fem_fields=(u, v, p), **kw)
+    assert np.array_equal(d.x_pde, d2.x_pde)
+    for a, b in zip(jax_free_leaves(d), jax_free_leaves(d2)):
+        assert np.array_equal(a, b)
+    with pytest.raises(FileNotFoundError):
+        problems.load_unsteady_fem_fields(str(tmp_path), n_times + 1)
+    with pytest.raises(ValueError):
+        problems.cavity_unsteady(seed=2, fem_fields=(u[:-1], v[:-1], p[:-1]), **kw)
+
+
+def jax_free_leaves(d):
+    """every numpy array a ProblemData holds (point sets and targets), in a fixed order"""
+    out = []
+    for key in sorted(vars(d)):
+        val = getattr(d, key)
+        if isinstance(val, np.ndarray):
+            out.append(val)
+        elif isinstance(val, dict):
+            out += [val[k] for k in sorted(val) if isinstance(val[k], np.ndarray)]
+        elif isinstance(val, (list, tuple)):
+            for item in val:
+                if isinstance(item, np.ndarray):
+                    out.append(item)
+                elif isinstance(item, dict):
+                    out += [item[k] for k in sorted(item) if isinstance(item[k], np.ndarray)]
+    return out
 
 
 def test_host_objective_matches_evaluate():

@@ -403,6 +403,18 @@ def run_ours(args):
     ms_e2e = float(t.item())
     e2e_value = n_global_pde * args.steps / (ms_e2e * 1e-3)
     sampler.stop()
+    # every rank samples its own GPU: a weak-scaling step waits for the slowest one, so the line carries all of them
+    clocks = sampler.summary()
+    if world > 1:
+        mine = torch.tensor([float(clocks["sm_mhz"] or 0), float(sum(1 << i for i, r in enumerate(
+            ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")) if r in clocks["reasons"]))],
+            dtype=torch.float64, device=dev)
+        allc = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allc, mine)
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        clocks["per_rank_sm_mhz"] = [int(c[0].item()) for c in allc]
+        clocks["reasons"] = sorted({n for c in allc for i, n in enumerate(names) if int(c[1].item()) >> i & 1})
+        clocks["sm_mhz_min_over_ranks"] = min(clocks["per_rank_sm_mhz"])
 
     # ---- the other BASELINE.json configs and strong scaling: device-timed steps, a few iterations each -----------------
     def time_config(config, total_pde, steps, warm):
@@ -478,7 +490,7 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "other_configs": others,
             "strong_scaling": strong,
-            "clocks": sampler.summary(),
+            "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -196,6 +196,7 @@ def minimize_bfgs_device(pb, maxiter: int, callback: Optional[Callable[[], None]
     # (at 10 k collocation points the launches, not the kernels, set the pace).  PINN_BFGS_GRAPH=0 keeps it eager.
     use_graph = os.environ.get("PINN_BFGS_GRAPH", "1") != "0" and not getattr(plan, "timing_enabled", False)
     alpha_host = torch.zeros(1, dtype=torch.float64, pin_memory=True)
+    alpha_np, scal_np = alpha_host.numpy(), scal_host.numpy()      # views of the pinned buffers: scalar access without tensor overhead
     alpha_dev = torch.zeros(1, **f64)
     graphs = {"eval": None, "accept": None}
 
@@ -241,11 +242,11 @@ def minimize_bfgs_device(pb, maxiter: int, callback: Optional[Callable[[], None]
         else:
             enqueue()
         torch.cuda.current_stream(dev).synchronize()
-        return scal_host
+        return scal_np
 
     def evaluate(alpha: float):
         """phi(alpha), phi'(alpha), |g|_inf at x + alpha p"""
-        alpha_host[0] = float(alpha)
+        alpha_np[0] = alpha
         h = run("eval", enqueue_eval)
         nfev[0] += 1
         return float(h[0]), float(h[1]), float(h[2])

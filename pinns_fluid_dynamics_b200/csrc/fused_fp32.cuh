@@ -1301,4 +1301,31 @@ finalize_rows_kernel(const float* __restrict__ ws, int rows, int stride, int i_b
   }
 }
 
+// the same over the columns [i_begin, i_end) only (the layered tensor-core engine: rows are wider than the output vector)
+__global__ void __launch_bounds__(1024)
+finalize_rows_range_kernel(const float* __restrict__ ws, int rows, int stride, int i_begin, int i_end, float* __restrict__ out) {
+  __shared__ float part[32][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = i_begin + blockIdx.x * 32 + lane;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (i < i_end) {
+    int r = warp;
+    for (; r + 96 < rows; r += 128) {
+      s0 += ws[(size_t)r * stride + i];
+      s1 += ws[(size_t)(r + 32) * stride + i];
+      s2 += ws[(size_t)(r + 64) * stride + i];
+      s3 += ws[(size_t)(r + 96) * stride + i];
+    }
+    for (; r < rows; r += 32) s0 += ws[(size_t)r * stride + i];
+  }
+  part[warp][lane] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (warp == 0 && i < i_end) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 32; ++w) s += part[w][lane];
+    out[i] = s;
+  }
+}
+
 }  // namespace pinn

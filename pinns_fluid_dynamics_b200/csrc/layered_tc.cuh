@@ -622,15 +622,17 @@ constexpr int kWgSmem = kWgBarOff + 128 + kH * 4;
 // slabs: 16-row slabs of the batch; a tile holds NR/16 of them (NR % 16 == 0); value-channel rows are the
 // first P rows of a tile = its first P/16 slabs when P % 16 == 0 -- in general rows [0, P): checked per chunk.
 __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad(const float* __restrict__ act_prev, const float* __restrict__ zbar,
-                                                          long long n_slabs, int NR, int P, float* __restrict__ gK,
-                                                          float* __restrict__ gb) {
+                                                          long long n_slabs, int NR, int P, float* __restrict__ rows,
+                                                          size_t row_stride, size_t off_gk) {
+  // this CTA's own workspace row (summed over the rows in a fixed order afterwards: no atomics, bit-reproducible)
+  float* __restrict__ gK = rows + (size_t)blockIdx.x * row_stride + off_gk;
+  float* __restrict__ gb = gK + (size_t)kH * kH;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kWgBarOff);
   uint64_t* empty = full + kWgStages;
   uint64_t* tfull = empty + kWgStages;   // [2]
   uint64_t* tempty = tfull + 2;          // [2]
   uint32_t* tslot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* sB = reinterpret_cast<float*>(smem + kWgBarOff + 128);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int slabs_per_tile = NR / kWgRows;
   const long long my_stages = n_slabs > (long long)blockIdx.x ? (n_slabs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -640,7 +642,6 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad(const float* __restric
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
     fence_barrier_init();
   }
-  if (tid < kH) sB[tid] = 0.f;
   if (warp == kWgMmaWarp) umma::tmem_alloc<256>(tslot);
   umma::fence_before_thread_sync();
   __syncthreads();
@@ -702,11 +703,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad(const float* __restric
       if (st + G < n_slabs) { issue(st + 3 * G, va, ra); consume(vb, rb); }
       if (st + 2 * G < n_slabs) { issue(st + 4 * G, vb, rb); consume(vc, rcv); }
     }
-    // bias gradient: thread (tid, u) always holds neuron 8*(ig0 + 4u) + i7
+    // bias gradient: thread (tid, u) always holds neuron 8*(ig0 + 4u) + i7; its four row chunks rc (lane bits 3, 4) are added
+    // in a fixed order and the rc == 0 lane -- the only owner of that neuron in the CTA -- adds the sum to the CTA's row
 #pragma unroll
-    for (int u = 0; u < 4; ++u) atomicAdd(&sB[8 * (ig0 + 4 * u) + i7], bsum[u]);
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (my_stages > 0) atomicAdd(gb + tid, sB[tid]);
+    for (int u = 0; u < 4; ++u) {
+      float b = bsum[u];
+      b += __shfl_xor_sync(0xffffffffu, b, 8);
+      b += __shfl_xor_sync(0xffffffffu, b, 16);
+      if (rc == 0 && my_stages > 0) gb[8 * (ig0 + 4 * u) + i7] += b;
+    }
   } else if (warp < 8) {
     // ===== drain warps: chunk partial sums -> FP32 registers -> global atomics =====
     const int q = warp & 3;
@@ -732,8 +737,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad(const float* __restric
       if (lane == 0) mbar_arrive(&tempty[buf]);
     }
     if (my_chunks > 0) {
+      float4* g4 = reinterpret_cast<float4*>(gK + (size_t)i * kH);       // row i of this CTA's K-bar block: one owner thread
 #pragma unroll
-      for (int c = 0; c < kH; ++c) atomicAdd(gK + (size_t)i * kH + c, acc[c]);
+      for (int c = 0; c < kH; c += 4) {
+        float4 t = g4[c >> 2];
+        t.x += acc[c]; t.y += acc[c + 1]; t.z += acc[c + 2]; t.w += acc[c + 3];
+        g4[c >> 2] = t;
+      }
     }
   } else if (warp == kWgMmaWarp && lane == 0) {
     const uint32_t idesc = umma::idesc_tf32(kH, kH);
@@ -774,6 +784,17 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad(const float* __restric
   if (warp == kWgMmaWarp) umma::tmem_dealloc<256>(tmem);
 }
 
+// sum of v over the first `nact` lanes of a warp (the other lanes are not in the branch), fixed order; result in lane 0
+__device__ __forceinline__ float warp_sum_active(float v, int lane, int nact) {
+  const unsigned mask = nact >= 32 ? 0xffffffffu : ((1u << nact) - 1u);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float other = __shfl_down_sync(mask, v, o);
+    if (lane + o < nact) v += other;
+  }
+  return v;
+}
+
 // ---- output layer + residuals + adjoint (SIMT), one tile per CTA iteration ---------------------------
 // phase 1  thread = (point, k-slice): partial output jets J[c][o] over its slice of the 128 neurons (consecutive
 //          lanes = consecutive points = consecutive 4-byte words of the 16-byte chunks), slices summed through
@@ -783,23 +804,27 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad(const float* __restric
 template <int D, int O, int ORDER, bool TRAIN>
 __global__ void __launch_bounds__(256) tc_out_layer(const float* __restrict__ params, int off_ko, const SegDev* __restrict__ segs,
                                                     const TileDev* __restrict__ tiles, int n_tiles, float* __restrict__ actL,
-                                                    float* __restrict__ grad, float* __restrict__ sumsq) {
+                                                    float* __restrict__ rows, size_t row_stride, int n_params) {
+  // this CTA's own workspace row: [gradient | term sums], summed over the rows in a fixed order afterwards
+  float* __restrict__ grad = rows + (size_t)blockIdx.x * row_stride;
+  float* __restrict__ sumsq = grad + n_params;
   using G = Geo<D, ORDER>;
   constexpr int C = G::C, P = G::P, NR = G::NR, H = kH, CO = C * O;
+  constexpr int PW = (P + 31) / 32;                 // warps that hold points in the residual phase
   constexpr int SX = D - 2, SY = D - 1;
   constexpr int NS = 256 / P;                       // k-slices in phase 1
   constexpr int KS = (H + NS - 1) / NS;
   __shared__ float sKo[H * 4];
   __shared__ float sJp[NS * P * CO];
   __shared__ float sJb[P * CO];
-  __shared__ float sSq[kMaxTerms];
-  __shared__ float sGbo[kMaxOut];
+  __shared__ float sSq[PW][kMaxTerms];              // per-warp partial sums, added in warp order
+  __shared__ float sGbo[PW][kMaxOut];
+  __shared__ float sGko[H * O];                     // K_out gradient partials of the h2 == 1 threads
   const int tid = threadIdx.x;
   const float* Ko = params + off_ko;
   const float* bo = Ko + H * O;
   for (int i = tid; i < H * 4; i += 256) sKo[i] = (i & 3) < O ? __ldg(Ko + (i >> 2) * O + (i & 3)) : 0.f;
-  if (tid < kMaxTerms) sSq[tid] = 0.f;
-  if (tid < kMaxOut) sGbo[tid] = 0.f;
+  float gbo_acc = 0.f;                              // thread o < O: b_out gradient of this CTA over all its tiles
   __syncthreads();
   // phase-2 identity
   const int k2 = tid & (H - 1), h2 = tid >> 7;
@@ -840,6 +865,8 @@ __global__ void __launch_bounds__(256) tc_out_layer(const float* __restrict__ pa
     }
     __syncthreads();
     if (tid < P) {
+      const int lane1 = tid & 31, warp1 = tid >> 5;
+      const int nact1 = P - 32 * warp1 < 32 ? P - 32 * warp1 : 32;      // lanes of this warp that hold points
       const long long gp = p_begin + tid;
       const bool valid = gp < n;
       float J[C][O], Jb[C][O];
@@ -880,7 +907,10 @@ __global__ void __launch_bounds__(256) tc_out_layer(const float* __restrict__ pa
         }
         if (T->rhs != nullptr && valid) r = fmaf(-__ldg(&T->rhs_scale), __ldg(T->rhs + gp), r);
         if (!valid) r = 0.f;
-        atomicAdd(&sSq[t], r * r);
+        {
+          const float sq = warp_sum_active(r * r, lane1, nact1);
+          if (lane1 == 0) sSq[warp1][t] = sq;
+        }
         if constexpr (TRAIN) {
           const float rb = __ldg(&T->scale) * r;
 #pragma unroll
@@ -907,14 +937,25 @@ __global__ void __launch_bounds__(256) tc_out_layer(const float* __restrict__ pa
 #pragma unroll
           for (int o = 0; o < O; ++o) sJb[tid * CO + c * O + o] = Jb[c][o];
 #pragma unroll
-        for (int o = 0; o < O; ++o) atomicAdd(&sGbo[o], Jb[0][o]);
+        for (int o = 0; o < O; ++o) {
+          const float g = warp_sum_active(Jb[0][o], lane1, nact1);
+          if (lane1 == 0) sGbo[warp1][o] = g;
+        }
       }
     }
     __syncthreads();
     // this tile's sums of squares go to its own set's slots (tiles of several sets share the launch)
     if (tid < n_terms && (!TRAIN || seg->terms[tid].train)) {
-      atomicAdd(sumsq + seg->terms[tid].out_index, sSq[tid]);
-      sSq[tid] = 0.f;
+      float sq = 0.f;
+#pragma unroll
+      for (int w = 0; w < PW; ++w) sq += sSq[w][tid];
+      sumsq[seg->terms[tid].out_index] += sq;
+    }
+    if constexpr (TRAIN) {
+      if (tid < O) {
+#pragma unroll
+        for (int w = 0; w < PW; ++w) gbo_acc += sGbo[w][tid];
+      }
     }
     if constexpr (TRAIN) {
       // ---- phase 2 ----
@@ -957,21 +998,29 @@ __global__ void __launch_bounds__(256) tc_out_layer(const float* __restrict__ pa
     __syncthreads();      // sJp / sJb are reused by the next tile
   }
   if constexpr (TRAIN) {
+    // neuron k2 lives in two threads (h2 = 0, 1): the h2 == 1 partial goes through shared memory, h2 == 0 adds and owns the slot
+    if (h2 == 1) {
 #pragma unroll
-    for (int o = 0; o < O; ++o) atomicAdd(grad + off_ko + k2 * O + o, gko[o]);
-    if (tid < O) atomicAdd(grad + off_ko + H * O + tid, sGbo[tid]);
+      for (int o = 0; o < O; ++o) sGko[k2 * O + o] = gko[o];
+    }
+    __syncthreads();
+    if (h2 == 0) {
+#pragma unroll
+      for (int o = 0; o < O; ++o) grad[off_ko + k2 * O + o] += gko[o] + sGko[k2 * O + o];
+    }
+    if (tid < O) grad[off_ko + H * O + tid] += gbo_acc;
   }
 }
 
 // ---- K1 / b1 gradients from z-bar_1 (SIMT): thread = (neuron, 4-point group), block-strided over tiles ------
 template <int D, int ORDER>
 __global__ void __launch_bounds__(256) tc_layer1_grad(const float* __restrict__ zbar1, const SegDev* __restrict__ segs,
-                                                      const TileDev* __restrict__ tiles, int n_tiles, float* __restrict__ grad) {
+                                                      const TileDev* __restrict__ tiles, int n_tiles, float* __restrict__ rows,
+                                                      size_t row_stride) {
+  float* __restrict__ grad = rows + (size_t)blockIdx.x * row_stride;     // this CTA's own workspace row
   using G = Geo<D, ORDER>;
   constexpr int P = G::P, NR = G::NR;
   __shared__ float sG[(1 + D) * kH];
-  for (int i = threadIdx.x; i < (1 + D) * kH; i += blockDim.x) sG[i] = 0.f;
-  __syncthreads();
   const int j = threadIdx.x & (kH - 1), gj = threadIdx.x >> 7;
   float gk[D], gbv = 0.f;
 #pragma unroll
@@ -1002,11 +1051,18 @@ __global__ void __launch_bounds__(256) tc_layer1_grad(const float* __restrict__ 
       }
     }
   }
-  atomicAdd(&sG[D * kH + j], gbv);
+  // neuron j lives in two threads (gj = 0, 1): gj == 1 hands its partials over through shared memory, gj == 0 owns the slots
+  if (gj == 1) {
+    sG[D * kH + j] = gbv;
 #pragma unroll
-  for (int i = 0; i < D; ++i) atomicAdd(&sG[i * kH + j], gk[i]);
+    for (int i = 0; i < D; ++i) sG[i * kH + j] = gk[i];
+  }
   __syncthreads();
-  for (int i = threadIdx.x; i < (1 + D) * kH; i += blockDim.x) atomicAdd(grad + i, sG[i]);   // [K1 | b1] are contiguous
+  if (gj == 0) {
+    grad[D * kH + j] += gbv + sG[D * kH + j];                             // [K1 | b1] are contiguous
+#pragma unroll
+    for (int i = 0; i < D; ++i) grad[i * kH + j] += gk[i] + sG[i * kH + j];
+  }
 }
 
 }  // namespace tc

@@ -105,6 +105,9 @@ struct pinn_plan {
   bool tc = false;               // layered_tf32x3: tcgen05 hidden layers (H = 128)
   float* wimg = nullptr;         // tc: hi/lo operand images of K_l and K_l^T
   size_t layer_stride = 0;       // tc: floats between per-layer jet buffers
+  float* tc_rows = nullptr;      // tc: one [P + T] row per CTA of the accumulating kernels (summed in a fixed order: no atomics)
+  int tc_row_count = 0;
+  size_t tc_row_stride = 0;
   bool timing = false;
   cudaEvent_t ev0[3] = {nullptr, nullptr, nullptr}, ev1[3] = {nullptr, nullptr, nullptr};
   bool ev_valid[3] = {false, false, false};
@@ -375,6 +378,12 @@ static int tc_alloc(pinn_plan* p) {
   p->ws_bytes = act_bytes + img_bytes;
   if (cudaMalloc(&p->act, act_bytes) != cudaSuccess) return fail(PINN_E_ALLOC, "cannot allocate %zu activation bytes", act_bytes);
   if (cudaMalloc(&p->wimg, img_bytes) != cudaSuccess) return fail(PINN_E_ALLOC, "cannot allocate weight images");
+  // per-CTA accumulation rows: the widest accumulating launch (tc_out_layer) has 4 CTAs per SM
+  p->tc_row_count = 4 * p->num_sms;
+  p->tc_row_stride = (size_t)((p->P + p->T + 31) / 32) * 32;
+  const size_t row_bytes = (size_t)p->tc_row_count * p->tc_row_stride * 4;
+  if (cudaMalloc(&p->tc_rows, row_bytes) != cudaSuccess) return fail(PINN_E_ALLOC, "cannot allocate %zu bytes of accumulation rows", row_bytes);
+  p->ws_bytes += row_bytes;
   return PINN_OK;
 }
 
@@ -445,16 +454,19 @@ static int tc_run_order(pinn_plan* p, const float* params, float* out, cudaStrea
     }
     const int grid_out = tiles < 4 * p->num_sms ? tiles : 4 * p->num_sms;
     if (train)
-      tc::tc_out_layer<D, O, ORDER, true><<<grid_out, 256, 0, st>>>(params, off_ko, lt.segs_dev, td, tiles, act(L), out, out + p->P);
+      tc::tc_out_layer<D, O, ORDER, true><<<grid_out, 256, 0, st>>>(params, off_ko, lt.segs_dev, td, tiles, act(L), p->tc_rows,
+                                                                    p->tc_row_stride, (int)p->P);
     else
-      tc::tc_out_layer<D, O, ORDER, false><<<grid_out, 256, 0, st>>>(params, off_ko, lt.segs_dev, td, tiles, act(L), out, out + p->P);
+      tc::tc_out_layer<D, O, ORDER, false><<<grid_out, 256, 0, st>>>(params, off_ko, lt.segs_dev, td, tiles, act(L), p->tc_rows,
+                                                                     p->tc_row_stride, (int)p->P);
     *launches += L + 1;
     if (train) {
       const long long n_slabs = (long long)tiles * (G::NR / tc::kWgRows);
       const int gw = (int)(n_slabs < p->num_sms ? n_slabs : p->num_sms);
       for (int l = L; l >= 2; --l) {
-        float* gK = out + D * H + H + (size_t)(l - 2) * (H * H + H);
-        tc::tc_wgrad<<<gw, tc::kWgThreads, tc::kWgSmem, st>>>(act(l - 1), act(l), n_slabs, G::NR, G::P, gK, gK + H * H);
+        const size_t off_gk = (size_t)(D * H + H) + (size_t)(l - 2) * (H * H + H);
+        tc::tc_wgrad<<<gw, tc::kWgThreads, tc::kWgSmem, st>>>(act(l - 1), act(l), n_slabs, G::NR, G::P, p->tc_rows, p->tc_row_stride,
+                                                              off_gk);
         const float* img = p->wimg + (size_t)(l - 2) * tc::kLayerImgFloats + 2 * tc::kImgFloats;
         if (l > 2)
           tc::tc_layer<D, ORDER, 1><<<grid, tc::kLayerThreads, S::TOTAL, st>>>(img, nullptr, act(l), act(l - 1), params, tiles);
@@ -463,7 +475,7 @@ static int tc_run_order(pinn_plan* p, const float* params, float* out, cudaStrea
         *launches += 2;
       }
       const int g1 = tiles < 2 * p->num_sms ? tiles : 2 * p->num_sms;
-      tc::tc_layer1_grad<D, ORDER><<<g1, 256, 0, st>>>(act(1), lt.segs_dev, td, tiles, out);
+      tc::tc_layer1_grad<D, ORDER><<<g1, 256, 0, st>>>(act(1), lt.segs_dev, td, tiles, p->tc_rows, p->tc_row_stride);
       ++*launches;
     }
     CUDA_TRY(cudaGetLastError());
@@ -493,7 +505,15 @@ static int tc_run_t(pinn_plan* p, const float* params, float* out, cudaStream_t 
 static int run_tc(pinn_plan* p, const float* params, float* out, cudaStream_t st, bool train) {
   const pinn_mlp_desc& m = p->mlp;
   const int i_begin = train ? 0 : (int)p->P;
-  CUDA_TRY(cudaMemsetAsync(out + i_begin, 0, sizeof(float) * (size_t)(p->P + p->T - i_begin), st));
+  // every accumulating kernel adds into its CTAs' own rows; rows_used = the widest grid any launch of this step can have
+  long long max_tiles = 1;
+  for (int o = 0; o < 3; ++o) {
+    const long long t = (long long)(train ? p->train[o] : p->eval[o]).tiles_host.size();
+    if (t > max_tiles) max_tiles = t;
+  }
+  // (tc_wgrad strides over 16-row slabs: up to 15 per tile)
+  const int rows_used = (int)(15 * max_tiles < p->tc_row_count ? 15 * max_tiles : p->tc_row_count);
+  CUDA_TRY(cudaMemsetAsync(p->tc_rows, 0, sizeof(float) * (size_t)rows_used * p->tc_row_stride, st));
   int launches = 0;
   dim3 g(16, m.n_hidden - 1);
   tc::tc_prep_weights<<<g, 256, 0, st>>>(params, m.in_dim * m.width + m.width, m.width * m.width + m.width, p->wimg);
@@ -501,6 +521,14 @@ static int run_tc(pinn_plan* p, const float* params, float* out, cudaStream_t st
   int rc = PINN_E_INVALID;
   if (m.in_dim == 3) rc = tc_run_t<3, 3>(p, params, out, st, train, &launches);
   else if (m.in_dim == 2) rc = tc_run_t<2, 3>(p, params, out, st, train, &launches);
+  if (rc == PINN_OK) {
+    // fixed-order sum of the rows -> out[i_begin .. P + T): the result does not depend on scheduling (bit-reproducible)
+    const int n_out = (int)(p->P + p->T);
+    if (n_out > i_begin)      // (a values-only forward through a temporary plan has no terms: nothing to sum)
+      finalize_rows_range_kernel<<<(n_out - i_begin + 31) / 32, 1024, 0, st>>>(p->tc_rows, rows_used, (int)p->tc_row_stride, i_begin, n_out, out);
+    CUDA_TRY(cudaGetLastError());
+    ++launches;
+  }
   p->last_launches = launches;
   return rc;
 }
@@ -566,13 +594,23 @@ extern "C" int pinn_plan_create(const pinn_mlp_desc* mlp, const pinn_pointset_de
     // the highest derivative order instead of getting kernels of their own: their residual coefficients on the extra
     // channels are zero, the value channel is computed by the same instruction sequence, and the step loses a launch
     // and its tail.  Only when they are at most 1/16 of that launch.
-    long long chunks[3] = {0, 0, 0};
+    // Also when they fit into the idle part of that launch's last wave (10 k collocation points are 79 tiles of 128 points on
+    // 148 SMs: the boundary tiles run beside them for free and the step is one launch instead of three).
+    const bool tc_tiles = tcgen05_supported(*mlp);
+    const long long per_unit = tc_tiles ? 8 : 1;                       // chunks per work unit: 128-point tile | 16-point chunk
+    const long long wave = tc_tiles ? p->num_sms : 8LL * p->num_sms;   // work units in flight: one tile per CTA | one chunk per warp
+    long long chunks[3] = {0, 0, 0}, units[3] = {0, 0, 0};
     for (const pinn_pointset_desc& ps : p->sets)
-      if (ps.n_local > 0 && ps.n_terms > 0) chunks[ps.deriv_order] += (ps.n_local + kChunk - 1) / kChunk;
+      if (ps.n_local > 0 && ps.n_terms > 0) {
+        const long long c = (ps.n_local + kChunk - 1) / kChunk;
+        chunks[ps.deriv_order] += c;
+        units[ps.deriv_order] += (c + per_unit - 1) / per_unit;
+      }
     int top = chunks[2] ? 2 : (chunks[1] ? 1 : 0);
-    long long lower = 0;
-    for (int o = 0; o < top; ++o) lower += chunks[o];
-    if (top > 0 && lower > 0 && lower * 16 <= chunks[top] && !(getenv("PINN_NO_PROMOTE") && atoi(getenv("PINN_NO_PROMOTE"))))
+    long long lower = 0, lower_units = 0;
+    for (int o = 0; o < top; ++o) { lower += chunks[o]; lower_units += units[o]; }
+    const bool rides_free = (units[top] + lower_units + wave - 1) / wave == (units[top] + wave - 1) / wave;
+    if (top > 0 && lower > 0 && (lower * 16 <= chunks[top] || rides_free) && !(getenv("PINN_NO_PROMOTE") && atoi(getenv("PINN_NO_PROMOTE"))))
       for (pinn_pointset_desc& ps : p->sets) ps.deriv_order = top;
     p->tcgen05 = tcgen05_supported(*mlp);
   }
@@ -686,6 +724,7 @@ extern "C" int pinn_plan_destroy(pinn_plan* p) {
   if (p->act) cudaFree(p->act);
   if (p->wt) cudaFree(p->wt);
   if (p->wimg) cudaFree(p->wimg);
+  if (p->tc_rows) cudaFree(p->tc_rows);
   for (int o = 0; o < 3; ++o) {
     if (p->ev0[o]) cudaEventDestroy(p->ev0[o]);
     if (p->ev1[o]) cudaEventDestroy(p->ev1[o]);
@@ -870,6 +909,8 @@ extern "C" int pinn_forward(const pinn_mlp_desc* mlp, const float* params_dev, c
     if (tmp.act) cudaFree(tmp.act);
     if (tmp.wt) cudaFree(tmp.wt);
     if (tmp.wimg) cudaFree(tmp.wimg);
+    if (tmp.tc_rows) cudaFree(tmp.tc_rows);
+    tmp.tc_rows = nullptr;
     tmp.act = tmp.wt = tmp.wimg = nullptr;
     if (tmp.eval[0].tiles_dev) cudaFree(tmp.eval[0].tiles_dev);
     tmp.eval[0].tiles_dev = nullptr;

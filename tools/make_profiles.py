@@ -111,6 +111,9 @@ with open(os.path.join(root, "profiles", f"sass_fused_tc_{tag}.txt"), "w") as fh
     fh.write("# cuobjdump -sass of fused_tc_kernel<2,3,TRAIN> in pinns_fluid_dynamics_b200/lib/libpinnstep.so\n# static opcode histogram:\n")
     for op, c in hist.most_common():
         fh.write(f"#   {op:14s} {c}\n")
-    fh.write(sass)
+    for l in sass.split("\n"):                                  # drop the instruction encodings: keep `/*offset*/ instruction ;`
+        l = re.sub(r"\s*/\* 0x[0-9a-f]{16} \*/\s*$", "", l)
+        if l.strip():
+            fh.write(l.rstrip() + "\n")
 print(json.dumps(out, indent=1))
 print("UTCHMMA static:", hist.get("UTCHMMA"), "HMMA static:", hist.get("HMMA"), "LDTM:", hist.get("LDTM"), "STTM:", hist.get("STTM"))

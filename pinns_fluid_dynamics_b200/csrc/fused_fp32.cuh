@@ -35,20 +35,15 @@
 #include "common.cuh"
 #include "umma.cuh"
 
-// Build-time switches of the H = 32 tensor path.  The defaults are the shipped kernel; the others are the variants measured
-// in DESIGN.md section 6 (accuracy / speed table) and are kept so those measurements can be repeated
-// (nvcc -D..., load the result with PINN_LIBPINNSTEP=/path/to/lib.so).
+// Structural build-time switches of the H = 32 warp-level tensor path (engine "fused_tf32x3": the unsteady script's 3-32x3-3
+// network; 2-32x3-O networks run csrc/fused_tc.cuh).  The defaults are the shipped kernel.  The accuracy / speed variants of
+// DESIGN.md section 6 (truncating / cvt.rna splits, lo not rounded, k-steps accumulated in the tensor core, tf32-only weight
+// gradient) were measured in round 1 and have been removed from the source.
 #ifndef PINN_FUSED_MMA_WGRAD
 #define PINN_FUSED_MMA_WGRAD 1     // weight-gradient GEMM on mma.sync (0: the whole kernel stays FP32, like PINN_ENGINE=fused_fp32)
 #endif
 #ifndef PINN_FUSED_MMA_GEMM
 #define PINN_FUSED_MMA_GEMM 1      // forward / input-adjoint GEMMs on mma.sync as well
-#endif
-#ifndef PINN_FUSED_LO_RNA
-#define PINN_FUSED_LO_RNA 1        // round (not truncate) the lo part of an activation: +0x1000 before the hardware cut
-#endif
-#ifndef PINN_FUSED_KSTEP_DRAIN
-#define PINN_FUSED_KSTEP_DRAIN 1   // join the 4 k-steps of a forward / adjoint accumulator with FP32 FADDs (0: in the tensor core)
 #endif
 #ifndef PINN_FUSED_TMEM_TOTALS
 #define PINN_FUSED_TMEM_TOTALS 1   // running weight- and bias-gradient totals in tensor memory instead of 80 registers
@@ -56,17 +51,8 @@
 #ifndef PINN_FUSED_BWD_BF16
 #define PINN_FUSED_BWD_BF16 1      // input-adjoint GEMM: the same bf16 correction passes (needs 10 KB of bf16 weight images)
 #endif
-#ifndef PINN_FUSED_WGRAD_BF16
-#define PINN_FUSED_WGRAD_BF16 1    // weight gradient: correction passes lo*hi, hi*lo as bf16 m16n8k16 over pairs of k-steps
-#endif
 #ifndef PINN_FUSED_MAX_WARPS
 #define PINN_FUSED_MAX_WARPS 8     // 4: one warp per scheduler (33 k instead of 47 k cycles per chunk and warp: latency vs contention)
-#endif
-#ifndef PINN_FUSED_SPLIT_CVT
-#define PINN_FUSED_SPLIT_CVT 0     // hi by cvt.rna.tf32.f32 (4 SASS instructions on sm_100a: 5 % slower)
-#endif
-#ifndef PINN_FUSED_SPLIT_TRUNC
-#define PINN_FUSED_SPLIT_TRUNC 0   // raw operand as hi (the hardware truncates): 1 % faster, worst loss term 9e-6 -- rejected
 #endif
 
 namespace pinn {
@@ -385,19 +371,9 @@ __device__ __forceinline__ void warp_wgrad(const float* __restrict__ A, const fl
 // (30-36 MMAs) and is then added to the running totals with FADD.
 // Fragment loads are bank-conflict free with RS = 16C+4: A/B element (row g, col t) sits at g*RS + t, RS mod 32 = 4 | 20.
 __device__ __forceinline__ void tf32_hi_lo(float x, unsigned& hi, unsigned& lo) {
-#if PINN_FUSED_SPLIT_TRUNC
-  hi = __float_as_uint(x);                               // the tensor core reads the top 19 bits
-  lo = __float_as_uint(x - __uint_as_float(hi & 0xFFFFE000u));
-#elif PINN_FUSED_SPLIT_CVT
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  lo = __float_as_uint(x - __uint_as_float(hi));
-#else
   hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
   lo = __float_as_uint(x - __uint_as_float(hi));
-#if PINN_FUSED_LO_RNA
   lo += 0x1000u;      // the tensor core truncates the low 13 bits: adding half an ulp first makes that a round-to-nearest
-#endif                // (without it every product is biased towards zero by ~2^-24, which adds up over the layers)
-#endif
 }
 __device__ __forceinline__ void mma_m16n8k8_tf32(float (&d)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
   asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -474,7 +450,6 @@ __device__ __forceinline__ void warp_wgrad_mma(const float* __restrict__ A, cons
       for (int i = 0; i < 4; ++i) d[m][n][i] = 0.f;
   const float* ap = A + g * RS + t;
   const float* zp = Z + g * RS + t;
-#if PINN_FUSED_WGRAD_BF16
   // The gradient tolerance (1e-4) is loose next to the loss tolerance, so the two correction passes lo*hi and hi*lo run
   // as bf16 m16n8k16 MMAs over a PAIR of k-steps (their 2^-9 operand rounding sits on terms 2^-12 below the product:
   // 5e-7 per product), the main pass hi*hi stays tf32: 32 instead of 48 MMAs per pair.  The bf16 instruction's K index
@@ -532,39 +507,6 @@ __device__ __forceinline__ void warp_wgrad_mma(const float* __restrict__ A, cons
 #pragma unroll
         for (int n = 0; n < 4; ++n) mma_m16n8k8_tf32(d[m][n], ah[u][m], bh[u][n]);
   }
-#else
-#pragma unroll 2
-  for (int s = 0; s < 2 * C; ++s) {
-    unsigned ah[2][4], al[2][4], bh[4][2], bl[4][2];
-#pragma unroll
-    for (int m = 0; m < 2; ++m) {
-      const float* q = ap + 16 * m * RS + 8 * s;
-      tf32_hi_lo(q[0], ah[m][0], al[m][0]);
-      tf32_hi_lo(q[8 * RS], ah[m][1], al[m][1]);
-      tf32_hi_lo(q[4], ah[m][2], al[m][2]);
-      tf32_hi_lo(q[8 * RS + 4], ah[m][3], al[m][3]);
-    }
-#pragma unroll
-    for (int n = 0; n < 4; ++n) {
-      const float* q = zp + 8 * n * RS + 8 * s;
-      tf32_hi_lo(q[0], bh[n][0], bl[n][0]);
-      tf32_hi_lo(q[4], bh[n][1], bl[n][1]);
-    }
-    // pass-major: the 8 accumulators are independent, the three passes of one accumulator are 8 MMAs apart
-#pragma unroll
-    for (int m = 0; m < 2; ++m)
-#pragma unroll
-      for (int n = 0; n < 4; ++n) mma_m16n8k8_tf32(d[m][n], al[m], bh[n]);
-#pragma unroll
-    for (int m = 0; m < 2; ++m)
-#pragma unroll
-      for (int n = 0; n < 4; ++n) mma_m16n8k8_tf32(d[m][n], ah[m], bl[n]);
-#pragma unroll
-    for (int m = 0; m < 2; ++m)
-#pragma unroll
-      for (int n = 0; n < 4; ++n) mma_m16n8k8_tf32(d[m][n], ah[m], bh[n]);
-  }
-#endif
   if constexpr (Cfg::TMEM_TOTALS) {
     float tot[32];
     tmem_ld32(tmem_totals, tot);
@@ -617,7 +559,6 @@ __device__ __forceinline__ void warp_gemm_mma(const float* __restrict__ in, cons
       tf32_hi_lo(v0.y, ah[1], al[1]);
       tf32_hi_lo(v1.x, ah[2], al[2]);
       tf32_hi_lo(v1.y, ah[3], al[3]);
-#if PINN_FUSED_KSTEP_DRAIN
       // the tensor core truncates when it adds into its accumulator: the three passes of ONE k-step go into a fresh
       // accumulator (small lo-terms first, so only the final hi*hi addition sees a full-magnitude sum) and the k-steps
       // are joined in FP32 with round-to-nearest FADDs on the otherwise idle FMA pipe
@@ -636,14 +577,6 @@ __device__ __forceinline__ void warp_gemm_mma(const float* __restrict__ in, cons
       for (int n = 0; n < 4; ++n)
 #pragma unroll
         for (int i = 0; i < 4; ++i) d[c][n][i] += tacc[n][i];
-#else
-#pragma unroll
-      for (int n = 0; n < 4; ++n) mma_m16n8k8_tf32(d[c][n], al, bh[n]);
-#pragma unroll
-      for (int n = 0; n < 4; ++n) mma_m16n8k8_tf32(d[c][n], ah, bl[n]);
-#pragma unroll
-      for (int n = 0; n < 4; ++n) mma_m16n8k8_tf32(d[c][n], ah, bh[n]);
-#endif
     }
   }
 }

@@ -88,12 +88,6 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, uint32_t byte
 #ifndef PINN_TC_L2PF
 #define PINN_TC_L2PF 4
 #endif
-#ifndef PINN_TC_PFWARPS
-#define PINN_TC_PFWARPS 0
-#endif
-#ifndef PINN_TC_COALESCED
-#define PINN_TC_COALESCED 0
-#endif
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // round-to-nearest split: hi and lo are both exact TF32 values, so the tensor core's own truncation of its
 // operands loses nothing and the residual x - hi - lo (<= 2^-22 |x|) has no sign bias.  (A truncating split
@@ -316,19 +310,6 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer(const float* __rest
       }
       if (t >= T) return;
       const int tile = (int)blockIdx.x + (t / NKC) * (int)gridDim.x, kc = t % NKC;
-#if PINN_TC_COALESCED   // experiment (off): fully coalesced loads + 4x4 transposes by shuffles -- correct, but measured slower
-                       // (forward 260 -> 326 us per batch: the shuffles cost more data-pipe time than the loads save)
-      // line L = 16 it + 4 warp + rcl of the stage's 2*NRB 128-byte lines ([neuron group][row chunk]); lane = (kh, rcl, i)
-      // reads the 16-byte chunk of neuron 4 kh + i: a warp instruction covers 4 whole lines
-      const uint8_t* sbase = reinterpret_cast<const uint8_t*>(act_in + (size_t)tile * NR * kH) + (size_t)(kc * 2) * (NR * 32);
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int L = it * 16 + warp * 4 + ((lane >> 2) & 3);
-        if (L < 2 * NRB) v[it] = __ldg(reinterpret_cast<const float4*>(sbase + (size_t)L * 128 + ((lane >> 4) * 4 + (lane & 3)) * 16));
-        else v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      return;
-#endif
       const uint8_t* src = reinterpret_cast<const uint8_t*>(act_in + (size_t)tile * NR * kH) +
                            (size_t)(kc * 2 + (kb >> 1)) * (NR * 32) + (kb & 1) * 64;
 #pragma unroll
@@ -337,13 +318,8 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer(const float* __rest
         if (rb < NRB) {
           const float4* p = reinterpret_cast<const float4*>(src + rb * 128);
 #pragma unroll
-#ifdef PINN_TC_EXP_NOLOAD   // experiment: how much of the layer kernels is the HBM read stream?
-          for (int r = 0; r < 4; ++r) v[4 * u + r] = make_float4(0.25f, -0.5f, 0.125f, 1.f);
-          (void)p;
-#else
           ldg256(p, v[4 * u], v[4 * u + 1]);                             // v[4u + r] = neuron 4kb + r, rows 4rb..4rb+3
           ldg256(p + 2, v[4 * u + 2], v[4 * u + 3]);
-#endif
         }
       }
     };
@@ -353,32 +329,6 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer(const float* __rest
       ++t_cons;
       { TCP_T0(); mbar_wait(&empty[stage], phase ^ 1u); if (warp == 0) TCP_ADD(0); }
       uint8_t* dst = sStage + stage * S::STAGE;
-#if PINN_TC_COALESCED
-      {
-        const int i = lane & 3, kh = lane >> 4;
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          // 4x4 transpose across the 4 lanes of a group: lane i ends with row 4 rc + i of neurons 4 kh .. 4 kh + 3
-          const float4 a = v[it];
-          const float2 s1 = (i & 2) ? make_float2(a.x, a.y) : make_float2(a.z, a.w);
-          const float r1x = __shfl_xor_sync(0xffffffffu, s1.x, 2), r1y = __shfl_xor_sync(0xffffffffu, s1.y, 2);
-          const float4 c = (i & 2) ? make_float4(r1x, r1y, a.z, a.w) : make_float4(a.x, a.y, r1x, r1y);
-          const float2 s2 = (i & 1) ? make_float2(c.x, c.z) : make_float2(c.y, c.w);
-          const float r2x = __shfl_xor_sync(0xffffffffu, s2.x, 1), r2y = __shfl_xor_sync(0xffffffffu, s2.y, 1);
-          const float4 d = (i & 1) ? make_float4(r2x, c.y, r2y, c.w) : make_float4(c.x, r2x, c.z, r2y);
-          const int L = it * 16 + warp * 4 + ((lane >> 2) & 3);
-          if (L < 2 * NRB) {
-            const int kg = L >= NRB ? 1 : 0, rc = L - kg * NRB;
-            const int n = 4 * rc + i;
-            float4 hi, lo;
-            tf32_split4(d, hi, lo);
-            const uint32_t off = (uint32_t)(n >> 3) * S::SBO + (uint32_t)(kg * 2 + kh) * 128u + (uint32_t)(n & 7) * 16u;
-            *reinterpret_cast<float4*>(dst + off) = hi;
-            *reinterpret_cast<float4*>(dst + S::HALF + off) = lo;
-          }
-        }
-      }
-#else
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int rb = rb0 + 32 * u;
@@ -398,7 +348,6 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer(const float* __rest
           }
         }
       }
-#endif
       umma::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[stage]);
@@ -419,20 +368,6 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer(const float* __rest
   } else if (warp >= kMmaWarp) {
     // ===== MMA issuer =====
     reg_dec<24>();
-#if PINN_TC_PFWARPS
-    if (warp == kMmaWarp + 1 || (MODE == 1 && warp == kMmaWarp + 2)) {
-      // ===== experiment (off): L2 prefetch warps one tile ahead of the producers, one 128-byte line per lane and
-      // instruction.  Measured SLOWER: forward 264 -> 275 us, backward 354 -> 448 us per batch -- the layer kernels are
-      // limited by the HBM system itself, not by the latency of their own loads =====
-      const float* base = warp == kMmaWarp + 1 ? act_in : act_io;
-      const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-      for (int it = 1; it < my_tiles; ++it) {
-        while (*prog + 1 < it) __nanosleep(200);
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(base + (size_t)((int)blockIdx.x + it * (int)gridDim.x) * NR * kH);
-        for (int ln = lane; ln < NR * kH * 4 / 128; ln += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (size_t)ln * 128));
-      }
-    }
-#endif
     if (warp == kMmaWarp && lane == 0) {
       mbar_wait(wbar, 0);
       const uint32_t idesc = umma::idesc_tf32(kH, NR);
@@ -588,9 +523,6 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer(const float* __rest
         }
 #pragma unroll
         for (int c = 0; c < C; ++c)
-#ifdef PINN_TC_EXP_NOSTORE  // experiment: results are computed but (practically) never written
-          if (acc[c][4 * gg] == 12345.678f)
-#endif
           *reinterpret_cast<float4*>(io + (c * (P / 4) + gg) * 32) =
               make_float4(acc[c][4 * gg], acc[c][4 * gg + 1], acc[c][4 * gg + 2], acc[c][4 * gg + 3]);
       }

@@ -168,7 +168,8 @@ def minimize_bfgs_device(pb, maxiter: int, callback: Optional[Callable[[], None]
     g, p, xt, gt, s, y, u = (torch.zeros(n, **f64) for _ in range(7))
     scal = torch.zeros(8, **f64)
     scal_host = torch.zeros(8, dtype=torch.float64, pin_memory=True)
-    dense = dense_hessian_fits(n, dev)
+    # PINN_BFGS_DENSE=0 forces the limited-memory recursion (tests; the 8x128 network takes it by itself)
+    dense = dense_hessian_fits(n, dev) and os.environ.get("PINN_BFGS_DENSE", "1") != "0"
     H = torch.empty((n, n), **f64) if dense else None
     S, Y = [], []                                  # limited-memory pairs (only when H does not fit)
     # total loss from the kernel-order term sums: phi = sum_t coef_t * (|v_t| for |mean| terms, else v_t)

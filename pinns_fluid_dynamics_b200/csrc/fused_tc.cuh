@@ -736,16 +736,31 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
       const int n_terms = (int)(sseg[4 * si_c] >> 32);
 #pragma unroll 1
       for (int t = 0; t < n_terms; ++t) {
-        const float* T = sterm + (term0 + t) * TW;
+        // the term's 24 staged words in six 16-byte loads (one shared-memory latency instead of a chain of scalar loads)
+        float T[TW];
+        {
+          const float4* T4 = reinterpret_cast<const float4*>(sterm + (term0 + t) * TW);
+#pragma unroll
+          for (int i = 0; i < TW / 4; ++i) {
+            const float4 w = T4[i];
+            T[4 * i] = w.x; T[4 * i + 1] = w.y; T[4 * i + 2] = w.z; T[4 * i + 3] = w.w;
+          }
+        }
         const int flags = __float_as_int(T[Cfg::T_FLAGS]);
         const int ck = flags & 0xff;
         const bool abs_mean = ((flags >> 8) & 0xff) != 0;
         if (TRAIN && ((flags >> 16) & 0xff) == 0) continue;
-        float r = 0.f;
+        // one partial sum per network output: three independent chains of C fused multiply-adds
+        float ro[O];
 #pragma unroll
-        for (int o = 0; o < O; ++o)
+        for (int o = 0; o < O; ++o) {
+          ro[o] = T[o * C] * J[0][o];
 #pragma unroll
-          for (int c = 0; c < C; ++c) r = fmaf(T[o * C + c], J[c][o], r);
+          for (int c = 1; c < C; ++c) ro[o] = fmaf(T[o * C + c], J[c][o], ro[o]);
+        }
+        float r = ro[0];
+#pragma unroll
+        for (int o = 1; o < O; ++o) r += ro[o];
         const float cv = T[Cfg::T_CONV];
         if constexpr (O >= 2) {
           const float ukx = ck == 0 ? J[1 + SX][0] : J[1 + SX][1];

@@ -383,6 +383,26 @@ def test_device_bfgs_round_follows_scipy_round(monkeypatch):
     assert np.linalg.norm(x_dev - x_ref) / np.linalg.norm(x_ref) < 1e-3
 
 
+def test_limited_memory_round_when_the_inverse_hessian_does_not_fit(monkeypatch):
+    """P = 116 483 (8x128) would need a 108 GB inverse Hessian: the device driver then runs the L-BFGS two-loop recursion on
+    the same line search.  Forced here on the small network: the round must decrease the loss monotonically (strong Wolfe
+    steps), stay close to the dense round over the first iterations (identical while fewer than m pairs exist only up to the
+    initial scaling), and report its algebra."""
+    def run(dense):
+        monkeypatch.setenv("PINN_BFGS_DENSE", dense)
+        data, var, model, pb = _setup("colliding_flow", SMALL["colliding_flow"])
+        t0 = pb.evaluate()[0]
+        ns.minimize(pb, "scipy", "BFGS", num_epochs=31)
+        return t0, pb.evaluate()[0], pb.last_result, list(pb.history["log"]["loss_global"])
+    t0, t_lm, res, hist = run("0")
+    assert "L-BFGS" in res.algebra and res.nit == 30
+    assert t_lm < 0.5 * t0
+    assert all(b <= a * (1 + 1e-6) for a, b in zip(hist, hist[1:]))
+    _, t_dense, res_d, _ = run("1")
+    assert "dense" in res_d.algebra
+    assert t_lm < 3.0 * t_dense and t_dense < 3.0 * t_lm     # same ballpark after 30 iterations
+
+
 def test_graph_replayed_training_steps_equal_eager_steps(monkeypatch):
     """the CUDA-graph replay of the Adam training step (single GPU) takes exactly the eager steps"""
     def run(flag):

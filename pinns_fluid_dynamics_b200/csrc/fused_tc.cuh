@@ -320,25 +320,30 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
     for (int i = (int)(bulk_bytes / 4) + tid; i < P; i += nthr) raw[i] = __ldg(params + i);
     // the launch's loss terms in a compact form (coefficients of the O x C output jets first): read once per tile and
     // thread from shared memory instead of through 15 dependent global loads per term
-    if (tid == 0) {
-      int t0 = 0;
-      for (int si = 0; si < n_segs; ++si) {
-        segt[si] = t0;
-        t0 += segs[si].n_terms;
-      }
-    }
     for (int si = tid; si < n_segs; si += nthr) {
       sseg[4 * si + 0] = (long long)(unsigned)segs[si].chunk_begin | ((long long)segs[si].n_terms << 32);
       sseg[4 * si + 1] = segs[si].n;
       sseg[4 * si + 2] = (long long)reinterpret_cast<uintptr_t>(segs[si].pts);
       sseg[4 * si + 3] = (long long)reinterpret_cast<uintptr_t>(segs[si].y_out);
     }
-    for (int si = 0; si < n_segs; ++si) {
+    __syncthreads();
+    if (tid == 0) {                            // first staged term of each segment: prefix sum over the table in shared memory
       int t0 = 0;
-      for (int sj = 0; sj < si; ++sj) t0 += __ldg(&segs[sj].n_terms);
-      const int nt = __ldg(&segs[si].n_terms);
-      for (int idx = tid; idx < nt * TW; idx += nthr) {
-        const int t = idx / TW, k = idx % TW;
+      for (int si = 0; si < n_segs; ++si) {
+        segt[si] = t0;
+        t0 += (int)(sseg[4 * si] >> 32);
+      }
+      tslot[1] = (uint32_t)t0;                 // terms of THIS launch (n_terms_total counts the whole plan)
+    }
+    __syncthreads();
+    {
+      // one flat pass over (term, word): every thread issues its global loads at once instead of one round per segment
+      const int launch_terms = (int)tslot[1];
+      for (int idx = tid; idx < launch_terms * TW; idx += nthr) {
+        const int gt = idx / TW, k = idx % TW;
+        int si = 0;
+        while (si + 1 < n_segs && gt >= segt[si + 1]) ++si;
+        const int t0 = segt[si], t = gt - t0;
         const TermDev* T = segs[si].terms + t;
         float val = 0.f;
         if (k < O * C) val = T->coef[k / C][k % C];

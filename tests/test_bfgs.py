@@ -46,3 +46,42 @@ def test_quadratic_matches_scipy_including_inverse_hessian():
     assert np.allclose(res.x, np.linalg.solve(A, b), atol=1e-8)
     assert res.nit == ref.nit
     assert np.allclose(res.hess_inv.numpy(), ref.hess_inv, rtol=1e-6, atol=1e-9)
+
+
+# ---- the More-Thuente search on its own ---------------------------------------------------------------------------------
+
+def _wolfe_ok(phi, a, f0, g0, c1=1e-4, c2=0.9):
+    f, g = phi(a)
+    return f <= f0 + c1 * a * g0 and abs(g) <= c2 * abs(g0)
+
+
+@pytest.mark.parametrize("alpha1", [1e-3, 0.1, 1.0, 10.0, 1e3])
+def test_more_thuente_returns_strong_wolfe_steps(alpha1):
+    """functions 1-3 of the More-Thuente paper (table 1-3 there) from starting steps over six decades"""
+    from pinns_fluid_dynamics_b200.linesearch import more_thuente
+    b = 2.0
+    f1 = lambda a: (-a / (a * a + b), (a * a - b) / (a * a + b) ** 2)
+    b2 = 0.004
+    f2 = lambda a: ((a + b2) ** 5 - 2 * (a + b2) ** 4, 5 * (a + b2) ** 4 - 8 * (a + b2) ** 3)
+    for phi in (f1, f2):
+        f0, g0 = phi(0.0)
+        assert g0 < 0
+        a, fa, ga = more_thuente(phi, f0, g0, alpha1, ftol=1e-4, gtol=0.9)
+        assert a is not None and a > 0
+        assert _wolfe_ok(phi, a, f0, g0)
+        assert (fa, ga) == phi(a)
+
+
+def test_more_thuente_rejects_ascent_directions_and_counts_evaluations():
+    from pinns_fluid_dynamics_b200.linesearch import first_step, more_thuente
+    calls = []
+
+    def phi(a):
+        calls.append(a)
+        return (a - 1.0) ** 2, 2.0 * (a - 1.0)
+    assert more_thuente(phi, 1.0, +2.0, 1.0)[0] is None and not calls          # slope >= 0: no step, no evaluation
+    a, fa, ga = more_thuente(phi, 1.0, -2.0, 1.0)
+    assert a == 1.0 and calls == [1.0]                                            # the first trial already satisfies both conditions
+    # SciPy's first trial step of a BFGS line search: min(1, 1.01 * 2 (f - f_old) / slope), 1 when that is negative
+    assert first_step(1.0, 1.5, -2.0) == pytest.approx(min(1.0, 1.01 * 2 * (1.0 - 1.5) / -2.0))
+    assert first_step(1.0, 0.5, -2.0) == 1.0 and first_step(1.0, None, -2.0) == 1.0

@@ -140,13 +140,28 @@ def cpu_reference_step_rate(config: str, steps: int, warmup: int, budget_s: floa
     except Exception:
         avail = 32 << 30
     n = full_pde
-    # measured on this image: the step is ~3x slower per point once the tape leaves the caches (200 k points), 40 KB of tape per point
-    while n > probe_n and ((steps + warmup) * t_probe * (n / probe_n) * 3.0 > budget_s or n * 40_000 > 0.5 * avail):
+    # 40 KB of tape per point; the step is up to ~3x slower per point once the tape leaves the caches (200 k points), so the
+    # probe only rules out sizes that are hopeless (3x over budget even at the probe's rate) -- the decision is then made on
+    # a MEASURED step at the candidate size, which also serves as its first warm-up step
+    while n > probe_n and ((steps + warmup) * t_probe * (n / probe_n) > 3.0 * budget_s or n * 40_000 > 0.5 * avail):
         n //= 2
     n = max(n, probe_n)
-    if n != probe_n:
-        step = _cpu_step_fn(config, n)
-    for i in range(warmup):
+    done_warm = 0
+    while True:
+        if n != probe_n:
+            step = _cpu_step_fn(config, n)
+        t0 = time.perf_counter()
+        step(1)
+        t_one = time.perf_counter() - t0
+        done_warm = 1
+        if n <= probe_n or (steps + warmup) * t_one <= budget_s:
+            break
+        n = max(n // 2, probe_n)
+        if n == probe_n:
+            step = _cpu_step_fn(config, n)
+            done_warm = 0
+            break
+    for i in range(done_warm, warmup):
         step(i + 1)
     t0 = time.perf_counter()
     for i in range(steps):
@@ -173,7 +188,7 @@ def run_reference(args):
     from pinns_fluid_dynamics_b200 import loss_tables, problems
     full = args.pde_per_gpu or problems.BASELINE_CONFIGS[args.config].get("PDE", 200)
     warm = max(args.warmup, 1)
-    value, ms, cores, sample, n = cpu_reference_step_rate(args.config, args.steps, warm, budget_s=150.0, full_pde=full)
+    value, ms, cores, sample, n = cpu_reference_step_rate(args.config, args.steps, warm, budget_s=240.0, full_pde=full)
     data = problems.build_baseline_config(args.config, seed=1, PDE=1000)
     losses, _ = loss_tables.build_loss_table(data, faithful=data.name.startswith("cavity"))
     L = len(data.hidden)

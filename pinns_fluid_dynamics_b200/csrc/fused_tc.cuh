@@ -186,17 +186,24 @@ __device__ __forceinline__ void tmem_st4u(uint32_t taddr, uint32_t a, uint32_t b
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// x = hi + lo for two values at once.  ROUND: hi rounded to tf32, half an ulp added to lo before the tensor core truncates its
-// 13 low bits (forward operands: they set the loss values).  !ROUND: the raw value serves as hi (the hardware reads its top
-// 19 bits), lo = x - trunc(x) (adjoint operands: gradients only, tolerance 1e-4; 1.5 instead of 3.5 instructions per value)
+// x = hi + lo for two values at once.  ROUND: hi and lo both rounded to nearest tf32 (the tensor core would truncate their 13
+// low bits, a one-sided error that adds up over the layers; forward operands: they set the loss values) -- 2.5 instructions per
+// value with the one-instruction conversion.  !ROUND: the raw value serves as hi (the hardware reads its top 19 bits),
+// lo = x - trunc(x) (adjoint operands: gradients only, tolerance 1e-4; 1.5 instructions per value)
+// round-to-nearest tf32 in one instruction (SASS F2FP.SATFINITE.TF32.F32; cvt.rna is an add and a mask)
+__device__ __forceinline__ uint32_t cvt_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
 template <bool ROUND>
 __device__ __forceinline__ void split2(float2 x, uint32_t& h0, uint32_t& h1, uint32_t& l0, uint32_t& l1) {
   if constexpr (ROUND) {
-    h0 = (__float_as_uint(x.x) + 0x1000u) & 0xFFFFE000u;
-    h1 = (__float_as_uint(x.y) + 0x1000u) & 0xFFFFE000u;
+    h0 = cvt_tf32(x.x);
+    h1 = cvt_tf32(x.y);
     const float2 lo = fma2(make_float2(__uint_as_float(h0), __uint_as_float(h1)), bc2(-1.0f), x);
-    l0 = __float_as_uint(lo.x) + 0x1000u;
-    l1 = __float_as_uint(lo.y) + 0x1000u;
+    l0 = cvt_tf32(lo.x);
+    l1 = cvt_tf32(lo.y);
   } else {
     h0 = __float_as_uint(x.x);
     h1 = __float_as_uint(x.y);
@@ -208,12 +215,20 @@ __device__ __forceinline__ void split2(float2 x, uint32_t& h0, uint32_t& h1, uin
 // two neighbouring neurons as bf16 pairs: p1 = (bf16(x0) | bf16(x1) << 16), p2 the same of the remainders
 __device__ __forceinline__ void bf16_pair(float2 x, uint32_t& p1, uint32_t& p2) {
   p1 = pack_bf16(x.x, x.y);
-  const float2 r = fma2(make_float2(__uint_as_float(p1 << 16), __uint_as_float(p1 & 0xFFFF0000u)), bc2(-1.0f), x);
+  // remainder x - b1 by the mixed-precision FMA (SASS FHFMA.BF16 with a half selector: p1 is not unpacked; full FP32 rate)
+  float2 r;
+  asm("{\n.reg .b16 lo, hi, m1;\nmov.b32 {lo, hi}, %2;\nmov.b16 m1, 0xBF80;\n"
+      "fma.rn.f32.bf16 %0, lo, m1, %3;\nfma.rn.f32.bf16 %1, hi, m1, %4;\n}\n"
+      : "=f"(r.x), "=f"(r.y)
+      : "r"(p1), "f"(x.x), "f"(x.y));
   p2 = pack_bf16(r.x, r.y);
 }
 __device__ __forceinline__ float2 bf16_unpair(uint32_t p1, uint32_t p2) {
-  return add2(make_float2(__uint_as_float(p1 << 16), __uint_as_float(p1 & 0xFFFF0000u)),
-              make_float2(__uint_as_float(p2 << 16), __uint_as_float(p2 & 0xFFFF0000u)));
+  float2 r;   // b1 + b2 with b1 taken by the mixed-precision add's half selector (SASS FHADD.BF16)
+  asm("{\n.reg .b16 lo, hi;\nmov.b32 {lo, hi}, %2;\nadd.rn.f32.bf16 %0, lo, %3;\nadd.rn.f32.bf16 %1, hi, %4;\n}\n"
+      : "=f"(r.x), "=f"(r.y)
+      : "r"(p1), "f"(__uint_as_float(p2 << 16)), "f"(__uint_as_float(p2 & 0xFFFF0000u)));
+  return r;
 }
 
 // sums of V per-lane values over the 32 lanes of a warp by halving exchanges: V = 8 m values v[m * n8 + t] (n8 = 0..7) end
@@ -381,9 +396,9 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
       const int l = idx / H, j = idx % H;
       sB[idx] = (l == 0) ? raw[D * H + j] : raw[Cfg::offK(l + 1) + H * H + j];
     }
-    for (int idx = tid; idx < H * 4; idx += nthr) {
-      const int j = idx >> 2, o = idx & 3;
-      sKo[idx] = (o < O) ? raw[Cfg::OFF_KO + j * O + o] : 0.f;
+    for (int idx = tid; idx < H * 4; idx += nthr) {     // K_out as neuron PAIRS: sKo[j / 2][o][j % 2] -- a thread's (j, j + 1) weights of
+      const int j = idx >> 2, o = idx & 3;              // one output are an aligned register pair of its 16-byte loads (packed FFMA2 operand)
+      sKo[(j >> 1) * 8 + o * 2 + (j & 1)] = (o < O) ? raw[Cfg::OFF_KO + j * O + o] : 0.f;
     }
     if (tid < 4) sBo[tid] = (tid < O) ? raw[Cfg::OFF_BO + tid] : 0.f;
     for (int idx = tid; idx < 2 * H * H; idx += nthr) tot[idx] = 0.f;
@@ -581,18 +596,15 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
       prepare(blockIdx.x);
       layer1();
     }
-    float sqacc[4] = {0.f, 0.f, 0.f, 0.f};     // sum r^2 of the first 4 terms of the current segment: this thread's points
+    // sum r^2 of term h of the current segment over this thread's points (the four threads of a point hold the same residuals:
+    // warp h of the quadrant keeps the sums of the terms t = h mod 4)
+    float sqacc = 0.f;
     int sq_si = si;
-    auto flush_sq = [&]() {                    // (warps 0..3) registers -> per-warp slots, when the segment changes
-      if (h == 0) {
-        const int nt = (int)(sseg[4 * sq_si] >> 32);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const float tsum = reduce_warp(sqacc[t]);
-          if (lane == 0 && t < nt) ssq[__float_as_int(sterm[(segt[sq_si] + t) * TW + Cfg::T_OUT])] += tsum;
-          sqacc[t] = 0.f;
-        }
-      }
+    auto flush_sq = [&]() {                    // register -> per-quadrant slot, when the segment changes
+      const int nt = (int)(sseg[4 * sq_si] >> 32);
+      const float tsum = reduce_warp(sqacc);
+      if (lane == 0 && h < nt) ssq[__float_as_int(sterm[(segt[sq_si] + h) * TW + Cfg::T_OUT])] += tsum;
+      sqacc = 0.f;
     };
 
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -685,13 +697,13 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
             const float2 z0 = add2(make_float2(d[0][2 * pr], d[0][2 * pr + 1]), b);
             jet2_from_a0<Cfg>(tanh2(z0), zd, zxx, zyy, a);
             const float4 k0 = *reinterpret_cast<const float4*>(sKo + j * 4), k1 = *reinterpret_cast<const float4*>(sKo + j * 4 + 4);
-            const float kv0[4] = {k0.x, k0.y, k0.z, k0.w}, kv1[4] = {k1.x, k1.y, k1.z, k1.w};
+            const float2 kv[4] = {make_float2(k0.x, k0.y), make_float2(k0.z, k0.w), make_float2(k1.x, k1.y), make_float2(k1.z, k1.w)};
 #pragma unroll
             for (int c = 0; c < C; ++c) {
               a3[c][4 * hs + 2 * pr] = a[c].x;
               a3[c][4 * hs + 2 * pr + 1] = a[c].y;
 #pragma unroll
-              for (int o = 0; o < O; ++o) Jp[c][o] = fma2(a[c], make_float2(kv0[o], kv1[o]), Jp[c][o]);
+              for (int o = 0; o < O; ++o) Jp[c][o] = fma2(a[c], kv[o], Jp[c][o]);
             }
           }
         }
@@ -739,8 +751,9 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
 #pragma unroll
         for (int o = 0; o < O; ++o) Jb[c][o] = 0.f;
       const int n_terms = (int)(sseg[4 * si_c] >> 32);
-#pragma unroll 1
-      for (int t = 0; t < n_terms; ++t) {
+      // one loss term; K = t mod 4 is static: warp h == K of the quadrant adds the residual up
+      auto term = [&](int t, auto Kc) {
+        constexpr int K = decltype(Kc)::value;
         // the term's 24 staged words in six 16-byte loads (one shared-memory latency instead of a chain of scalar loads)
         float T[TW];
         {
@@ -754,7 +767,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
         const int flags = __float_as_int(T[Cfg::T_FLAGS]);
         const int ck = flags & 0xff;
         const bool abs_mean = ((flags >> 8) & 0xff) != 0;
-        if (TRAIN && ((flags >> 16) & 0xff) == 0) continue;
+        if (TRAIN && ((flags >> 16) & 0xff) == 0) return;
         // one partial sum per network output: three independent chains of C fused multiply-adds
         float ro[O];
 #pragma unroll
@@ -776,13 +789,10 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
                                                           ((uintptr_t)__float_as_uint(T[Cfg::T_RHS + 1]) << 32));
         if (rhs != nullptr) r = fmaf(-T[Cfg::T_RHS_SCALE], __ldg(rhs + pi_c), r);
         r = valid_c ? r : 0.f;
-        if (h == 0) {                          // one of the four threads of a point adds the residual up
+        if (h == K) {                          // one of the four threads of a point adds the residual up
           const float sq = abs_mean ? r : r * r;
           if (t < 4) {
-            sqacc[0] += t == 0 ? sq : 0.f;
-            sqacc[1] += t == 1 ? sq : 0.f;
-            sqacc[2] += t == 2 ? sq : 0.f;
-            sqacc[3] += t == 3 ? sq : 0.f;
+            sqacc += sq;
           } else {
             const float tsum = reduce_warp(sq);
             if (lane == 0) ssq[__float_as_int(T[Cfg::T_OUT])] += tsum;
@@ -812,14 +822,21 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
             Jb[1 + SY][1] = fmaf(m1, J[0][1], Jb[1 + SY][1]);
           }
         }
+      };
+#pragma unroll 1
+      for (int tb = 0; tb < n_terms; tb += 4) {
+        term(tb, std::integral_constant<int, 0>{});
+        if (tb + 1 < n_terms) term(tb + 1, std::integral_constant<int, 1>{});
+        if (tb + 2 < n_terms) term(tb + 2, std::integral_constant<int, 2>{});
+        if (tb + 3 < n_terms) term(tb + 3, std::integral_constant<int, 3>{});
       }
       TC_PROF(6);
 
       if constexpr (TRAIN) {
         // ---- output layer backward + tanh-jet backward of layer 3: z-bar_3 -> operand of the adjoint GEMM + image Y ----
-        if (h == 0) {
 #pragma unroll
-          for (int o = 0; o < O; ++o) {
+        for (int o = 0; o < O; ++o) {          // b_out gradient: output o is summed by warp h == o of the quadrant
+          if (h == o) {
             const float vsum = reduce_warp(Jb[0][o]);
             if (lane == 0) sg[Cfg::SG_BO + o] += vsum;
           }
@@ -834,7 +851,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
             for (int pr = 0; pr < 2; ++pr) {
               const int n8 = 4 * hs + 2 * pr, j = j0 + 2 * pr;
               const float4 k0 = *reinterpret_cast<const float4*>(sKo + j * 4), k1 = *reinterpret_cast<const float4*>(sKo + j * 4 + 4);
-              const float kv0[4] = {k0.x, k0.y, k0.z, k0.w}, kv1[4] = {k1.x, k1.y, k1.z, k1.w};
+              const float2 kv[4] = {make_float2(k0.x, k0.y), make_float2(k0.z, k0.w), make_float2(k1.x, k1.y), make_float2(k1.z, k1.w)};
               float2 aj[C], ab[C], zb[C], zdummy[D];
 #pragma unroll
               for (int i = 0; i < D; ++i) zdummy[i] = bc2(0.f);
@@ -847,7 +864,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
                 float2 b = bc2(0.f);
 #pragma unroll
                 for (int o = 0; o < O; ++o) {
-                  b = fma2(bc2(Jb[c][o]), make_float2(kv0[o], kv1[o]), b);
+                  b = fma2(bc2(Jb[c][o]), kv[o], b);
                   pk[o] = fma2(aj[c], bc2(Jb[c][o]), pk[o]);
                 }
                 ab[c] = b;
@@ -1052,7 +1069,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
           j = r / O; off = Cfg::SG_KO + (r % O); stride = 4;
         } else {
 #pragma unroll
-          for (int w = 0; w < 4; ++w) s += sg_all[w * Cfg::SG_FLOATS + Cfg::SG_BO + (idx - Cfg::OFF_BO)];
+          for (int w = 0; w < 4; ++w) s += sg_all[(4 * (idx - Cfg::OFF_BO) + w) * Cfg::SG_FLOATS + Cfg::SG_BO + (idx - Cfg::OFF_BO)];
         }
         if (j >= 0) {
           const int hh = 2 * ((j >> 3) & 1) + ((j >> 2) & 1), n8 = 4 * (j >> 4) + (j & 3);

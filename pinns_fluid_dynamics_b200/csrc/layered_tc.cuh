@@ -317,7 +317,6 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer(const float* __rest
         const int rb = rb0 + 32 * u;
         if (rb < NRB) {
           const float4* p = reinterpret_cast<const float4*>(src + rb * 128);
-#pragma unroll
           ldg256(p, v[4 * u], v[4 * u + 1]);                             // v[4u + r] = neuron 4kb + r, rows 4rb..4rb+3
           ldg256(p + 2, v[4 * u + 2], v[4 * u + 3]);
         }

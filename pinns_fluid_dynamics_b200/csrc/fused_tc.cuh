@@ -33,6 +33,8 @@
 // Tensor-memory map (512 columns, lane = point): D_c at 32c, A_c hi at 160 + 64c, lo at 160 + 64c + 32, W at 480.
 // Shared-memory map: TcCfg.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "fused_fp32.cuh"
 
 namespace pinn {
@@ -88,9 +90,17 @@ __device__ unsigned long long g_tc_prof[160][20][16];
     if ((threadIdx.x & 31) == 0) atomicAdd(&g_tc_prof[blockIdx.x][threadIdx.x >> 5][k], (unsigned long long)(now_ - prof_t)); \
     prof_t = now_;                                                                                         \
   } while (0)
+// raw time stamps of CTA 0, tiles 2..9 of its sequence: g_tc_trace[tile][warp][event] (tools/tc_trace.py)
+__device__ long long g_tc_trace[8][20][24];
+#define TC_TRACE(seq, ev)                                                                                  \
+  do {                                                                                                     \
+    if (blockIdx.x == 0 && (seq) >= 2 && (seq) < 10 && (threadIdx.x & 31) == 0)                            \
+      g_tc_trace[(seq) - 2][threadIdx.x >> 5][ev] = clock64();                                             \
+  } while (0)
 #else
 #define TC_PROF_DECL
 #define TC_PROF(k)
+#define TC_TRACE(seq, ev)
 #endif
 
 // barriers (uint64 slots at OFF_BAR)
@@ -130,6 +140,11 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int m, int n, int a_mn, int b_
 }
 __device__ __forceinline__ void mma_tf32_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d),
+               "r"(a), "l"(b), "r"(idesc), "r"(acc)
+               : "memory");
+}
+__device__ __forceinline__ void mma_bf16_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d),
                "r"(a), "l"(b), "r"(idesc), "r"(acc)
                : "memory");
 }
@@ -184,33 +199,26 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
 __device__ __forceinline__ void tmem_st4u(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ void tmem_st2u(uint32_t taddr, uint32_t a, uint32_t b) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(a), "r"(b) : "memory");
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// x = hi + lo for two values at once.  ROUND: hi and lo both rounded to nearest tf32 (the tensor core would truncate their 13
-// low bits, a one-sided error that adds up over the layers; forward operands: they set the loss values) -- 2.5 instructions per
-// value with the one-instruction conversion.  !ROUND: the raw value serves as hi (the hardware reads its top 19 bits),
-// lo = x - trunc(x) (adjoint operands: gradients only, tolerance 1e-4; 1.5 instructions per value)
 // round-to-nearest tf32 in one instruction (SASS F2FP.SATFINITE.TF32.F32; cvt.rna is an add and a mask)
 __device__ __forceinline__ uint32_t cvt_tf32(float x) {
   uint32_t r;
   asm("cvt.rn.satfinite.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return r;
 }
-template <bool ROUND>
+// x = hi + lo for two values at once, hi and lo both rounded to nearest tf32 (the tensor core would truncate their 13 low bits, a
+// one-sided error that adds up over the layers; these operands set the loss values): 2.5 instructions per value with the
+// one-instruction conversion
 __device__ __forceinline__ void split2(float2 x, uint32_t& h0, uint32_t& h1, uint32_t& l0, uint32_t& l1) {
-  if constexpr (ROUND) {
-    h0 = cvt_tf32(x.x);
-    h1 = cvt_tf32(x.y);
-    const float2 lo = fma2(make_float2(__uint_as_float(h0), __uint_as_float(h1)), bc2(-1.0f), x);
-    l0 = cvt_tf32(lo.x);
-    l1 = cvt_tf32(lo.y);
-  } else {
-    h0 = __float_as_uint(x.x);
-    h1 = __float_as_uint(x.y);
-    const float2 lo = fma2(make_float2(__uint_as_float(h0 & 0xFFFFE000u), __uint_as_float(h1 & 0xFFFFE000u)), bc2(-1.0f), x);
-    l0 = __float_as_uint(lo.x);
-    l1 = __float_as_uint(lo.y);
-  }
+  h0 = cvt_tf32(x.x);
+  h1 = cvt_tf32(x.y);
+  const float2 lo = fma2(make_float2(__uint_as_float(h0), __uint_as_float(h1)), bc2(-1.0f), x);
+  l0 = cvt_tf32(lo.x);
+  l1 = cvt_tf32(lo.y);
 }
 // two neighbouring neurons as bf16 pairs: p1 = (bf16(x0) | bf16(x1) << 16), p2 the same of the remainders
 __device__ __forceinline__ void bf16_pair(float2 x, uint32_t& p1, uint32_t& p2) {
@@ -256,15 +264,25 @@ __device__ __forceinline__ void xreduce8(float (&v)[8 * M], int lane) {
 }
 
 // hi / lo images of a half-octet (4 neurons = 2 pairs) x C channels of this thread's row into tensor memory
-template <int C, bool ROUND>
+template <int C>
 __device__ __forceinline__ void emit_operand(const float2 (&v)[C][2], uint32_t tm_a) {
 #pragma unroll
   for (int c = 0; c < C; ++c) {
     uint32_t h[4], l[4];
-    split2<ROUND>(v[c][0], h[0], h[1], l[0], l[1]);
-    split2<ROUND>(v[c][1], h[2], h[3], l[2], l[3]);
+    split2(v[c][0], h[0], h[1], l[0], l[1]);
+    split2(v[c][1], h[2], h[3], l[2], l[3]);
     tmem_st4u(tm_a + 64u * c, h[0], h[1], h[2], h[3]);
     tmem_st4u(tm_a + 64u * c + 32u, l[0], l[1], l[2], l[3]);
+  }
+}
+// the adjoint GEMMs take the SAME bf16 pairs the weight-gradient images are made of as their operand (kind::f16, A in tensor
+// memory: a 32-bit column holds two neighbouring neurons): part b1 of channel c at columns 64c + j / 2, part b2 at 64c + 32 + j / 2
+template <int C>
+__device__ __forceinline__ void emit_pairs(const uint2 (&p1)[C], const uint2 (&p2)[C], uint32_t tm_a) {
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    tmem_st2u(tm_a + 64u * c, p1[c].x, p1[c].y);
+    tmem_st2u(tm_a + 64u * c + 32u, p2[c].x, p2[c].y);
   }
 }
 // bf16-pair images of the same values: rows (c, p), 4 neurons = 8 bytes per part
@@ -376,20 +394,24 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
     }
     if (bulk_bytes) pinn::mbar_wait(&bar[B_STAGE], 0);
     __syncthreads();
-    // K-major operand images of the 32 x 32 matrices (rows n, contraction index k: umma::tile_offset, SBO = 1024):
-    //   forward  D[p][j] = sum_k a[p][k] K_l[k][j]:  B[n = j][k]      = K_l[k][j]
-    //   adjoint  D[p][k] = sum_j z[p][j] K_l[k][j]:  B[n = k][kk = j] = K_l[k][j]
+    // K-major operand images of the 32 x 32 matrices (rows n, contraction index k):
+    //   forward  D[p][j] = sum_k a[p][k] K_l[k][j]:  B[n = j][k]      = K_l[k][j]   tf32 hi / lo (umma::tile_offset, SBO = 1024)
+    //   adjoint  D[p][k] = sum_j z[p][j] K_l[k][j]:  B[n = k][kk = j] = K_l[k][j]   bf16 pair w1 / w2 (SBO = 512)
     for (int idx = tid; idx < 2 * H * H; idx += nthr) {
       const int l = idx / (H * H), r = (idx / H) % H, c = idx % H;   // r = row of K_l (k), c = column (j)
       const float w = raw[Cfg::offK(l + 2) + r * H + c];
       const uint32_t hi = (__float_as_uint(w) + 0x1000u) & 0xFFFFE000u;
       const uint32_t lo = __float_as_uint(w - __uint_as_float(hi)) + 0x1000u;
-      const uint32_t of = umma::tile_offset(c, r, 1024) / 4, ob = umma::tile_offset(r, c, 1024) / 4;
-      float* base = wimg + l * 4096;   // 4 images of 1024 floats per layer
+      const uint32_t of = umma::tile_offset(c, r, 1024) / 4;
+      float* base = wimg + l * 4096;   // 4 image slots of 4096 bytes per layer
       base[of] = __uint_as_float(hi);
       base[1024 + of] = __uint_as_float(lo);
-      base[2048 + ob] = __uint_as_float(hi);
-      base[3072 + ob] = __uint_as_float(lo);
+      // adjoint: bf16 pair w = w1 + w2, K-major 16-bit core matrices (8 rows x 8 elements): rows n = r, contraction index kk = c
+      const uint32_t ob = (uint32_t)(r >> 3) * 512u + (uint32_t)(c >> 3) * 128u + (uint32_t)(r & 7) * 16u + (uint32_t)(c & 7) * 2u;
+      const __nv_bfloat16 w1 = __float2bfloat16_rn(w);
+      const __nv_bfloat16 w2 = __float2bfloat16_rn(w - __bfloat162float(w1));
+      *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(base + 2048) + ob) = w1;
+      *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(base + 3072) + ob) = w2;
     }
     for (int idx = tid; idx < D * H; idx += nthr) sK1[idx] = raw[idx];
     for (int idx = tid; idx < 3 * H; idx += nthr) {
@@ -426,6 +448,8 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
       bool first_gemm = true;
       TC_PROF_DECL
       // one forward / adjoint GEMM over the 5 channel tiles: image index 0..3 = (layer, direction)
+      int seq = 0;                                 // tiles this CTA has started (trace builds)
+      (void)seq;
       auto gemm = [&](int image) {
         const uint64_t wh = umma::smem_desc(smem_base + Cfg::OFF_W + image * 8192, 128, 1024);
         const uint64_t wl = umma::smem_desc(smem_base + Cfg::OFF_W + image * 8192 + 4096, 128, 1024);
@@ -442,6 +466,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
           }
           umma::fence_after_thread_sync();
           TC_PROF(1 + g);
+          TC_TRACE(seq, (image == 0 ? 0 : image == 2 ? 5 : image == 3 ? 10 : 15) + g);
           if (leader) {
 #pragma unroll
             for (int c = 0; c < C; ++c) {
@@ -457,6 +482,44 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
         if (leader) mma_commit(BAR(B_DFULL));
         __syncwarp();
         TC_PROF(5);
+        TC_TRACE(seq, (image == 0 ? 0 : image == 2 ? 5 : image == 3 ? 10 : 15) + 4);
+      };
+      // adjoint GEMM on the bf16 pairs (gradients only, tolerance 1e-4): z = b1 + b2, K = w1 + w2, three kind::f16 MMAs of K = 16
+      // per channel and half (b2 w1 + b1 w2 + b1 w1): 30 instead of 60 MMAs, and no operand split in the epilogue
+      constexpr uint32_t idesc_a = idesc_bf16(128, 32, 0, 0);
+      auto gemm_adj = [&](int image) {
+        const uint64_t w1 = umma::smem_desc(smem_base + Cfg::OFF_W + image * 8192, 128, 512);
+        const uint64_t w2 = umma::smem_desc(smem_base + Cfg::OFF_W + image * 8192 + 4096, 128, 512);
+#pragma unroll
+        for (int k2 = 0; k2 < 2; ++k2) {         // half k2 contracts over the neuron octets 2 k2, 2 k2 + 1
+#pragma unroll
+          for (int g = 2 * k2; g < 2 * k2 + 2; ++g) {
+            mbar_wait(BAR(B_AREADY + g), (ph_a >> g) & 1u);
+            ph_a ^= 1u << g;
+          }
+          if (k2 == 0) {
+            mbar_wait(BAR(B_DLOADED), ph_dl);
+            ph_dl ^= 1u;
+          }
+          umma::fence_after_thread_sync();
+          TC_PROF(1 + 2 * k2);
+          TC_TRACE(seq, (image == 3 ? 10 : 15) + 2 * k2);
+          if (leader) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              const uint32_t d = tmem + Cfg::COL_D + 32u * c;
+              const uint32_t a1 = tmem + Cfg::COL_A + 64u * c + 8u * k2, a2 = a1 + 32u;
+              mma_bf16_ts(d, a2, w1 + (uint64_t)(k2 * 16), idesc_a, k2 > 0 ? 1u : 0u);
+              mma_bf16_ts(d, a1, w2 + (uint64_t)(k2 * 16), idesc_a, 1u);
+              mma_bf16_ts(d, a1, w1 + (uint64_t)(k2 * 16), idesc_a, 1u);
+            }
+          }
+          __syncwarp();
+        }
+        if (leader) mma_commit(BAR(B_DFULL));
+        __syncwarp();
+        TC_PROF(5);
+        TC_TRACE(seq, (image == 3 ? 10 : 15) + 4);
       };
       // weight gradient of one layer: D_w[(k-octet, part, k % 8)][j] = sum_rows a[row][k] z[row][j]
       auto wgrad = [&](int a_off, int z_off) {
@@ -464,6 +527,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
         ph_img ^= 1u;
         umma::fence_after_thread_sync();
         TC_PROF(6);
+        TC_TRACE(seq, a_off == Cfg::OFF_X ? 21 : 23);
         if (leader) {
           const uint64_t ad = umma::smem_desc(smem_base + a_off, 1024, 128);          // M = 64: all 8 (octet, part) blocks of a k-block
           const uint64_t z1 = umma::smem_desc(smem_base + z_off, 1024, 256);          // N = 32: the b1 blocks
@@ -482,16 +546,18 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
         }
         __syncwarp();
         TC_PROF(7);
+        TC_TRACE(seq, a_off == Cfg::OFF_X ? 20 : 22);
       };
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         gemm(0);                                  // layer 2 forward
         gemm(2);                                  // layer 3 forward
         if constexpr (TRAIN) {
-          gemm(3);                                // layer 3 adjoint: a-bar_2 = z-bar_3 K_3^T
+          gemm_adj(3);                            // layer 3 adjoint: a-bar_2 = z-bar_3 K_3^T
           wgrad(Cfg::OFF_X, Cfg::OFF_Y);          // K-bar_3 = a_2^T z-bar_3
-          gemm(1);                                // layer 2 adjoint
+          gemm_adj(1);                            // layer 2 adjoint
           wgrad(Cfg::OFF_Y, Cfg::OFF_X);          // K-bar_2 = a_1^T z-bar_2
         }
+        ++seq;
       }
     }
   } else {
@@ -588,7 +654,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
 #pragma unroll
           for (int c = 0; c < C; ++c) v[c][pr] = a[c];
         }
-        emit_operand<C, true>(v, tm_lane + Cfg::COL_A + 8u * g + 4u * v4);
+        emit_operand<C>(v, tm_lane + Cfg::COL_A + 8u * g + 4u * v4);
         arrive_group(g);
       }
     };
@@ -607,7 +673,9 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
       sqacc = 0.f;
     };
 
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    int eseq = 0;                                // tiles this CTA has started (trace builds)
+    (void)eseq;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++eseq) {
       const int si_c = si;
       const long long pg_c = pg, pi_c = pi;
       const bool valid_c = valid;
@@ -627,6 +695,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
         ph_df ^= 1u;
         umma::fence_after_thread_sync();
         TC_PROF(1);
+        TC_TRACE(eseq, 0);
         if constexpr (TRAIN) {
           if (w_pending) {                     // K-bar_2 batch of the previous tile: drain before image X is overwritten
             drain_w(0);
@@ -655,8 +724,9 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
 #pragma unroll
             for (int c = 0; c < C; ++c) v[c][pr] = a[c];
           }
-          emit_operand<C, true>(v, tm_lane + Cfg::COL_A + 8u * g + 4u * v4);
+          emit_operand<C>(v, tm_lane + Cfg::COL_A + 8u * g + 4u * v4);
           arrive_group(g);                     // the GEMM only needs the operand: the images below are written under its MMAs
+          TC_TRACE(eseq, 1 + hs);
           if constexpr (TRAIN) {
             uint2 p1[C], p2[C];
             pack_images<C>(v, p1, p2);
@@ -665,6 +735,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
         }
       }
       TC_PROF(2);
+      TC_TRACE(eseq, 3);
 
       // ---- layer 3 + output layer ------------------------------------------------------------------------------------
       float a3[C][8];                          // a-jets of layer 3 of this thread's 8 neurons
@@ -674,6 +745,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
         ph_df ^= 1u;
         umma::fence_after_thread_sync();
         TC_PROF(4);
+        TC_TRACE(eseq, 4);
         float2 Jp[C][O];
 #pragma unroll
         for (int c = 0; c < C; ++c)
@@ -743,6 +815,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
         for (int o = 0; o < O; ++o) y[pg_c * O + o] = J[0][o];
       }
       TC_PROF(5);
+      TC_TRACE(eseq, 5);
 
       // ---- residuals, sums of squares, adjoint of the output jets (identical in the four threads of a point) ---------
       float Jb[C][O];
@@ -831,6 +904,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
         if (tb + 3 < n_terms) term(tb + 3, std::integral_constant<int, 3>{});
       }
       TC_PROF(6);
+      TC_TRACE(eseq, 6);
 
       if constexpr (TRAIN) {
         // ---- output layer backward + tanh-jet backward of layer 3: z-bar_3 -> operand of the adjoint GEMM + image Y ----
@@ -880,17 +954,19 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
 #pragma unroll
               for (int c = 0; c < C; ++c) v[c][pr] = zb[c];
             }
-            emit_operand<C, false>(v, tm_lane + Cfg::COL_A + 8u * g + 4u * v4);
-            arrive_group(g);
             {
-              uint2 p1[C], p2[C];
+              uint2 p1[C], p2[C];              // z-bar_3 as bf16 pairs: operand of the adjoint GEMM AND image Y of the weight gradient
               pack_images<C>(v, p1, p2);
+              emit_pairs<C>(p1, p2, tm_lane + Cfg::COL_A + 4u * g + 2u * v4);
+              arrive_group(g);
+              TC_TRACE(eseq, 7 + hs);
               store_images<C>(imgY + img_thr + g * 256, p1, p2);
             }
           }
           umma::fence_proxy_async_smem();      // images X (a_2) and Y (z-bar_3) -> visible to the weight-gradient MMAs
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR(B_IMG));
+          TC_TRACE(eseq, 9);
           // K_out gradient of this warp's 8 neurons: sums over its 32 points
           xreduce8<3>(gko, lane);
           if ((lane & 3) == 0) {
@@ -899,6 +975,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
           }
         }
         TC_PROF(7);
+        TC_TRACE(eseq, 10);
 
         // ---- layer 2 backward: a-bar_2 (accumulators) + a_2 (image X) -> z-bar_2 ------------------------------------
         {
@@ -914,6 +991,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
           ph_df ^= 1u;
           umma::fence_after_thread_sync();
           TC_PROF(8);
+          TC_TRACE(eseq, 11);
           uint2 zp1[2][C], zp2[2][C];          // images of z-bar_2: written once the K-bar_3 MMAs have finished reading X and Y
 #pragma unroll
           for (int hs = 0; hs < 2; ++hs) {
@@ -938,13 +1016,16 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
 #pragma unroll
               for (int c = 0; c < C; ++c) v[c][pr] = zb[c];
             }
-            emit_operand<C, false>(v, tm_lane + Cfg::COL_A + 8u * g + 4u * v4);
-            arrive_group(g);
             pack_images<C>(v, zp1[hs], zp2[hs]);
+            emit_pairs<C>(zp1[hs], zp2[hs], tm_lane + Cfg::COL_A + 4u * g + 2u * v4);
+            arrive_group(g);
+            TC_TRACE(eseq, 12 + hs);
           }
           TC_PROF(9);
+          TC_TRACE(eseq, 14);
           drain_w(1);                          // K-bar_3 batch finished: its accumulator -> totals; X and Y are free
           TC_PROF(10);
+          TC_TRACE(eseq, 15);
 #pragma unroll
           for (int hs = 0; hs < 2; ++hs) {
             const int g = 2 * hs + u, j0 = 8 * g + 4 * v4;
@@ -972,6 +1053,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
           w_pending = true;
         }
         TC_PROF(11);
+        TC_TRACE(eseq, 16);
       }
 
       // the next tile's segment and point coordinates (global loads), then its layer 1 as soon as the operand columns of
@@ -993,12 +1075,14 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
         ph_df ^= 1u;
         umma::fence_after_thread_sync();
         TC_PROF(12);
+        TC_TRACE(eseq, 17);
         float d[2][C][4];
         tmem_ld4x5(tm_lane + Cfg::COL_D + 8u * u + 4u * v4, d[0]);
         tmem_ld4x5(tm_lane + Cfg::COL_D + 8u * (2 + u) + 4u * v4, d[1]);
         arrive_dloaded();
         if (more) layer1();                    // the adjoint GEMM has released the operand columns: next tile's layer 1 -> its GEMM runs during the math below
         TC_PROF(13);
+        TC_TRACE(eseq, 18);
         float gk[8 * (D + 1)];
 #pragma unroll
         for (int hs = 0; hs < 2; ++hs) {
@@ -1031,6 +1115,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
           sg[Cfg::SG_B1 + (lane >> 2)] += gk[D];
         }
         TC_PROF(14);
+        TC_TRACE(eseq, 19);
       } else {
         (void)a3;
         if (more) layer1();

@@ -1139,4 +1139,10 @@ extern "C" int pinn_tc_profile_read(unsigned long long* host_out) {
   CUDA_TRY(cudaMemcpyToSymbol(pinn::ftc::g_tc_prof, zero, sizeof(zero)));
   return PINN_OK;
 }
+// raw clock64 stamps of CTA 0, tiles 2..9 of its sequence (tools/tc_trace.py)
+extern "C" int pinn_tc_trace_read(long long* host_out) {
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpyFromSymbol(host_out, pinn::ftc::g_tc_trace, sizeof(pinn::ftc::g_tc_trace)));
+  return PINN_OK;
+}
 #endif

@@ -309,12 +309,12 @@ def run_ours(args):
         except Exception:
             pass
     elif plan.engine == "fused_tcgen05":
-        # hidden-layer forward / adjoint GEMMs on tcgen05 kind::tf32 (3 passes per product, operands in tensor memory), weight
-        # gradient as bf16-pair kind::f16 MMAs; `peak` is the chip's 3xTF32 tensor roofline.  The kernel also needs the FMA /
+        # hidden-layer forward GEMMs on tcgen05 kind::tf32 (3 passes per product, operands in tensor memory), adjoint GEMMs and
+        # weight gradient as bf16-pair kind::f16 MMAs; `peak` is the chip's 3xTF32 tensor roofline.  The kernel also needs the FMA /
         # ALU pipes for the tanh-jet math and the operand splits: `two_pipe` holds the floors of both.
         bound, peak, peak_src = "tensor", 368.4, "fallback"
-        kernel_name = ("fused_tc_kernel<D=2,O=3,TRAIN> (tcgen05.mma kind::tf32 3-pass forward / adjoint GEMMs with TMEM operands and "
-                       "accumulators, kind::f16 bf16-pair MN-major weight-gradient MMAs, FFMA2 tanh-jet epilogue warps)")
+        kernel_name = ("fused_tc_kernel<D=2,O=3,TRAIN> (tcgen05.mma kind::tf32 3-pass forward GEMMs and kind::f16 bf16-pair adjoint GEMMs with "
+                       "TMEM operands and accumulators, kind::f16 bf16-pair MN-major weight-gradient MMAs, FFMA2 tanh-jet epilogue warps)")
         try:
             with open(os.path.join(ROOT, "profiles", "tf32_peak_r01.json")) as fh:
                 pk = json.load(fh)
@@ -331,7 +331,8 @@ def run_ours(args):
             sms = torch.cuda.get_device_properties(dev).multi_processor_count
             tiles_sm = -(-(-(-n_local_pde // 128)) // sms)             # 128-point tiles of the busiest SM
             pts_sm = tiles_sm * 128
-            t_tensor = tiles_sm * (nk["mma_tf32_per_tile"] * nk["cycles_per_mma_tf32"] + nk["mma_bf16_per_tile"] * nk["cycles_per_mma_bf16"]) / clk
+            t_tensor = tiles_sm * (nk["mma_tf32_per_tile"] * nk["cycles_per_mma_tf32"] + nk["mma_bf16_per_tile"] * nk["cycles_per_mma_bf16"] +
+                                   nk.get("mma_bf16_ts_per_tile", 0) * nk.get("cycles_per_mma_bf16_ts", 17.9)) / clk
             t_fma = pts_sm * nk["fma_pipe_warp_inst_per_point"] / 4.0 / clk
             t_issue = pts_sm * nk["warp_inst_per_point"] / 4.0 / clk
             extra = {"two_pipe": {"tensor_floor_ms": t_tensor * 1e3, "fma_floor_ms": t_fma * 1e3, "issue_floor_ms": t_issue * 1e3,

@@ -294,12 +294,23 @@ __device__ __forceinline__ void pack_images(const float2 (&v)[C][2], uint2 (&p1)
     bf16_pair(v[c][1], p1[c].y, p2[c].y);
   }
 }
+// A side of a weight-gradient batch (a_2, a_1): the 16-byte atom of a row is [b1 of 4 neurons | b2 of the same 4 neurons] -- one
+// conflict-free STS.128 per channel (the M index of the MMA is ours to order: row 8 hq + e of the accumulator = neuron 4 hq + e % 4,
+// part e / 4, hq = half-octet).  The Z side below keeps one atom per (octet, part), which the two MMAs of a k-block select by stride.
 template <int C>
-__device__ __forceinline__ void store_images(uint8_t* img_thr_g, const uint2 (&p1)[C], const uint2 (&p2)[C]) {
+__device__ __forceinline__ void store_images_a(uint8_t* img_thr_g, const uint2 (&p1)[C], const uint2 (&p2)[C]) {
+#pragma unroll
+  for (int c = 0; c < C; ++c) *reinterpret_cast<uint4*>(img_thr_g + c * 16384) = make_uint4(p1[c].x, p1[c].y, p2[c].x, p2[c].y);
+}
+// Z side (z-bar_3, z-bar_2): the two MMAs of a k-block take the b1 atoms and the b2 atoms by stride, so an atom holds one part of 8
+// neurons -- the 4 + 4 neurons this thread owns in the two halves of a phase (N index 8 h + e of the accumulator = neuron
+// 8 u + 4 v + e % 4 + 16 (e / 4) of warp h = 2 u + v): again one conflict-free STS.128 per channel and part.
+template <int C>
+__device__ __forceinline__ void store_images_z(uint8_t* img_thr_h, const uint2 (&p1)[2][C], const uint2 (&p2)[2][C]) {
 #pragma unroll
   for (int c = 0; c < C; ++c) {
-    *reinterpret_cast<uint2*>(img_thr_g + c * 16384) = p1[c];
-    *reinterpret_cast<uint2*>(img_thr_g + c * 16384 + 128) = p2[c];
+    *reinterpret_cast<uint4*>(img_thr_h + c * 16384) = make_uint4(p1[0][c].x, p1[0][c].y, p1[1][c].x, p1[1][c].y);
+    *reinterpret_cast<uint4*>(img_thr_h + c * 16384 + 128) = make_uint4(p2[0][c].x, p2[0][c].y, p2[1][c].x, p2[1][c].y);
   }
 }
 
@@ -566,7 +577,8 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
     const int q = warp & 3, h = warp >> 2, u = h >> 1, v4 = h & 1;
     const int p = 32 * q + lane;                                   // point of the tile = tensor-memory lane
     const uint32_t tm_lane = tmem + ((uint32_t)(32 * q) << 16);
-    const int img_thr = (p >> 3) * 1024 + (p & 7) * 16 + v4 * 8;   // byte offset of (row (c = 0, p), neuron octet 0, part b1, this half-octet)
+    const int img_thr_z = (p >> 3) * 1024 + (p & 7) * 16 + h * 256;    // Z-side layout: byte offset of (row (c = 0, p), atom b1 of warp h)
+    const int img_thr_a = (p >> 3) * 1024 + (p & 7) * 16 + v4 * 128;   // A-side layout: atom of half-octet 2 g + v4
     float* sg = sg_all + warp * Cfg::SG_FLOATS;
     float* ssq = ssq_all + (warp & 3) * kMaxLaunchTerms;
     uint32_t ph_df = 0, ph_wd = 0;
@@ -585,16 +597,18 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
         // the four warps of a quadrant share the drain: warp h takes columns 8h .. 8h+7 (neurons j) of the quadrant's 16 rows
         float wv[8];
         tmem_ld8(tm_lane + Cfg::COL_W + 8u * (uint32_t)h, wv);
-        // quadrant q holds rows 16q..16q+15 of the M = 64 accumulator: lanes 0-7 the b1 part of neurons 8q..8q+7, lanes 8-15 the b2 part
+        // quadrant q holds rows 16q..16q+15 of the M = 64 accumulator (A-side atom order): lanes 8a..8a+3 the b1 part of neurons
+        // 8q + 4a .. +3 (a = 0, 1), lanes 8a+4..8a+7 their b2 part
 #pragma unroll
-        for (int j = 0; j < 8; ++j) wv[j] += __shfl_down_sync(0xffffffffu, wv[j], 8);
-        if (lane < 8) {
-          float4* t4 = reinterpret_cast<float4*>(tot + li * 1024 + (8 * q + lane) * 32 + 8 * h);
+        for (int j = 0; j < 8; ++j) wv[j] += __shfl_down_sync(0xffffffffu, wv[j], 4);
+        if (lane < 16 && (lane & 4) == 0) {
+          // columns 8h..8h+7 (Z-side atom order): neurons 8u + 4v .. +3 and the same + 16
+          float4* t4 = reinterpret_cast<float4*>(tot + li * 1024 + (8 * q + 4 * (lane >> 3) + (lane & 3)) * 32 + 8 * u + 4 * v4);
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
-            float4 t = t4[j];
+            float4 t = t4[4 * j];
             t.x += wv[4 * j]; t.y += wv[4 * j + 1]; t.z += wv[4 * j + 2]; t.w += wv[4 * j + 3];
-            t4[j] = t;
+            t4[4 * j] = t;
           }
         }
         umma::fence_before_thread_sync();
@@ -730,7 +744,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
           if constexpr (TRAIN) {
             uint2 p1[C], p2[C];
             pack_images<C>(v, p1, p2);
-            store_images<C>(imgX + img_thr + g * 256, p1, p2);
+            store_images_a<C>(imgX + img_thr_a + g * 256, p1, p2);
           }
         }
       }
@@ -917,6 +931,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
         }
         {
           float gko[24];
+          uint2 zq1[2][C], zq2[2][C];            // z-bar_3 as bf16 pairs: operand of the adjoint GEMM AND image Y of the weight gradient
 #pragma unroll
           for (int hs = 0; hs < 2; ++hs) {
             const int g = 2 * hs + u, j0 = 8 * g + 4 * v4;
@@ -954,15 +969,12 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
 #pragma unroll
               for (int c = 0; c < C; ++c) v[c][pr] = zb[c];
             }
-            {
-              uint2 p1[C], p2[C];              // z-bar_3 as bf16 pairs: operand of the adjoint GEMM AND image Y of the weight gradient
-              pack_images<C>(v, p1, p2);
-              emit_pairs<C>(p1, p2, tm_lane + Cfg::COL_A + 4u * g + 2u * v4);
-              arrive_group(g);
-              TC_TRACE(eseq, 7 + hs);
-              store_images<C>(imgY + img_thr + g * 256, p1, p2);
-            }
+            pack_images<C>(v, zq1[hs], zq2[hs]);
+            emit_pairs<C>(zq1[hs], zq2[hs], tm_lane + Cfg::COL_A + 4u * g + 2u * v4);
+            arrive_group(g);
+            TC_TRACE(eseq, 7 + hs);
           }
+          store_images_z<C>(imgY + img_thr_z, zq1, zq2);
           umma::fence_proxy_async_smem();      // images X (a_2) and Y (z-bar_3) -> visible to the weight-gradient MMAs
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR(B_IMG));
@@ -984,8 +996,9 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
           for (int hs = 0; hs < 2; ++hs)
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-              q1[hs][c] = *reinterpret_cast<const uint2*>(imgX + img_thr + (2 * hs + u) * 256 + c * 16384);
-              q2[hs][c] = *reinterpret_cast<const uint2*>(imgX + img_thr + (2 * hs + u) * 256 + c * 16384 + 128);
+              const uint4 qq = *reinterpret_cast<const uint4*>(imgX + img_thr_a + (2 * hs + u) * 256 + c * 16384);
+              q1[hs][c] = make_uint2(qq.x, qq.y);
+              q2[hs][c] = make_uint2(qq.z, qq.w);
             }
           mbar_wait(BAR(B_DFULL), ph_df);
           ph_df ^= 1u;
@@ -1026,10 +1039,10 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
           drain_w(1);                          // K-bar_3 batch finished: its accumulator -> totals; X and Y are free
           TC_PROF(10);
           TC_TRACE(eseq, 15);
+          store_images_z<C>(imgX + img_thr_z, zp1, zp2);
 #pragma unroll
           for (int hs = 0; hs < 2; ++hs) {
             const int g = 2 * hs + u, j0 = 8 * g + 4 * v4;
-            store_images<C>(imgX + img_thr + g * 256, zp1[hs], zp2[hs]);
             // a_1 jets re-materialised from tanh(z1) into image Y (left operand of the K-bar_2 MMAs)
             float2 v[C][2];
 #pragma unroll
@@ -1045,7 +1058,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
             }
             uint2 p1[C], p2[C];
             pack_images<C>(v, p1, p2);
-            store_images<C>(imgY + img_thr + g * 256, p1, p2);
+            store_images_a<C>(imgY + img_thr_a + g * 256, p1, p2);
           }
           umma::fence_proxy_async_smem();
           __syncwarp();

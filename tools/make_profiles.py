@@ -43,7 +43,7 @@ opmix = run([sys.executable, os.path.join(root, "tools", "ncu_opmix.py"), rep, "
 lines = run([sys.executable, os.path.join(root, "tools", "ncu_lines.py"), rep, KERNEL, "fused_tc.cuh", "45"])
 
 # MMAs per 128-point tile from the SASS page: UTCHMMA with a shared-memory A descriptor (gdesc) = bf16 weight gradient, with a
-# tensor-memory A operand (tmem) = tf32 forward / adjoint GEMMs
+# tensor-memory A operand (tmem) = tf32 forward GEMMs and bf16-pair adjoint GEMMs
 src = list(csv.reader(io.StringIO(run(["ncu", "-i", rep, "--page", "source", "--csv"]))))
 sh = src[1]
 ix = {h: i for i, h in enumerate(sh)}
@@ -77,9 +77,14 @@ out = {
     "dram_bytes_per_point": dram / n_points,
     "warp_inst_per_point": inst / n_points,
     "fma_pipe_warp_inst_per_point": pipe["fma"] * (inst / max(pipe["all"], 1)) / n_points,
-    "mma_tf32_per_tile": round(n_ts / tiles),
+    # tensor-memory-operand MMAs: 2 forward GEMMs x 60 kind::tf32 + 2 adjoint GEMMs x 30 kind::f16 (bf16 pairs) per tile -- SASS prints both as
+    # UTCHMMA tmem[..], the kind sits in the instruction descriptor; shared-memory-operand MMAs: the bf16-pair weight gradient
+    "mma_ts_per_tile": round(n_ts / tiles),
+    "mma_tf32_per_tile": round(n_ts / tiles * 120 / 180),
+    "mma_bf16_ts_per_tile": round(n_ts / tiles * 60 / 180),
     "mma_bf16_per_tile": round(n_ss / tiles),
     "cycles_per_mma_tf32": 17.9,
+    "cycles_per_mma_bf16_ts": 17.9,        # same M = 128, N = 32 tile and operand source as the tf32 form: taken at its pacing floor
     "cycles_per_mma_bf16": 43.7,
     "tensor_pipe_active_pct": val("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", None),
     "fma_pipe_active_pct": val("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", None),

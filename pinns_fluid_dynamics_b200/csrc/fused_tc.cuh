@@ -56,9 +56,11 @@ struct TcCfg {
   static constexpr int IMG_BYTES = C * TP * 32 * 4;               // [row = (c, p)][neuron] bf16 pairs: 81920
   static constexpr int OFF_X = 0, OFF_Y = IMG_BYTES;
   static constexpr int OFF_A1 = 2 * IMG_BYTES;                    // tanh(z1): a1[j][p] fp32
-  static constexpr int OFF_W = OFF_A1 + 32 * TP * 4;              // weight images [(l-2)][fwd|bwd][hi|lo] of 4096 bytes
-  static constexpr int OFF_TOT = OFF_W + 8 * 4096;                // weight-gradient totals [2][32][32] fp32
-  static constexpr int OFF_SMALL = OFF_TOT + 2 * 32 * 32 * 4;     // K1 [D][32] | b [3][32] | K_out [32][4] | b_out [4]
+  static constexpr int OFF_W = OFF_A1 + 32 * TP * 4;              // forward weight images [(l-2)][hi|lo] of 4096 bytes (tf32)
+  static constexpr int OFF_WB = OFF_W + 4 * 4096;                 // adjoint weight images [(l-2)][w1|w2] of 2048 bytes (bf16)
+  static constexpr int TOT_LD = 36;                               // row stride of the totals: the drain's 8 rows x 16 bytes hit 32 distinct banks
+  static constexpr int OFF_TOT = OFF_WB + 4 * 2048;               // weight-gradient totals [2][32][TOT_LD] fp32
+  static constexpr int OFF_SMALL = OFF_TOT + 2 * 32 * TOT_LD * 4; // K1 [D][32] | b [3][32] | K_out [32][4] | b_out [4]
   static constexpr int S_K1 = 0, S_B = D * 32, S_KO = S_B + 3 * 32, S_BO = S_KO + 32 * 4, SMALL_FLOATS = S_BO + 4;
   static constexpr int OFF_SG = OFF_SMALL + SMALL_FLOATS * 4;     // per epilogue warp: small-gradient accumulators of its 8 neurons
   static constexpr int SG_K1 = 0, SG_B1 = D * 8, SG_B2 = SG_B1 + 8, SG_B3 = SG_B2 + 8, SG_KO = SG_B3 + 8, SG_BO = SG_KO + 32,
@@ -390,7 +392,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
         const int t0 = segt[si], t = gt - t0;
         const TermDev* T = segs[si].terms + t;
         float val = 0.f;
-        if (k < O * C) val = T->coef[k / C][k % C];
+        if (k < O * C) val = T->coef[k % O][k / O];          // flat index c * O + o: the order of the exchanged output jets
         else if (k == Cfg::T_CONV) val = T->conv;
         else if (k == Cfg::T_RHS_SCALE) val = T->rhs_scale;
         else if (k == Cfg::T_SCALE) val = T->scale;
@@ -414,15 +416,16 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
       const uint32_t hi = (__float_as_uint(w) + 0x1000u) & 0xFFFFE000u;
       const uint32_t lo = __float_as_uint(w - __uint_as_float(hi)) + 0x1000u;
       const uint32_t of = umma::tile_offset(c, r, 1024) / 4;
-      float* base = wimg + l * 4096;   // 4 image slots of 4096 bytes per layer
+      float* base = wimg + l * 2048;   // hi | lo
       base[of] = __uint_as_float(hi);
       base[1024 + of] = __uint_as_float(lo);
       // adjoint: bf16 pair w = w1 + w2, K-major 16-bit core matrices (8 rows x 8 elements): rows n = r, contraction index kk = c
       const uint32_t ob = (uint32_t)(r >> 3) * 512u + (uint32_t)(c >> 3) * 128u + (uint32_t)(r & 7) * 16u + (uint32_t)(c & 7) * 2u;
       const __nv_bfloat16 w1 = __float2bfloat16_rn(w);
       const __nv_bfloat16 w2 = __float2bfloat16_rn(w - __bfloat162float(w1));
-      *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(base + 2048) + ob) = w1;
-      *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(base + 3072) + ob) = w2;
+      uint8_t* bb = smem + Cfg::OFF_WB + l * 4096;   // w1 | w2
+      *reinterpret_cast<__nv_bfloat16*>(bb + ob) = w1;
+      *reinterpret_cast<__nv_bfloat16*>(bb + 2048 + ob) = w2;
     }
     for (int idx = tid; idx < D * H; idx += nthr) sK1[idx] = raw[idx];
     for (int idx = tid; idx < 3 * H; idx += nthr) {
@@ -434,7 +437,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
       sKo[(j >> 1) * 8 + o * 2 + (j & 1)] = (o < O) ? raw[Cfg::OFF_KO + j * O + o] : 0.f;
     }
     if (tid < 4) sBo[tid] = (tid < O) ? raw[Cfg::OFF_BO + tid] : 0.f;
-    for (int idx = tid; idx < 2 * H * H; idx += nthr) tot[idx] = 0.f;
+    for (int idx = tid; idx < 2 * H * Cfg::TOT_LD; idx += nthr) tot[idx] = 0.f;
     for (int idx = tid; idx < Cfg::NEPI * Cfg::SG_FLOATS; idx += nthr) sg_all[idx] = 0.f;
     for (int idx = tid; idx < 4 * kMaxLaunchTerms; idx += nthr) ssq_all[idx] = 0.f;
     if (warp == Cfg::NEPI) umma::tmem_alloc<512>(tslot);
@@ -458,12 +461,12 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
       uint32_t ph_a = 0, ph_dl = 0, ph_img = 0;   // bit g of ph_a: parity of a_ready[g]
       bool first_gemm = true;
       TC_PROF_DECL
-      // one forward / adjoint GEMM over the 5 channel tiles: image index 0..3 = (layer, direction)
+      // one forward GEMM over the 5 channel tiles: image index 0 = layer 2, 2 = layer 3 (1, 3: their adjoints, gemm_adj)
       int seq = 0;                                 // tiles this CTA has started (trace builds)
       (void)seq;
       auto gemm = [&](int image) {
-        const uint64_t wh = umma::smem_desc(smem_base + Cfg::OFF_W + image * 8192, 128, 1024);
-        const uint64_t wl = umma::smem_desc(smem_base + Cfg::OFF_W + image * 8192 + 4096, 128, 1024);
+        const uint64_t wh = umma::smem_desc(smem_base + Cfg::OFF_W + (image >> 1) * 8192, 128, 1024);
+        const uint64_t wl = umma::smem_desc(smem_base + Cfg::OFF_W + (image >> 1) * 8192 + 4096, 128, 1024);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {            // k-step g contracts over neuron octet g; octets 0, 1 are ready first
           mbar_wait(BAR(B_AREADY + g), (ph_a >> g) & 1u);
@@ -499,8 +502,8 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
       // per channel and half (b2 w1 + b1 w2 + b1 w1): 30 instead of 60 MMAs, and no operand split in the epilogue
       constexpr uint32_t idesc_a = idesc_bf16(128, 32, 0, 0);
       auto gemm_adj = [&](int image) {
-        const uint64_t w1 = umma::smem_desc(smem_base + Cfg::OFF_W + image * 8192, 128, 512);
-        const uint64_t w2 = umma::smem_desc(smem_base + Cfg::OFF_W + image * 8192 + 4096, 128, 512);
+        const uint64_t w1 = umma::smem_desc(smem_base + Cfg::OFF_WB + (image >> 1) * 4096, 128, 512);
+        const uint64_t w2 = umma::smem_desc(smem_base + Cfg::OFF_WB + (image >> 1) * 4096 + 2048, 128, 512);
 #pragma unroll
         for (int k2 = 0; k2 < 2; ++k2) {         // half k2 contracts over the neuron octets 2 k2, 2 k2 + 1
 #pragma unroll
@@ -603,7 +606,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
         for (int j = 0; j < 8; ++j) wv[j] += __shfl_down_sync(0xffffffffu, wv[j], 4);
         if (lane < 16 && (lane & 4) == 0) {
           // columns 8h..8h+7 (Z-side atom order): neurons 8u + 4v .. +3 and the same + 16
-          float4* t4 = reinterpret_cast<float4*>(tot + li * 1024 + (8 * q + 4 * (lane >> 3) + (lane & 3)) * 32 + 8 * u + 4 * v4);
+          float4* t4 = reinterpret_cast<float4*>(tot + (li * 32 + 8 * q + 4 * (lane >> 3) + (lane & 3)) * Cfg::TOT_LD + 8 * u + 4 * v4);
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
             float4 t = t4[4 * j];
@@ -754,6 +757,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
       // ---- layer 3 + output layer ------------------------------------------------------------------------------------
       float a3[C][8];                          // a-jets of layer 3 of this thread's 8 neurons
       float J[C][O];
+      float2 Jv[8];                            // the same output jets as pairs of the flat index c * O + o (word 15 = 0)
       {
         mbar_wait(BAR(B_DFULL), ph_df);
         ph_df ^= 1u;
@@ -794,7 +798,9 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
           }
         }
         // the other 24 neurons live in the 3 partner warps of the quadrant (same lanes): exchange the partial output jets
-        // through tensor memory (columns of the operand region, idle between the forward and the adjoint GEMM)
+        // through tensor memory -- columns 64 h + 16 .. + 31 of the operand region: idle once the forward GEMM has finished, and not
+        // written by the bf16-pair operands of the reverse sweep (which take columns 64 c + 0..15 and 64 c + 32..47), so in the
+        // training kernel nobody has to wait for the readers; the next writer is layer 1 of the next tile, after the last adjoint GEMM
         float mine[16], part[16];
 #pragma unroll
         for (int c = 0; c < C; ++c)
@@ -802,26 +808,28 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
           for (int o = 0; o < O; ++o) mine[c * O + o] = Jp[c][o].x + Jp[c][o].y;
 #pragma unroll
         for (int i = C * O; i < 16; ++i) mine[i] = 0.f;
-        tmem_st16(tm_lane + Cfg::COL_A + 16u * h, mine);
+        tmem_st16(tm_lane + Cfg::COL_A + 64u * h + 16u, mine);
         tmem_wait_st();
         umma::fence_before_thread_sync();
         named_bar_sync(1 + q, 128);
         umma::fence_after_thread_sync();
 #pragma unroll
-        for (int c = 0; c < C; ++c)
-#pragma unroll
-          for (int o = 0; o < O; ++o) J[c][o] = (c == 0 ? sBo[o] : 0.f);
+        for (int i = 0; i < 8; ++i) Jv[i] = make_float2(2 * i < O ? sBo[(2 * i) % 4] : 0.f, 2 * i + 1 < O ? sBo[(2 * i + 1) % 4] : 0.f);
 #pragma unroll
         for (int hh = 0; hh < 4; ++hh) {       // same order in all four threads of a point: identical sums
-          tmem_ld16(tm_lane + Cfg::COL_A + 16u * hh, part);
+          tmem_ld16(tm_lane + Cfg::COL_A + 64u * hh + 16u, part);
 #pragma unroll
-          for (int c = 0; c < C; ++c)
-#pragma unroll
-            for (int o = 0; o < O; ++o) J[c][o] += part[c * O + o];
+          for (int i = 0; i < 8; ++i) Jv[i] = add2(Jv[i], make_float2(part[2 * i], part[2 * i + 1]));
         }
-        umma::fence_before_thread_sync();
-        named_bar_sync(1 + q, 128);             // everybody has read: the columns may take operand data again
-        umma::fence_after_thread_sync();
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+#pragma unroll
+          for (int o = 0; o < O; ++o) J[c][o] = ((c * O + o) & 1) ? Jv[(c * O + o) >> 1].y : Jv[(c * O + o) >> 1].x;
+        if constexpr (!TRAIN) {                 // forward only: layer 1 of the next tile follows at once and overwrites the columns
+          umma::fence_before_thread_sync();
+          named_bar_sync(1 + q, 128);
+          umma::fence_after_thread_sync();
+        }
       }
       if (h == 0 && valid_c && sseg[4 * si_c + 3] != 0) {
         float* y = reinterpret_cast<float*>((uintptr_t)sseg[4 * si_c + 3]);
@@ -832,11 +840,10 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
       TC_TRACE(eseq, 5);
 
       // ---- residuals, sums of squares, adjoint of the output jets (identical in the four threads of a point) ---------
-      float Jb[C][O];
+      float2 Jbv[8];                           // adjoint of the output jets, linear part, same pairs
+      float jcv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // convective part: J-bar[0][0], [0][1], [1+SX][0], [1+SY][0], [1+SX][1], [1+SY][1]
 #pragma unroll
-      for (int c = 0; c < C; ++c)
-#pragma unroll
-        for (int o = 0; o < O; ++o) Jb[c][o] = 0.f;
+      for (int i = 0; i < 8; ++i) Jbv[i] = make_float2(0.f, 0.f);
       const int n_terms = (int)(sseg[4 * si_c] >> 32);
       // one loss term; K = t mod 4 is static: warp h == K of the quadrant adds the residual up
       auto term = [&](int t, auto Kc) {
@@ -855,17 +862,15 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
         const int ck = flags & 0xff;
         const bool abs_mean = ((flags >> 8) & 0xff) != 0;
         if (TRAIN && ((flags >> 16) & 0xff) == 0) return;
-        // one partial sum per network output: three independent chains of C fused multiply-adds
-        float ro[O];
+        // linear part: packed dot product over the 8 pairs (two independent chains; word 15 of the jets is zero)
+        float2 ra = mul2(make_float2(T[0], T[1]), Jv[0]), rc = mul2(make_float2(T[2], T[3]), Jv[1]);
 #pragma unroll
-        for (int o = 0; o < O; ++o) {
-          ro[o] = T[o * C] * J[0][o];
-#pragma unroll
-          for (int c = 1; c < C; ++c) ro[o] = fmaf(T[o * C + c], J[c][o], ro[o]);
+        for (int i = 2; i < 8; i += 2) {
+          ra = fma2(make_float2(T[2 * i], T[2 * i + 1]), Jv[i], ra);
+          rc = fma2(make_float2(T[2 * i + 2], T[2 * i + 3]), Jv[i + 1], rc);
         }
-        float r = ro[0];
-#pragma unroll
-        for (int o = 1; o < O; ++o) r += ro[o];
+        ra = add2(ra, rc);
+        float r = ra.x + ra.y;
         const float cv = T[Cfg::T_CONV];
         if constexpr (O >= 2) {
           const float ukx = ck == 0 ? J[1 + SX][0] : J[1 + SX][1];
@@ -893,20 +898,18 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
             rb = valid_c ? T[Cfg::T_SCALE] * __ldg(sgn) : 0.f;
           }
 #pragma unroll
-          for (int o = 0; o < O; ++o)
-#pragma unroll
-            for (int c = 0; c < C; ++c) Jb[c][o] = fmaf(T[o * C + c], rb, Jb[c][o]);
+          for (int i = 0; i < 8; ++i) Jbv[i] = fma2(make_float2(T[2 * i], T[2 * i + 1]), bc2(rb), Jbv[i]);
           if constexpr (O >= 2) {
             const float ukx = ck == 0 ? J[1 + SX][0] : J[1 + SX][1];
             const float uky = ck == 0 ? J[1 + SY][0] : J[1 + SY][1];
             const float m = cv * rb;
-            Jb[0][0] = fmaf(m, ukx, Jb[0][0]);
-            Jb[0][1] = fmaf(m, uky, Jb[0][1]);
+            jcv[0] = fmaf(m, ukx, jcv[0]);
+            jcv[1] = fmaf(m, uky, jcv[1]);
             const float m0 = ck == 0 ? m : 0.f, m1 = ck == 0 ? 0.f : m;
-            Jb[1 + SX][0] = fmaf(m0, J[0][0], Jb[1 + SX][0]);
-            Jb[1 + SY][0] = fmaf(m0, J[0][1], Jb[1 + SY][0]);
-            Jb[1 + SX][1] = fmaf(m1, J[0][0], Jb[1 + SX][1]);
-            Jb[1 + SY][1] = fmaf(m1, J[0][1], Jb[1 + SY][1]);
+            jcv[2] = fmaf(m0, J[0][0], jcv[2]);
+            jcv[3] = fmaf(m0, J[0][1], jcv[3]);
+            jcv[4] = fmaf(m1, J[0][0], jcv[4]);
+            jcv[5] = fmaf(m1, J[0][1], jcv[5]);
           }
         }
       };
@@ -916,6 +919,19 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
         if (tb + 1 < n_terms) term(tb + 1, std::integral_constant<int, 1>{});
         if (tb + 2 < n_terms) term(tb + 2, std::integral_constant<int, 2>{});
         if (tb + 3 < n_terms) term(tb + 3, std::integral_constant<int, 3>{});
+      }
+      float Jb[C][O];
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+#pragma unroll
+        for (int o = 0; o < O; ++o) Jb[c][o] = ((c * O + o) & 1) ? Jbv[(c * O + o) >> 1].y : Jbv[(c * O + o) >> 1].x;
+      if constexpr (O >= 2) {
+        Jb[0][0] += jcv[0];
+        Jb[0][1] += jcv[1];
+        Jb[1 + SX][0] += jcv[2];
+        Jb[1 + SY][0] += jcv[3];
+        Jb[1 + SX][1] += jcv[4];
+        Jb[1 + SY][1] += jcv[5];
       }
       TC_PROF(6);
       TC_TRACE(eseq, 6);
@@ -1160,7 +1176,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
         else if (idx < Cfg::OFF_KO) {
           const int r = idx - Cfg::offK(2);
           const int l = r / (H * H + H), qq = r % (H * H + H);
-          if (qq < H * H) s = tot[l * 1024 + qq];
+          if (qq < H * H) s = tot[(l * 32 + qq / H) * Cfg::TOT_LD + qq % H];
           else { j = qq - H * H; off = l == 0 ? Cfg::SG_B2 : Cfg::SG_B3; }
         } else if (idx < Cfg::OFF_BO) {
           const int r = idx - Cfg::OFF_KO;

@@ -13,24 +13,33 @@
 //     neuron octets 0, 1 (k-steps 0, 1 of the next GEMM) are complete after the first half of an epilogue phase.
 //     Warp 16 issues the MMAs (whole warp in the loop, one lane by elect.sync: bare back-to-back UTCHMMA, 18 cycles each);
 //     warps 17-19 only fill its warp group (setmaxnreg moves their registers to the epilogue warps: 112 each).
-//   * forward / input-adjoint GEMM of a hidden layer: per channel c an M = 128 (points) x N = 32 (neurons) x K = 32 tile,
-//     kind::tf32 with the 3-pass split x = hi + lo (lo*W_hi + hi*W_lo + hi*W_hi), FP32 accumulators in TENSOR MEMORY
-//     (columns 32c..), the activation operand ALSO in tensor memory (TS form: the epilogue threads write the hi / lo images of
-//     their own row with tcgen05.st -- no shared-memory operand traffic; from shared memory the same MMA costs 41 cycles
-//     instead of 18), weights as K-major hi / lo images in shared memory.  60 MMAs = 1075 cycles per layer and tile.
-//     The k-steps are issued as soon as the epilogue has produced the 8 neurons they contract over.
+//   * forward GEMM of a hidden layer: per channel c an M = 128 (points) x N = 32 (neurons) x K = 32 tile, kind::tf32 with the
+//     3-pass split x = hi + lo (lo*W_hi + hi*W_lo + hi*W_hi), FP32 accumulators in TENSOR MEMORY (columns 32c..), the
+//     activation operand ALSO in tensor memory (TS form: the epilogue threads write the hi / lo images of their own row with
+//     tcgen05.st -- no shared-memory operand traffic; from shared memory the same MMA costs 41 cycles instead of 18), weights
+//     as K-major hi / lo images in shared memory.  hi and lo are rounded with the one-instruction conversion
+//     cvt.rn.satfinite.tf32.f32 (SASS F2FP.TF32).  60 MMAs per layer and tile; the k-steps are issued as soon as the epilogue
+//     has produced the 8 neurons they contract over.
 //   * weight gradient K-bar_l = a_{l-1}^T z-bar_l (contraction over the 128 x C rows of the tile): kind::f16 (bf16) MMAs with
-//     BOTH operands MN-major straight from [row][neuron] images in shared memory, M = 64 = (hi | lo part) x 32 neurons,
+//     BOTH operands MN-major straight from [row][neuron] images in shared memory, M = 64 = (b1 | b2 part) x 32 neurons,
 //     N = 32, K = 16 rows per instruction.  The a-jets and z-bars are kept in shared memory ONLY as these images: a bf16
-//     PAIR per value (b1 = bf16(x), b2 = bf16(x - b1): 16 mantissa bits), 4 bytes like the FP32 value they replace; the
-//     reverse sweep reads them back as b1 + b2 (they only feed gradients, tolerance 1e-4; the forward pass -- the loss
-//     values, tolerance 1e-5 -- never sees them: it goes registers -> tensor memory).  The accumulator (tensor memory,
-//     32 columns) is drained once per tile into FP32 totals in shared memory (the tensor core truncates when it adds).
+//     PAIR per value (b1 = bf16(x), b2 = bf16(x - b1): 16 mantissa bits; remainder by the mixed-precision FHFMA.BF16), 4 bytes
+//     like the FP32 value they replace; the reverse sweep reads them back as b1 + b2 (they only feed gradients, tolerance
+//     1e-4; the forward pass -- the loss values, tolerance 1e-5 -- never sees them: it goes registers -> tensor memory).
+//     Image layout: every thread writes 16-byte atoms (STS.128, conflict-free) -- on the A side [b1 | b2] of the 4 neurons of
+//     a half-octet, on the Z side one part of the 4 + 4 neurons it owns in the two halves of a phase; the accumulator's row /
+//     column order follows and is undone in the drain.  The accumulator (tensor memory, 32 columns) is drained once per
+//     tile into FP32 totals in shared memory (the tensor core truncates when it adds).
+//   * input-adjoint GEMM a-bar_{l-1} = z-bar_l K_l^T: on the SAME bf16 pairs (kind::f16, operand in tensor memory: a 32-bit
+//     column holds two neighbouring neurons; weights as a bf16 pair w1 + w2, K-major): b2 w1 + b1 w2 + b1 w1, K = 16 per
+//     instruction, 30 MMAs per layer and tile -- gradients only, no operand split in the epilogue.
 //   * small gradients (K1, b1, b_l, K_out, b_out): per-tile multi-value warp reductions into per-warp shared-memory
 //     accumulators; at the end the CTA writes ONE workspace row, finalize_rows_kernel sums the rows in a fixed order
 //     (no atomics anywhere: bit-reproducible).
 //
-// Tensor-memory map (512 columns, lane = point): D_c at 32c, A_c hi at 160 + 64c, lo at 160 + 64c + 32, W at 480.
+// Tensor-memory map (512 columns, lane = point): D_c at 32c; forward operand A_c hi at 160 + 64c, lo at 160 + 64c + 32;
+// adjoint operand b1 at 160 + 64c + [0, 16), b2 at 160 + 64c + 32 + [0, 16); output-jet exchange of warp h at 160 + 64h + [16, 32)
+// (never written during the reverse sweep); weight-gradient accumulator at 480.
 // Shared-memory map: TcCfg.
 #pragma once
 #include <cuda_bf16.h>

@@ -84,7 +84,7 @@ out = {
     "mma_bf16_ts_per_tile": round(n_ts / tiles * 60 / 180),
     "mma_bf16_per_tile": round(n_ss / tiles),
     "cycles_per_mma_tf32": 17.9,
-    "cycles_per_mma_bf16_ts": 17.9,        # same M = 128, N = 32 tile and operand source as the tf32 form: taken at its pacing floor
+    "cycles_per_mma_bf16_ts": 17.9,        # TS bf16 K-major M128 N32 K16, profiles/tc_probes_r02.md
     "cycles_per_mma_bf16": 43.7,
     "tensor_pipe_active_pct": val("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", None),
     "fma_pipe_active_pct": val("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", None),

@@ -11,7 +11,8 @@ script's 4x1000 boundary, 100 velocity and 1 pressure fitting points).
 Printed keys (one JSON line on rank 0):
   value      whole-job pts/s with inputs resident in HBM (device-timed per step, L2 flushed between steps)
   e2e        the same through the public facade with HOST inputs: every step copies all point / target
-             arrays from pinned host memory, runs the step, and reads the per-term sums back
+             arrays from pinned host memory, runs the step, and reads the per-term sums back (the host reads step i
+             after it has enqueued step i+1, so the device never waits for the host)
   roofline   the collocation kernel against the tensor roofline of its precision mode (3xTF32: the MEASURED tcgen05 kind::tf32
              rate / 3, profiles/tf32_peak_r01.json -- MEASURED_PEAKS.json holds no TF32 figure), and, in `two_pipe`, against the
              floors of BOTH pipes it needs: the tensor pipe (MMAs issued x measured cycles per MMA) and the FMA / issue pipes
@@ -395,21 +396,28 @@ def run_ours(args):
     # ---- e2e: host-resident inputs, H2D every step, D2H of the per-term sums every step ----------
     h2d = plan.pin_host_inputs()
     T = max(1, pb.compiled.n_out_terms)
-    host_out = torch.empty(T, dtype=torch.float32, pin_memory=True)
+    host_out = [torch.empty(T, dtype=torch.float32, pin_memory=True) for _ in range(2)]
+    read_evt = [torch.cuda.Event(), torch.cuda.Event()]
     for _ in range(3):
-        plan.prefetch_inputs(); plan.commit_inputs(); s = pb.training_step(opt); host_out.copy_(s[:T], non_blocking=True); torch.cuda.synchronize()
+        plan.prefetch_inputs(); plan.commit_inputs(); s = pb.training_step(opt); host_out[0].copy_(s[:T], non_blocking=True); torch.cuda.synchronize()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.active.set()
     e0.record()
     plan.prefetch_inputs()                             # step 0: one pinned-arena copy (every point / target array of the step)
+    loss_log = 0.0
     for i in range(args.steps):
         plan.commit_inputs()                           # this step's inputs become current (device-to-device from staging)
         if i + 1 < args.steps:
             plan.prefetch_inputs()                     # the next step's inputs travel on a side stream while this step computes
         s = pb.training_step(opt)
-        host_out.copy_(s[:T], non_blocking=True)
-        torch.cuda.current_stream().synchronize()      # the caller reads the loss every step
+        host_out[i & 1].copy_(s[:T], non_blocking=True)
+        read_evt[i & 1].record()
+        if i > 0:                                      # the caller reads the loss of EVERY step, one step behind the device:
+            read_evt[(i - 1) & 1].synchronize()        # step i is already enqueued when the host waits for step i-1's sums
+            loss_log += float(host_out[(i - 1) & 1][0])
+    read_evt[(args.steps - 1) & 1].synchronize()
+    loss_log += float(host_out[(args.steps - 1) & 1][0])
     e1.record()
     barrier()
     sampler.active.clear()
@@ -496,7 +504,9 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "pts/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(T * 4),
                     "ms_per_step": ms_e2e / args.steps,
                     "pipeline": "every step's inputs are copied from pinned host memory inside the timed region; the copy of "
-                                "step i+1 runs on a side stream during step i (two pinned arenas, one device staging buffer)"},
+                                "step i+1 runs on a side stream during step i (two pinned arenas, one device staging buffer); every "
+                                "step's per-term sums are copied to pinned host memory and read by the host one step behind the "
+                                "device (step i+1 is enqueued before the host waits for step i)"},
             "gpu_launches": int(launches_per_step * args.steps),
             "roofline": {"bound": bound, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": kernel_name, "kernel_ms": k_ms,

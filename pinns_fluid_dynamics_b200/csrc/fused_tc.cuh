@@ -108,10 +108,17 @@ __device__ long long g_tc_trace[8][20][24];
     if (blockIdx.x == 0 && (seq) >= 2 && (seq) < 10 && (threadIdx.x & 31) == 0)                            \
       g_tc_trace[(seq) - 2][threadIdx.x >> 5][ev] = clock64();                                             \
   } while (0)
+// prologue / epilogue stamps of CTA 0, thread 0
+__device__ long long g_tc_stage[16];
+#define TC_STAGE(k)                                                          \
+  do {                                                                       \
+    if (blockIdx.x == 0 && threadIdx.x == 0) g_tc_stage[k] = clock64();      \
+  } while (0)
 #else
 #define TC_PROF_DECL
 #define TC_PROF(k)
 #define TC_TRACE(seq, ev)
+#define TC_STAGE(k)
 #endif
 
 // barriers (uint64 slots at OFF_BAR)
@@ -355,6 +362,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
 
   // ---- stage the parameter vector (one TMA bulk copy + tail), build the operand images, stage the terms ---------------
   {
+    TC_STAGE(0);
     float* raw = reinterpret_cast<float*>(imgX);
     const uint32_t bulk_bytes = params_aligned ? ((uint32_t)(P * 4) & ~15u) : 0u;
     if (tid == 0) {
@@ -382,6 +390,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
       sseg[4 * si + 3] = (long long)reinterpret_cast<uintptr_t>(segs[si].y_out);
     }
     __syncthreads();
+    TC_STAGE(1);
     if (tid == 0) {                            // first staged term of each segment: prefix sum over the table in shared memory
       int t0 = 0;
       for (int si = 0; si < n_segs; ++si) {
@@ -414,8 +423,10 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
         sterm[(t0 + t) * TW + k] = val;
       }
     }
+    TC_STAGE(2);
     if (bulk_bytes) pinn::mbar_wait(&bar[B_STAGE], 0);
     __syncthreads();
+    TC_STAGE(3);
     // K-major operand images of the 32 x 32 matrices (rows n, contraction index k):
     //   forward  D[p][j] = sum_k a[p][k] K_l[k][j]:  B[n = j][k]      = K_l[k][j]   tf32 hi / lo (umma::tile_offset, SBO = 1024)
     //   adjoint  D[p][k] = sum_j z[p][j] K_l[k][j]:  B[n = k][kk = j] = K_l[k][j]   bf16 pair w1 / w2 (SBO = 512)
@@ -449,11 +460,13 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
     for (int idx = tid; idx < 2 * H * Cfg::TOT_LD; idx += nthr) tot[idx] = 0.f;
     for (int idx = tid; idx < Cfg::NEPI * Cfg::SG_FLOATS; idx += nthr) sg_all[idx] = 0.f;
     for (int idx = tid; idx < 4 * kMaxLaunchTerms; idx += nthr) ssq_all[idx] = 0.f;
+    TC_STAGE(4);
     if (warp == Cfg::NEPI) umma::tmem_alloc<512>(tslot);
     umma::fence_proxy_async_smem();
     umma::fence_before_thread_sync();
     __syncthreads();
     umma::fence_after_thread_sync();
+    TC_STAGE(5);
   }
   const uint32_t tmem = *tslot;
   const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
@@ -688,6 +701,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
       prepare(blockIdx.x);
       layer1();
     }
+    TC_STAGE(6);
     // sum r^2 of term h of the current segment over this thread's points (the four threads of a point hold the same residuals:
     // warp h of the quadrant keeps the sums of the terms t = h mod 4)
     float sqacc = 0.f;
@@ -1159,6 +1173,7 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
         if (more) layer1();
       }
     }
+    TC_STAGE(7);
     flush_sq();
     if constexpr (TRAIN) {
       if (w_pending) drain_w(0);
@@ -1210,9 +1225,11 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
     }
   }
 
+  TC_STAGE(8);
   umma::fence_before_thread_sync();
   __syncthreads();
   if (warp == Cfg::NEPI) umma::tmem_dealloc<512>(tmem);
+  TC_STAGE(9);
 }
 
 }  // namespace ftc

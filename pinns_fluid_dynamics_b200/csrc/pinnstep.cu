@@ -1139,6 +1139,11 @@ extern "C" int pinn_tc_profile_read(unsigned long long* host_out) {
   CUDA_TRY(cudaMemcpyToSymbol(pinn::ftc::g_tc_prof, zero, sizeof(zero)));
   return PINN_OK;
 }
+extern "C" int pinn_tc_stage_read(long long* host_out) {
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpyFromSymbol(host_out, pinn::ftc::g_tc_stage, sizeof(pinn::ftc::g_tc_stage)));
+  return PINN_OK;
+}
 // raw clock64 stamps of CTA 0, tiles 2..9 of its sequence (tools/tc_trace.py)
 extern "C" int pinn_tc_trace_read(long long* host_out) {
   CUDA_TRY(cudaDeviceSynchronize());

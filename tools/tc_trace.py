@@ -29,6 +29,13 @@ epi = ["G2 full", "E2 arrive h0", "E2 arrive h1", "E2 end", "G3 full", "J exchan
 mma = {0: "G2 k1", 1: "G2 k2", 2: "G2 k3", 3: "G2 k4", 4: "G2 commit", 5: "G3 k1", 6: "G3 k2", 7: "G3 k3", 8: "G3 k4", 9: "G3 commit",
        10: "GB3 k1", 11: "GB3 k2", 12: "GB3 k3", 13: "GB3 k4", 14: "GB3 commit", 15: "GB2 k1", 16: "GB2 k2", 17: "GB2 k3", 18: "GB2 k4",
        19: "GB2 commit", 21: "W3 img seen", 20: "W3 issued", 23: "W2 img seen", 22: "W2 issued"}
+st = np.zeros(16, dtype=np.int64)
+lib.pinn_tc_stage_read(st.ctypes.data_as(C.POINTER(C.c_longlong)))
+names = ["kernel start", "segment table staged", "terms staged", "parameters landed (TMA)", "weight images, small tables, zeroing", "tensor memory allocated",
+         "first tile: layer 1 done", "last tile done", "CTA row written", "kernel end"]
+print("prologue / epilogue of CTA 0, thread 0 (cycles since kernel start):")
+for i, nm in enumerate(names):
+    print(f"  {nm:40s} {st[i] - st[0]:9d}")
 for t in ([int(sys.argv[2])] if len(sys.argv) > 2 else [2, 3]):
     tr = buf[t]
     t0 = tr[:16, 0].min()

@@ -217,6 +217,15 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
 __device__ __forceinline__ void tmem_st4u(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, float a) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "f"(a) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n\ttcgen05.wait::ld.sync.aligned;"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st2u(uint32_t taddr, uint32_t a, uint32_t b) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(a), "r"(b) : "memory");
 }
@@ -862,86 +871,108 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
       TC_PROF(5);
       TC_TRACE(eseq, 5);
 
-      // ---- residuals, sums of squares, adjoint of the output jets (identical in the four threads of a point) ---------
+      // ---- residuals, sums of squares, adjoint of the output jets ----------------------------------------------------------
       float2 Jbv[8];                           // adjoint of the output jets, linear part, same pairs
       float jcv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // convective part: J-bar[0][0], [0][1], [1+SX][0], [1+SY][0], [1+SX][1], [1+SY][1]
 #pragma unroll
       for (int i = 0; i < 8; ++i) Jbv[i] = make_float2(0.f, 0.f);
       const int n_terms = (int)(sseg[4 * si_c] >> 32);
-      // one loss term; K = t mod 4 is static: warp h == K of the quadrant adds the residual up
-      auto term = [&](int t, auto Kc) {
-        constexpr int K = decltype(Kc)::value;
-        // the term's 24 staged words in six 16-byte loads (one shared-memory latency instead of a chain of scalar loads)
-        float T[TW];
-        {
-          const float4* T4 = reinterpret_cast<const float4*>(sterm + (term0 + t) * TW);
+      // The four threads of a point SHARE the residual work: thread h evaluates the terms t = h (mod 4) -- residual, square and the
+      // adjoint seed r-bar_t -- the seeds of a group of four terms travel through 4 tensor-memory columns, and every thread then
+      // accumulates the adjoint of the output jets from all of them (it needs it for its own 8 neurons).
+#pragma unroll 1
+      for (int tb = 0; tb < n_terms; tb += 4) {
+        const int t = tb + h;
+        float rb = 0.f;
+        if (t < n_terms) {
+          float T[TW];
+          {
+            const float4* T4 = reinterpret_cast<const float4*>(sterm + (term0 + t) * TW);
 #pragma unroll
-          for (int i = 0; i < TW / 4; ++i) {
-            const float4 w = T4[i];
-            T[4 * i] = w.x; T[4 * i + 1] = w.y; T[4 * i + 2] = w.z; T[4 * i + 3] = w.w;
+            for (int i = 0; i < TW / 4; ++i) {
+              const float4 w = T4[i];
+              T[4 * i] = w.x; T[4 * i + 1] = w.y; T[4 * i + 2] = w.z; T[4 * i + 3] = w.w;
+            }
           }
-        }
-        const int flags = __float_as_int(T[Cfg::T_FLAGS]);
-        const int ck = flags & 0xff;
-        const bool abs_mean = ((flags >> 8) & 0xff) != 0;
-        if (TRAIN && ((flags >> 16) & 0xff) == 0) return;
-        // linear part: packed dot product over the 8 pairs (two independent chains; word 15 of the jets is zero)
-        float2 ra = mul2(make_float2(T[0], T[1]), Jv[0]), rc = mul2(make_float2(T[2], T[3]), Jv[1]);
+          const int flags = __float_as_int(T[Cfg::T_FLAGS]);
+          const int ck = flags & 0xff;
+          const bool abs_mean = ((flags >> 8) & 0xff) != 0;
+          if (!(TRAIN && ((flags >> 16) & 0xff) == 0)) {
+            float2 ra = mul2(make_float2(T[0], T[1]), Jv[0]), rc = mul2(make_float2(T[2], T[3]), Jv[1]);
 #pragma unroll
-        for (int i = 2; i < 8; i += 2) {
-          ra = fma2(make_float2(T[2 * i], T[2 * i + 1]), Jv[i], ra);
-          rc = fma2(make_float2(T[2 * i + 2], T[2 * i + 3]), Jv[i + 1], rc);
-        }
-        ra = add2(ra, rc);
-        float r = ra.x + ra.y;
-        const float cv = T[Cfg::T_CONV];
-        if constexpr (O >= 2) {
-          const float ukx = ck == 0 ? J[1 + SX][0] : J[1 + SX][1];
-          const float uky = ck == 0 ? J[1 + SY][0] : J[1 + SY][1];
-          r = fmaf(cv, fmaf(J[0][0], ukx, J[0][1] * uky), r);
-        }
-        const float* rhs = reinterpret_cast<const float*>((uintptr_t)__float_as_uint(T[Cfg::T_RHS]) |
-                                                          ((uintptr_t)__float_as_uint(T[Cfg::T_RHS + 1]) << 32));
-        if (rhs != nullptr) r = fmaf(-T[Cfg::T_RHS_SCALE], __ldg(rhs + pi_c), r);
-        r = valid_c ? r : 0.f;
-        if (h == K) {                          // one of the four threads of a point adds the residual up
-          const float sq = abs_mean ? r : r * r;
-          if (t < 4) {
-            sqacc += sq;
-          } else {
-            const float tsum = reduce_warp(sq);
-            if (lane == 0) ssq[__float_as_int(T[Cfg::T_OUT])] += tsum;
+            for (int i = 2; i < 8; i += 2) {
+              ra = fma2(make_float2(T[2 * i], T[2 * i + 1]), Jv[i], ra);
+              rc = fma2(make_float2(T[2 * i + 2], T[2 * i + 3]), Jv[i + 1], rc);
+            }
+            ra = add2(ra, rc);
+            float r = ra.x + ra.y;
+            if constexpr (O >= 2) {
+              const float ukx = ck == 0 ? J[1 + SX][0] : J[1 + SX][1];
+              const float uky = ck == 0 ? J[1 + SY][0] : J[1 + SY][1];
+              r = fmaf(T[Cfg::T_CONV], fmaf(J[0][0], ukx, J[0][1] * uky), r);
+            }
+            const float* rhs = reinterpret_cast<const float*>((uintptr_t)__float_as_uint(T[Cfg::T_RHS]) |
+                                                              ((uintptr_t)__float_as_uint(T[Cfg::T_RHS + 1]) << 32));
+            if (rhs != nullptr) r = fmaf(-T[Cfg::T_RHS_SCALE], __ldg(rhs + pi_c), r);
+            r = valid_c ? r : 0.f;
+            const float sq = abs_mean ? r : r * r;
+            if (tb == 0) {
+              sqacc += sq;
+            } else {
+              const float tsum = reduce_warp(sq);
+              if (lane == 0) ssq[__float_as_int(T[Cfg::T_OUT])] += tsum;
+            }
+            if constexpr (TRAIN) {
+              rb = T[Cfg::T_SCALE] * r;
+              if (abs_mean) {
+                const float* sgn = reinterpret_cast<const float*>((uintptr_t)__float_as_uint(T[Cfg::T_SIGN]) |
+                                                                  ((uintptr_t)__float_as_uint(T[Cfg::T_SIGN + 1]) << 32));
+                rb = valid_c ? T[Cfg::T_SCALE] * __ldg(sgn) : 0.f;
+              }
+            }
           }
         }
         if constexpr (TRAIN) {
-          float rb = T[Cfg::T_SCALE] * r;
-          if (abs_mean) {
-            const float* sgn = reinterpret_cast<const float*>((uintptr_t)__float_as_uint(T[Cfg::T_SIGN]) |
-                                                              ((uintptr_t)__float_as_uint(T[Cfg::T_SIGN + 1]) << 32));
-            rb = valid_c ? T[Cfg::T_SCALE] * __ldg(sgn) : 0.f;
-          }
+          // seeds of the group: columns 160 + 256 + 16 + 4 (group parity) + h -- free during the whole reverse sweep, and two groups
+          // apart from their next writer (the barrier of the group in between orders them)
+          const uint32_t xcol = tm_lane + Cfg::COL_A + 256u + 16u + 4u * (uint32_t)((tb >> 2) & 1);
+          tmem_st1(xcol + (uint32_t)h, rb);
+          tmem_wait_st();
+          umma::fence_before_thread_sync();
+          named_bar_sync(1 + q, 128);
+          umma::fence_after_thread_sync();
+          float rbv[4];
+          tmem_ld4(xcol, rbv);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) Jbv[i] = fma2(make_float2(T[2 * i], T[2 * i + 1]), bc2(rb), Jbv[i]);
-          if constexpr (O >= 2) {
-            const float ukx = ck == 0 ? J[1 + SX][0] : J[1 + SX][1];
-            const float uky = ck == 0 ? J[1 + SY][0] : J[1 + SY][1];
-            const float m = cv * rb;
-            jcv[0] = fmaf(m, ukx, jcv[0]);
-            jcv[1] = fmaf(m, uky, jcv[1]);
-            const float m0 = ck == 0 ? m : 0.f, m1 = ck == 0 ? 0.f : m;
-            jcv[2] = fmaf(m0, J[0][0], jcv[2]);
-            jcv[3] = fmaf(m0, J[0][1], jcv[3]);
-            jcv[4] = fmaf(m1, J[0][0], jcv[4]);
-            jcv[5] = fmaf(m1, J[0][1], jcv[5]);
+          for (int k = 0; k < 4; ++k) {
+            if (tb + k < n_terms) {
+              const float4* T4 = reinterpret_cast<const float4*>(sterm + (term0 + tb + k) * TW);
+              const float4 w0 = T4[0], w1 = T4[1], w2 = T4[2], w3 = T4[3], w4 = T4[4];
+              const float2 rb2 = bc2(rbv[k]);
+              Jbv[0] = fma2(make_float2(w0.x, w0.y), rb2, Jbv[0]);
+              Jbv[1] = fma2(make_float2(w0.z, w0.w), rb2, Jbv[1]);
+              Jbv[2] = fma2(make_float2(w1.x, w1.y), rb2, Jbv[2]);
+              Jbv[3] = fma2(make_float2(w1.z, w1.w), rb2, Jbv[3]);
+              Jbv[4] = fma2(make_float2(w2.x, w2.y), rb2, Jbv[4]);
+              Jbv[5] = fma2(make_float2(w2.z, w2.w), rb2, Jbv[5]);
+              Jbv[6] = fma2(make_float2(w3.x, w3.y), rb2, Jbv[6]);
+              Jbv[7] = fma2(make_float2(w3.z, w3.w), rb2, Jbv[7]);      // .y: conv * rb, never read
+              if constexpr (O >= 2) {
+                const int ck = __float_as_int(w4.z) & 0xff;             // words 16..19: rhs_scale, scale, flags, out
+                const float ukx = ck == 0 ? J[1 + SX][0] : J[1 + SX][1];
+                const float uky = ck == 0 ? J[1 + SY][0] : J[1 + SY][1];
+                const float m = w3.w * rbv[k];                         // word 15: conv
+                jcv[0] = fmaf(m, ukx, jcv[0]);
+                jcv[1] = fmaf(m, uky, jcv[1]);
+                const float m0 = ck == 0 ? m : 0.f, m1 = ck == 0 ? 0.f : m;
+                jcv[2] = fmaf(m0, J[0][0], jcv[2]);
+                jcv[3] = fmaf(m0, J[0][1], jcv[3]);
+                jcv[4] = fmaf(m1, J[0][0], jcv[4]);
+                jcv[5] = fmaf(m1, J[0][1], jcv[5]);
+              }
+            }
           }
         }
-      };
-#pragma unroll 1
-      for (int tb = 0; tb < n_terms; tb += 4) {
-        term(tb, std::integral_constant<int, 0>{});
-        if (tb + 1 < n_terms) term(tb + 1, std::integral_constant<int, 1>{});
-        if (tb + 2 < n_terms) term(tb + 2, std::integral_constant<int, 2>{});
-        if (tb + 3 < n_terms) term(tb + 3, std::integral_constant<int, 3>{});
       }
       float Jb[C][O];
 #pragma unroll

@@ -602,3 +602,50 @@ def test_two_nccl_ranks_match_the_unsharded_oracle():
         m = re.search(r"total rel err ([0-9.e+-]+), worst term ([0-9.e+-]+), grad rel L2 ([0-9.e+-]+)", l)
         assert m, l
         assert float(m.group(1)) < LOSS_RTOL and float(m.group(2)) < 2e-5 and float(m.group(3)) < GRAD_RTOL, l
+
+
+@pytest.mark.parametrize("n_pde", [700, 4097])
+def test_more_than_four_terms_on_one_point_set(n_pde):
+    """A point set with eight train terms (the ABI's maximum per set) and a test set with six: the fused kernels keep the first four sums of a set in registers
+    and take another path for the rest; the four threads of a point share the terms in groups of four (two groups here).  Compared term by term with the Taylor oracle."""
+    from oracle import reference_step, taylor
+    from pinns_fluid_dynamics_b200 import residuals as R
+    from pinns_fluid_dynamics_b200.api import LossMeanSquares as LMS
+    from pinns_fluid_dynamics_b200.residuals import PointSet
+    kw = dict(PDE=n_pde, BC=50, Vel=20, Pres=1, Test=333, noise_bnd=0.01, noise_fit=0.01)
+    data = problems.cavity_steady(seed=5, **kw)
+    rng = np.random.default_rng(7)
+    pde, test = PointSet(data.x_pde, "PDE"), PointSet(data.x_test, "Test")
+    nv, npr = data.norm_vel, data.norm_pre
+    tgt = [rng.normal(size=data.x_pde.shape[0]) for _ in range(3)]
+    mom = lambda k, vxx: R.momentum(pde, k, nv, npr, conv_scale=nv, visc_xx=vxx, visc_yy=-1.0)
+    losses = [LMS("mass", lambda: R.mass(pde), weight=10.0),
+              LMS("momu", lambda: mom(0, 1.0), weight=1.0),
+              LMS("momv", lambda: mom(1, 1.0), weight=1.0),
+              LMS("fit_u", lambda: R.dirichlet(pde, 0, tgt[0]), weight=0.5),
+              LMS("fit_v", lambda: R.dirichlet(pde, 1, tgt[1]), weight=2.0),
+              LMS("fit_p", lambda: R.dirichlet(pde, 2, tgt[2]), weight=0.25),
+              LMS("momu_lap", lambda: mom(0, -1.0), weight=0.1),
+              LMS("momv_lap", lambda: mom(1, -1.0), weight=0.3)]
+    ltest = [LMS(f"t{i}", lambda i=i: R.dirichlet(test, i % 3, data.sol_test[i % 3] * (1.0 + i))) for i in range(6)]
+    var = reference_step.glorot_uniform_variables(data.dim, data.hidden, data.out_dim, seed=21, bias_std=0.1)
+    model = ns.TanhMLP(data.dim, data.hidden, data.out_dim, device="cuda")
+    model.set_weights([v.numpy() for v in var])
+    pb = ns.OptimizationProblem(model.variables, losses, ltest)
+    total, values, grad = pb.evaluate()
+    theta = torch.cat([v.reshape(-1) for v in var]).numpy()
+    out = taylor.loss_and_grad(pb.compiled, theta)
+    ref_total, ref_vals, _ = assemble_losses(pb.compiled, out[pb.compiled.n_params:])
+    assert _rel(total, ref_total) < LOSS_RTOL
+    assert len(values) == 8
+    for v, rv in zip(values, ref_vals):
+        assert _term_close(v, rv)
+    g = grad.double().cpu().numpy()
+    rg = out[:pb.compiled.n_params]
+    assert np.linalg.norm(g - rg) / np.linalg.norm(rg) < GRAD_RTOL
+    _, all_vals, test_vals = pb.evaluate_all()                 # forward-only kernel: train and test terms
+    out_all = taylor.loss_and_grad(pb.compiled, theta, with_grad=False, include_test=True)
+    _, ref_all, ref_test = assemble_losses(pb.compiled, out_all[pb.compiled.n_params:])
+    assert len(test_vals) == 6
+    for v, rv in zip(list(all_vals) + list(test_vals), list(ref_all) + list(ref_test)):
+        assert _term_close(v, rv)

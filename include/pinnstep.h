@@ -168,6 +168,17 @@ int pinn_nccl_unique_id(void* id128_out);                          /* 128-byte n
 int pinn_comm_create(const void* id128, int32_t world, int32_t rank, int32_t device, void** comm_out);
 int pinn_comm_destroy(void* comm);
 int pinn_allreduce_sum(void* comm, float* buf_dev, int64_t count, void* stream);
+/* The same SUM as ONE kernel over NVLink peer memory (ranks of one node, 2 <= world <= 8; csrc/p2p.cuh): every rank stores its
+ * vector into a receive block of every peer (mapped through CUDA IPC), publishes a step flag, waits for its peers' flags and sums
+ * the `world` vectors in rank order -- bit-identical on all ranks, graph-capturable, ~3x lower latency than ncclAllReduce at 9 KB.
+ * pinn_p2p_create returns this rank's 64-byte IPC handle; the caller gathers the handles of all ranks (rank order, e.g. with a
+ * torch.distributed all_gather) and passes the world x 64 bytes to pinn_p2p_connect.  Every rank must call
+ * pinn_p2p_allreduce_sum the same number of times.  pinn_p2p_status reports waits that timed out (0 in a healthy run). */
+int pinn_p2p_create(int32_t world, int32_t rank, int32_t device, int64_t max_count, void* handle64_out, void** ctx_out);
+int pinn_p2p_connect(void* ctx, const void* handles_world_x_64);
+int pinn_p2p_allreduce_sum(void* ctx, float* buf_dev, int64_t count, void* stream);
+int pinn_p2p_status(void* ctx, int32_t* timeouts_out);
+int pinn_p2p_destroy(void* ctx);
 
 /* Optimiser helpers on the flat vectors (rows (f) rank 1 of SURVEY.md section 8) ------------ */
 /* Keras Adam: m,v update with bias correction folded in the step size, epsilon outside the sqrt

@@ -16,7 +16,8 @@ EXPORTED_SYMBOLS = (
     "pinn_version", "pinn_last_error", "pinn_plan_create", "pinn_plan_destroy", "pinn_plan_param_count",
     "pinn_plan_term_count", "pinn_plan_workspace_bytes", "pinn_plan_engine", "pinn_plan_last_launch_count",
     "pinn_plan_set_rhs", "pinn_plan_enable_timing", "pinn_plan_kernel_time_ms", "pinn_loss_and_grad", "pinn_loss", "pinn_forward", "pinn_nccl_unique_id",
-    "pinn_comm_create", "pinn_comm_destroy", "pinn_allreduce_sum", "pinn_adam_step", "pinn_adam_step_dev",
+    "pinn_comm_create", "pinn_comm_destroy", "pinn_allreduce_sum", "pinn_p2p_create", "pinn_p2p_connect", "pinn_p2p_allreduce_sum",
+    "pinn_p2p_status", "pinn_p2p_destroy", "pinn_adam_step", "pinn_adam_step_dev",
     "pinn_bfgs_identity", "pinn_bfgs_trial", "pinn_bfgs_trial_dev", "pinn_bfgs_eval", "pinn_bfgs_direction", "pinn_bfgs_accept_update",
 )
 
@@ -90,6 +91,11 @@ def load(path: Optional[str] = None) -> C.CDLL:
     lib.pinn_comm_create.argtypes = [vp, i32, i32, i32, C.POINTER(vp)]
     lib.pinn_comm_destroy.argtypes = [vp]
     lib.pinn_allreduce_sum.argtypes = [vp, vp, i64, vp]
+    lib.pinn_p2p_create.argtypes = [i32, i32, i32, i64, vp, C.POINTER(vp)]
+    lib.pinn_p2p_connect.argtypes = [vp, vp]
+    lib.pinn_p2p_allreduce_sum.argtypes = [vp, vp, i64, vp]
+    lib.pinn_p2p_status.argtypes = [vp, C.POINTER(i32)]
+    lib.pinn_p2p_destroy.argtypes = [vp]
     lib.pinn_adam_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i64, vp]
     lib.pinn_adam_step_dev.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, vp, vp]
     lib.pinn_bfgs_identity.argtypes = [vp, i64, vp]

@@ -252,6 +252,11 @@ class OptimizationProblem:
         library's own NCCL communicator (``pinn_allreduce_sum``: a plain ncclAllReduce on the current stream, which a CUDA
         graph captures as one node); ``torch.distributed`` serves CPU / gloo groups and ``PINN_OWN_NCCL=0``."""
         if self._dist is not None and self.world > 1:
+            p2p = self._p2p_ctx() if out.is_cuda else None
+            if p2p is not None and out.numel() <= self._p2p_cap:
+                stream = C.c_void_p(torch.cuda.current_stream(out.device).cuda_stream)
+                _capi.check(self.plan.lib.pinn_p2p_allreduce_sum(p2p, C.c_void_p(out.data_ptr()), out.numel(), stream), "pinn_p2p_allreduce_sum")
+                return out
             comm = self._own_comm() if out.is_cuda else None
             if comm is not None:
                 stream = C.c_void_p(torch.cuda.current_stream(out.device).cuda_stream)
@@ -259,6 +264,45 @@ class OptimizationProblem:
             else:
                 self._dist.all_reduce(out, op=self._dist.ReduceOp.SUM, group=self.group)
         return out
+
+    _p2p = None
+    _p2p_tried = False
+    _p2p_cap = 0
+
+    def _p2p_ctx(self):
+        """One-shot all-reduce over NVLink peer memory (``pinn_p2p_*``, csrc/p2p.cuh) for the ranks of ONE node: every rank's
+        receive block is mapped into its peers through CUDA IPC; the 64-byte handles travel over torch.distributed once.
+        Used when ``PINN_P2P_ALLREDUCE=1`` and every rank could map every peer; otherwise None (the NCCL path serves)."""
+        if self._p2p_tried:
+            return self._p2p
+        self._p2p_tried = True
+        if (os.environ.get("PINN_P2P_ALLREDUCE", "0") != "1" or self.group is not None or not isinstance(self.plan, CudaPlan)
+                or self.world > 8):
+            return None
+        import socket
+        lib, dev = self.plan.lib, self.flat.device
+        index = dev.index if dev.index is not None else torch.cuda.current_device()
+        cap = int(self.plan.out.numel())
+        handle = (C.c_ubyte * 64)()
+        ctx = C.c_void_p()
+        ok = lib.pinn_p2p_create(self.world, self.rank, index, cap, handle, C.byref(ctx)) == 0
+        # one node only: the host name must agree on all ranks
+        names = [None] * self.world
+        self._dist.all_gather_object(names, socket.gethostname())
+        ok = ok and len(set(names)) == 1
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+        every = torch.empty(64 * self.world, dtype=torch.uint8, device=dev)
+        self._dist.all_gather_into_tensor(every, mine)
+        if ok:
+            raw = (C.c_ubyte * (64 * self.world))(*every.cpu().tolist())
+            ok = lib.pinn_p2p_connect(ctx, raw) == 0
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        self._dist.all_reduce(flag, op=self._dist.ReduceOp.MIN)          # all ranks or none
+        if int(flag.item()) == 1:
+            self._p2p, self._p2p_cap = ctx, cap
+        elif ctx.value:
+            lib.pinn_p2p_destroy(ctx)
+        return self._p2p
 
     def _own_comm(self):
         """NCCL communicator of the default group created through the C ABI (the 128-byte unique id travels over

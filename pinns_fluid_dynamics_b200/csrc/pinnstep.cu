@@ -14,6 +14,7 @@
 
 #include "fused_fp32.cuh"
 #include "fused_tc.cuh"
+#include "p2p.cuh"
 #include "bfgs.cuh"
 #include "layered_fp32.cuh"
 #include "layered_tc.cuh"
@@ -1070,6 +1071,109 @@ extern "C" int pinn_adam_step_dev(float* params_dev, const float* grad_dev, floa
                                                                      eps, step_dev);
   bump_step_kernel<<<1, 1, 0, st>>>(step_dev);
   CUDA_TRY(cudaGetLastError());
+  return PINN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// One-shot all-reduce over NVLink peer memory (csrc/p2p.cuh): the ranks of one node map each other's receive blocks via CUDA IPC.
+// ------------------------------------------------------------------------------------------------
+struct pinn_p2p {
+  int world = 0, rank = 0, device = 0;
+  int64_t cap = 0;
+  void* block = nullptr;                 // [2][world][cap] floats, then [2][kMaxWorld] flags
+  void* opened[pinn::p2p::kMaxWorld] = {};
+  pinn::p2p::Peers peers = {};
+  uint32_t* epoch = nullptr;
+  int* status = nullptr;
+  bool connected = false;
+};
+
+static size_t p2p_data_bytes(int world, int64_t cap) { return ((size_t)2 * world * cap * sizeof(float) + 255) & ~(size_t)255; }
+
+extern "C" int pinn_p2p_create(int32_t world, int32_t rank, int32_t device, int64_t max_count, void* handle64_out, void** ctx_out) {
+  if (!handle64_out || !ctx_out || world < 2 || world > pinn::p2p::kMaxWorld || rank < 0 || rank >= world || max_count <= 0)
+    return fail(PINN_E_INVALID, "pinn_p2p_create: bad argument (2 <= world <= %d)", pinn::p2p::kMaxWorld);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  DeviceGuard on_device(device);
+  if (on_device.err != cudaSuccess) return fail(PINN_E_CUDA, "cannot switch to device %d", device);
+  pinn_p2p* c = new (std::nothrow) pinn_p2p();
+  if (!c) return fail(PINN_E_ALLOC, "host allocation");
+  c->world = world; c->rank = rank; c->device = device;
+  c->cap = (max_count + 63) & ~(int64_t)63;
+  const size_t bytes = p2p_data_bytes(world, c->cap) + 2 * pinn::p2p::kMaxWorld * sizeof(uint32_t);
+  cudaIpcMemHandle_t h;
+  if (cudaMalloc(&c->block, bytes) != cudaSuccess || cudaMemset(c->block, 0, bytes) != cudaSuccess ||
+      cudaMalloc(&c->epoch, sizeof(uint32_t)) != cudaSuccess || cudaMemset(c->epoch, 0, sizeof(uint32_t)) != cudaSuccess ||
+      cudaMalloc(&c->status, sizeof(int)) != cudaSuccess || cudaMemset(c->status, 0, sizeof(int)) != cudaSuccess ||
+      cudaIpcGetMemHandle(&h, c->block) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+    const char* e = cudaGetErrorString(cudaGetLastError());
+    if (c->block) cudaFree(c->block);
+    if (c->epoch) cudaFree(c->epoch);
+    if (c->status) cudaFree(c->status);
+    delete c;
+    return fail(PINN_E_CUDA, "pinn_p2p_create: %s", e);
+  }
+  memcpy(handle64_out, &h, sizeof(h));
+  *ctx_out = c;
+  return PINN_OK;
+}
+
+extern "C" int pinn_p2p_connect(void* ctx, const void* handles) {
+  pinn_p2p* c = (pinn_p2p*)ctx;
+  if (!c || !handles) return fail(PINN_E_INVALID, "null argument");
+  DeviceGuard on_device(c->device);
+  const size_t data_bytes = p2p_data_bytes(c->world, c->cap);
+  for (int r = 0; r < c->world; ++r) {
+    void* base = c->block;
+    if (r != c->rank) {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, (const char*)handles + (size_t)r * sizeof(h), sizeof(h));
+      cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(PINN_E_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+      }
+      c->opened[r] = base;
+    }
+    c->peers.data[r] = (float*)base;
+    c->peers.flags[r] = (uint32_t*)((char*)base + data_bytes);
+  }
+  c->connected = true;
+  return PINN_OK;
+}
+
+extern "C" int pinn_p2p_allreduce_sum(void* ctx, float* buf_dev, int64_t count, void* stream) {
+  pinn_p2p* c = (pinn_p2p*)ctx;
+  if (!c || !buf_dev || count < 0 || count > c->cap) return fail(PINN_E_INVALID, "pinn_p2p_allreduce_sum: bad argument");
+  if (!c->connected) return fail(PINN_E_INVALID, "pinn_p2p_allreduce_sum: not connected");
+  pinn::p2p::allreduce_oneshot_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(c->peers, c->world, c->rank, c->cap, buf_dev, (int)count, c->epoch,
+                                                                         c->status);
+  CUDA_TRY(cudaGetLastError());
+  return PINN_OK;
+}
+
+/* number of waits that timed out so far (0 in a healthy run); synchronises the device */
+extern "C" int pinn_p2p_status(void* ctx, int32_t* timeouts_out) {
+  pinn_p2p* c = (pinn_p2p*)ctx;
+  if (!c || !timeouts_out) return fail(PINN_E_INVALID, "null argument");
+  DeviceGuard on_device(c->device);
+  int v = 0;
+  CUDA_TRY(cudaMemcpy(&v, c->status, sizeof(int), cudaMemcpyDeviceToHost));
+  *timeouts_out = v;
+  return PINN_OK;
+}
+
+extern "C" int pinn_p2p_destroy(void* ctx) {
+  pinn_p2p* c = (pinn_p2p*)ctx;
+  if (!c) return PINN_OK;
+  DeviceGuard on_device(c->device);
+  cudaDeviceSynchronize();
+  for (int r = 0; r < c->world; ++r)
+    if (c->opened[r]) cudaIpcCloseMemHandle(c->opened[r]);
+  if (c->block) cudaFree(c->block);
+  if (c->epoch) cudaFree(c->epoch);
+  if (c->status) cudaFree(c->status);
+  delete c;
   return PINN_OK;
 }
 

@@ -35,4 +35,43 @@ for name, kw, _ in cases:
     if rank == 0:
         print(f"{name} [{pb.plan.engine}] world={world}: total rel err {abs(total-ref_total)/abs(ref_total):.2e}, worst term {worst:.2e}, "
               f"grad rel L2 {np.linalg.norm(g-rg)/np.linalg.norm(rg):.2e}", flush=True)
+
+# ---- the two all-reduce paths side by side: NCCL in the graph vs the one-shot peer-memory kernel (PINN_P2P_ALLREDUCE=1) ----------
+if os.environ.get("PINN_P2P_COMPARE", "0") == "1":
+    import ctypes as C
+    from pinns_fluid_dynamics_b200.api import Adam
+    n_pde = int(os.environ.get("PINN_P2P_COMPARE_PDE", "200000"))
+    finals, times = {}, {}
+    for path in ("nccl", "p2p"):
+        os.environ["PINN_P2P_ALLREDUCE"] = "1" if path == "p2p" else "0"
+        data = problems.cavity_steady(seed=1, PDE=n_pde, BC=1000, Vel=100, Pres=1, Test=100, noise_bnd=0.01, noise_fit=0.01)
+        model = ns.TanhMLP(data.dim, data.hidden, data.out_dim, device="cuda", seed=3)
+        losses, ltest = loss_tables.build_loss_table(data)
+        pb = ns.OptimizationProblem(model.variables, losses, ltest)
+        opt = Adam(1e-3)
+        for _ in range(10):
+            pb.training_step(opt)
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(300):
+            pb.training_step(opt)
+        e1.record(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / 300], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        times[path] = float(t.item())
+        finals[path] = pb.flat.detach().double().cpu().numpy().copy()
+        used = "p2p" if pb._p2p is not None else "nccl"
+        timeouts = C.c_int32(0)
+        if pb._p2p is not None:
+            pb.plan.lib.pinn_p2p_status(pb._p2p, C.byref(timeouts))
+        # every rank must hold the same parameters bit for bit
+        mine = pb.flat.detach().clone(); ref = mine.clone(); dist.broadcast(ref, src=0)
+        same = bool(torch.equal(mine, ref))
+        if rank == 0 or not same:
+            print(f"allreduce path requested {path}, used {used}: {times[path]*1e3:.1f} us per step ({n_pde} points per rank), "
+                  f"timeouts {timeouts.value}, ranks bit-identical: {same}", flush=True)
+    if rank == 0:
+        d = np.linalg.norm(finals["p2p"] - finals["nccl"]) / np.linalg.norm(finals["nccl"])
+        print(f"p2p vs nccl after 310 Adam steps: relative difference of the parameters {d:.2e}; "
+              f"step {times['nccl']*1e3:.1f} -> {times['p2p']*1e3:.1f} us world={world}", flush=True)
 dist.destroy_process_group()

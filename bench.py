@@ -426,6 +426,10 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_e2e = float(t.item())
     e2e_value = n_global_pde * args.steps / (ms_e2e * 1e-3)
+    if pb.allreduce_timeouts():
+        raise RuntimeError("the peer-memory all-reduce timed out: the measurement is void")
+    allreduce_path = ("one-shot peer-memory kernel (pinn_p2p_*)" if pb._p2p is not None else
+                      "ncclAllReduce (own communicator)" if getattr(pb, "_comm", None) is not None else "torch.distributed") if world > 1 else "none"
     sampler.stop()
     # every rank samples its own GPU: a weak-scaling step waits for the slowest one, so the line carries all of them
     clocks = sampler.summary()
@@ -499,7 +503,7 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (3xtf32 tensor-core products, fp32 accumulate)" if plan.engine.endswith("tf32x3") or plan.engine == "fused_tcgen05" else "f32", "data": "synthetic",
             "config": {"workload": workload_text(args.config, per_gpu, n_global_pde, data, d, H, L, O, pb.compiled.n_params, len(losses)),
-                       "engine": plan.engine, "parallelism": f"dp{world} (points sharded, NCCL all-reduce of {pb.compiled.n_params + T} floats)",
+                       "engine": plan.engine, "parallelism": f"dp{world} (points sharded, SUM all-reduce of {pb.compiled.n_params + T} floats: {allreduce_path})",
                        "l2": "256 MiB device buffer rewritten between timed steps", "optimizer": "Adam(1e-2) update inside the step"},
             "e2e": {"value": e2e_value, "unit": "pts/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(T * 4),
                     "ms_per_step": ms_e2e / args.steps,

@@ -272,12 +272,13 @@ class OptimizationProblem:
     def _p2p_ctx(self):
         """One-shot all-reduce over NVLink peer memory (``pinn_p2p_*``, csrc/p2p.cuh) for the ranks of ONE node: every rank's
         receive block is mapped into its peers through CUDA IPC; the 64-byte handles travel over torch.distributed once.
-        Used when ``PINN_P2P_ALLREDUCE=1`` and every rank could map every peer; otherwise None (the NCCL path serves)."""
+        Used for the default group of up to 8 ranks on one host when every rank could map every peer; otherwise None and the
+        NCCL path serves (also with ``PINN_P2P_ALLREDUCE=0``).  Measured on 8 B200s, 1 M points per rank: 716 -> 676 us per
+        step (profiles/scaling_r02.md)."""
         if self._p2p_tried:
             return self._p2p
         self._p2p_tried = True
-        if (os.environ.get("PINN_P2P_ALLREDUCE", "0") != "1" or self.group is not None or not isinstance(self.plan, CudaPlan)
-                or self.world > 8):
+        if (out_of_env("PINN_P2P_ALLREDUCE") or self.group is not None or not isinstance(self.plan, CudaPlan) or self.world > 8):
             return None
         import socket
         lib, dev = self.plan.lib, self.flat.device
@@ -303,6 +304,21 @@ class OptimizationProblem:
         elif ctx.value:
             lib.pinn_p2p_destroy(ctx)
         return self._p2p
+
+    def allreduce_timeouts(self) -> int:
+        """Waits of the peer-memory all-reduce that timed out (a peer died or never launched): 0 in a healthy run."""
+        if self._p2p is None:
+            return 0
+        n = C.c_int32(0)
+        _capi.check(self.plan.lib.pinn_p2p_status(self._p2p, C.byref(n)), "pinn_p2p_status")
+        return int(n.value)
+
+    def close(self) -> None:
+        """Release the peer-memory mappings (every rank, after the last step; the ranks should pass a barrier first)."""
+        if self._p2p is not None:
+            ctx, self._p2p = self._p2p, None
+            self._graph = None
+            self.plan.lib.pinn_p2p_destroy(ctx)
 
     def _own_comm(self):
         """NCCL communicator of the default group created through the C ABI (the 128-byte unique id travels over

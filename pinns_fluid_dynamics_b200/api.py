@@ -278,7 +278,8 @@ class OptimizationProblem:
         if self._p2p_tried:
             return self._p2p
         self._p2p_tried = True
-        if (out_of_env("PINN_P2P_ALLREDUCE") or self.group is not None or not isinstance(self.plan, CudaPlan) or self.world > 8):
+        if (out_of_env("PINN_P2P_ALLREDUCE") or self.group is not None or not isinstance(self.plan, CudaPlan) or self.world > 8
+                or int(self.plan.out.numel()) > 16384):      # one CTA per rank: latency-bound vectors only (8x128 has 116 k parameters)
             return None
         import socket
         lib, dev = self.plan.lib, self.flat.device

@@ -7,8 +7,8 @@
 //   3. waits until all `world` flags of its OWN block carry the step number (acquire),
 //   4. sums the `world` slots in rank order into the caller's buffer -- the same order on every rank: bit-identical results.
 // Two parities alternate: a peer can only reach step e + 2 (and overwrite parity e) after it has received this rank's
-// contribution to step e + 1, which is sent after step e has been summed.  The wait is bounded; a time-out raises a flag the
-// host can read (pinn_p2p_status) instead of hanging the GPU.
+// contribution to step e + 1, which is sent after step e has been summed.  The wait is bounded by wall-clock time (2 minutes); a time-out raises a
+// flag the host can read (pinn_p2p_status) instead of hanging the GPU.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -23,6 +23,12 @@ struct Peers {
   uint32_t* flags[kMaxWorld];    // flags of rank r: [2][kMaxWorld]
 };
 
+constexpr unsigned long long kTimeoutNs = 120ull * 1000ull * 1000ull * 1000ull;   // 2 minutes
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -51,10 +57,15 @@ allreduce_oneshot_kernel(Peers peers, int world, int rank, int64_t cap, float* _
     st_release_sys(peers.flags[tid] + par * kMaxWorld + rank, epoch);
     const uint32_t* mine = peers.flags[rank] + par * kMaxWorld + tid;
     uint32_t spins = 0;
+    unsigned long long t0 = 0;
     while (ld_acquire_sys(mine) != epoch) {
-      if (++spins > (1u << 24)) {                          // seconds: a peer died or never launched
-        atomicAdd(status, 1);
-        break;
+      if ((++spins & 1023u) == 0) {                        // wall-clock bound: ranks may legitimately be seconds apart (host work
+        const unsigned long long now = globaltimer_ns();   // between steps), but a peer that died must not hang the GPU for ever
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > kTimeoutNs) {
+          atomicAdd(status, 1);
+          break;
+        }
       }
     }
   }

@@ -581,8 +581,9 @@ def test_tensor_core_engine_200k_points_matches_taylor_oracle(monkeypatch, works
 
 
 def test_two_nccl_ranks_match_the_unsharded_oracle():
-    """N > 1 on the device: two ranks (torchrun, NCCL) evaluate their shards of every point set, one all-reduce joins
-    them, and the global loss terms and gradient must match the float64 oracle of the WHOLE problem (both engines).
+    """N > 1 on the device: two ranks (torchrun) evaluate their shards of every point set, one all-reduce joins them (peer-memory
+    kernel for the 3x32 network, NCCL for 8x128), and the global loss terms and gradient must match the float64 oracle of the
+    WHOLE problem (both engines); then the two all-reduce paths are run side by side over 310 Adam steps.
     Skipped on a single-GPU box; tests/test_distributed_gloo.py covers the same host logic on CPU."""
     import re
     import subprocess
@@ -594,14 +595,24 @@ def test_two_nccl_ranks_match_the_unsharded_oracle():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(root, "tools", "multi_gpu_check.py")]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    env = dict(os.environ, PINN_P2P_COMPARE="1", PINN_P2P_COMPARE_PDE="20000")
+    env.pop("PINN_P2P_ALLREDUCE", None)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root, env=env)
     assert res.returncode == 0, res.stderr[-2000:]
-    lines = [l for l in res.stdout.splitlines() if "world=2" in l]
+    lines = [l for l in res.stdout.splitlines() if "world=2" in l and "total rel err" in l]
     assert len(lines) == 2, res.stdout
     for l in lines:
         m = re.search(r"total rel err ([0-9.e+-]+), worst term ([0-9.e+-]+), grad rel L2 ([0-9.e+-]+)", l)
         assert m, l
         assert float(m.group(1)) < LOSS_RTOL and float(m.group(2)) < 2e-5 and float(m.group(3)) < GRAD_RTOL, l
+    # the two all-reduce paths (ncclAllReduce in the step's graph / the one-shot peer-memory kernel): both really used, no wait timed
+    # out, every rank holds bit-identical parameters after 310 Adam steps, and the two runs agree
+    paths = [l for l in res.stdout.splitlines() if l.startswith("allreduce path requested")]
+    assert len(paths) == 2, res.stdout
+    assert "requested nccl, used nccl" in paths[0] and "requested p2p, used p2p" in paths[1], paths
+    assert all("timeouts 0" in l and "bit-identical: True" in l for l in paths), paths
+    m = re.search(r"relative difference of the parameters ([0-9.e+-]+)", res.stdout)
+    assert m and float(m.group(1)) < 1e-5, res.stdout
 
 
 @pytest.mark.parametrize("n_pde", [700, 4097])

@@ -33,6 +33,8 @@
 //   * input-adjoint GEMM a-bar_{l-1} = z-bar_l K_l^T: on the SAME bf16 pairs (kind::f16, operand in tensor memory: a 32-bit
 //     column holds two neighbouring neurons; weights as a bf16 pair w1 + w2, K-major): b2 w1 + b1 w2 + b1 w1, K = 16 per
 //     instruction, 30 MMAs per layer and tile -- gradients only, no operand split in the epilogue.
+//   * residuals: the launch's loss terms sit in shared memory (24 words each); the four threads of a point share them -- thread h
+//     evaluates the terms t = h (mod 4) as packed dot products, the adjoint seeds travel through 4 tensor-memory columns.
 //   * small gradients (K1, b1, b_l, K_out, b_out): per-tile multi-value warp reductions into per-warp shared-memory
 //     accumulators; at the end the CTA writes ONE workspace row, finalize_rows_kernel sums the rows in a fixed order
 //     (no atomics anywhere: bit-reproducible).

@@ -97,11 +97,13 @@ __device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
   hi = umma::rna_tf32(x);
   lo = umma::rna_tf32(x - hi);
 }
-// activation split on the hot path: hi rounded to nearest by integer arithmetic (2 ops), lo = x - hi exact and
-// left for the tensor core to truncate.  lo's sign is independent of x's (hi is rounded, not truncated), so that
-// truncation is zero-mean: no bias, error <= 2^-22 |x|.  (cvt.rna.tf32 expands to 4 instructions on sm_100a.)
+// activation split on the hot path: hi rounded to nearest by the one-instruction conversion (SASS F2FP.SATFINITE.TF32.F32;
+// cvt.rna.tf32 expands to an add and a mask on sm_100a), lo = x - hi exact and left for the tensor core to truncate.  lo's sign
+// is independent of x's (hi is rounded, not truncated), so that truncation is zero-mean: no bias, error <= 2^-22 |x|.
 __device__ __forceinline__ void tf32_split_fast(float x, float& hi, float& lo) {
-  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+  uint32_t h;
+  asm("cvt.rn.satfinite.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  hi = __uint_as_float(h);
   lo = x - hi;
 }
 __device__ __forceinline__ void tf32_split4(const float4& v, float4& hi, float4& lo) {

@@ -168,12 +168,8 @@ __device__ __forceinline__ void mma_bf16_ts(uint32_t d, uint32_t a, uint64_t b, 
                "r"(a), "l"(b), "r"(idesc), "r"(acc)
                : "memory");
 }
-__device__ __forceinline__ void mma_bf16_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d),
-               "l"(a), "l"(b), "r"(idesc), "r"(acc)
-               : "memory");
-}
-// the same with the A operand kept in / taken from the collector buffer (two MMAs of a k-step share their A operand)
+// bf16 MMAs with both operands from shared memory; the A operand is kept in / taken from the collector buffer (the two MMAs of
+// a k-step share it)
 __device__ __forceinline__ void mma_bf16_ss_keep_a(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d),
                "l"(a), "l"(b), "r"(idesc), "r"(acc)
@@ -581,13 +577,8 @@ fused_tc_kernel(const float* __restrict__ params, const SegDev* __restrict__ seg
           const uint64_t z2 = umma::smem_desc(smem_base + z_off + 128, 1024, 256);    //         the b2 blocks
 #pragma unroll 4
           for (int ks = 0; ks < C * Cfg::TP / 16; ++ks) {
-#ifdef PINN_TC_NO_COLLECTOR
-            mma_bf16_ss(tmem + Cfg::COL_W, ad + (uint64_t)(ks * 128), z1 + (uint64_t)(ks * 128), idesc_w, ks > 0 ? 1u : 0u);
-            mma_bf16_ss(tmem + Cfg::COL_W, ad + (uint64_t)(ks * 128), z2 + (uint64_t)(ks * 128), idesc_w, 1u);
-#else
             mma_bf16_ss_keep_a(tmem + Cfg::COL_W, ad + (uint64_t)(ks * 128), z1 + (uint64_t)(ks * 128), idesc_w, ks > 0 ? 1u : 0u);
             mma_bf16_ss_reuse_a(tmem + Cfg::COL_W, ad + (uint64_t)(ks * 128), z2 + (uint64_t)(ks * 128), idesc_w, 1u);
-#endif
           }
           mma_commit(BAR(B_WDONE));
         }

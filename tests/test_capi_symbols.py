@@ -37,6 +37,18 @@ def test_library_loads_and_reports_errors_without_a_gpu():
     assert rc == -1 and b"no engine" in lib.pinn_last_error()
 
 
+def test_peer_memory_allreduce_rejects_bad_arguments_before_touching_cuda():
+    _ensure_built()
+    import ctypes as C
+    lib = _capi.load()
+    handle, ctx = (C.c_ubyte * 64)(), C.c_void_p()
+    for world, rank, count in ((1, 0, 16), (9, 0, 16), (2, 2, 16), (2, 0, 0)):      # one rank, more than 8, rank out of range, empty
+        assert lib.pinn_p2p_create(world, rank, 0, count, handle, C.byref(ctx)) == -1
+        assert b"pinn_p2p_create" in lib.pinn_last_error()
+    assert lib.pinn_p2p_allreduce_sum(None, None, 0, None) == -1
+    assert lib.pinn_p2p_destroy(None) == 0
+
+
 def test_struct_layout_matches_header():
     import ctypes as C
     # pinn_term_desc: 24 floats + conv + conv_k + rhs_scale (+4 pad) + ptr + 2 doubles + int64 + int32 (+4 pad)

@@ -256,7 +256,9 @@ def run_ours(args):
     while getattr(pb, "_graph", None) is None and pb._graph_eligible(opt) and extra < 8:
         pb.training_step(opt)
         extra += 1
-    launches_per_step = plan.last_launch_count() + 1   # + Adam kernel
+    launches_per_step = plan.last_launch_count() + 1   # + Adam kernel (it also advances the device step counter)
+    if world > 1 and getattr(pb, "_p2p", None) is not None:
+        launches_per_step += 1                         # + the one-kernel peer-memory all-reduce
     barrier()
 
     # ---- value: inputs resident in HBM, device-timed per step, L2 flushed between steps -----------

@@ -1048,17 +1048,26 @@ extern "C" int pinn_adam_step(float* params_dev, const float* grad_dev, float* m
 // graph-capturable variant: the step number lives on the device
 __global__ void adam_dev_kernel(float* __restrict__ theta, const float* __restrict__ g, float* __restrict__ m,
                                 float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
-                                const int64_t* __restrict__ step) {
+                                int64_t* __restrict__ step) {
+  // *step: number of steps taken (low word; < 2^32).  The high word is this launch's arrival counter, zero between launches: the
+  // last CTA to finish advances the step number -- no second launch for the increment.
+  unsigned* words = reinterpret_cast<unsigned*>(step);
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const double t = (double)(*step + 1);
-  const float step_size = (float)((double)lr * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t)));
-  const float gi = g[i];
-  const float mi = fmaf(b1, m[i], (1.f - b1) * gi);
-  const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
-  m[i] = mi;
-  v[i] = vi;
-  theta[i] -= step_size * mi / (sqrtf(vi) + eps);
+  const double t = (double)words[0] + 1.0;
+  if (i < n) {
+    const float step_size = (float)((double)lr * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t)));
+    const float gi = g[i];
+    const float mi = fmaf(b1, m[i], (1.f - b1) * gi);
+    const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+    m[i] = mi;
+    v[i] = vi;
+    theta[i] -= step_size * mi / (sqrtf(vi) + eps);
+  }
+  __syncthreads();                                        // every thread of this CTA has read the step number
+  if (threadIdx.x == 0 && atomicAdd(words + 1, 1u) == gridDim.x - 1) {
+    words[1] = 0u;
+    words[0] += 1u;
+  }
 }
 __global__ void bump_step_kernel(int64_t* step) { *step += 1; }
 
@@ -1069,7 +1078,8 @@ extern "C" int pinn_adam_step_dev(float* params_dev, const float* grad_dev, floa
   if (count > 0)
     adam_dev_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(params_dev, grad_dev, m_dev, v_dev, count, lr, beta1, beta2,
                                                                      eps, step_dev);
-  bump_step_kernel<<<1, 1, 0, st>>>(step_dev);
+  else
+    bump_step_kernel<<<1, 1, 0, st>>>(step_dev);
   CUDA_TRY(cudaGetLastError());
   return PINN_OK;
 }
